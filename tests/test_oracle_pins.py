@@ -1,0 +1,179 @@
+"""Pin the oracle against the reference's own known-answer tests.
+
+Each test cites the reference test it replays (paths relative to /root/reference).  They need the
+reference fixtures, so they skip on the GPU box; the committed golden vectors in tests/golden/ are
+produced by the oracle pinned here.
+"""
+import os
+
+import cv2
+import numpy as np
+import pytest
+
+from conftest import REF_DATA, needs_reference
+from kimera_vio_b200.params import CameraParams, FrontendParams
+from oracle import frontend as ofe
+from oracle.rig import StereoRig
+
+pytestmark = needs_reference
+
+
+def _frame(img_rel):
+    img = cv2.imread(os.path.join(REF_DATA, img_rel), cv2.IMREAD_GRAYSCALE)
+    cam = CameraParams.from_yaml(os.path.join(REF_DATA, "sensor.yaml"))
+    return ofe.Frame(0, 123, img, cam)
+
+
+def _bins(fr, p):
+    brs = np.float32(fr.img.shape[0]) / np.float32(p.nr_vertical_bins)
+    bcs = np.float32(fr.img.shape[1]) / np.float32(p.nr_horizontal_bins)
+    cnt = np.zeros((p.nr_vertical_bins, p.nr_horizontal_bins), int)
+    for x, y in fr.keypoints:
+        cnt[int(np.float32(y) / brs), int(np.float32(x) / bcs)] += 1
+    return cnt
+
+
+# tests/testFeatureDetector.cpp:26-52
+def test_detector_no_nms_393():
+    p = FrontendParams.from_yaml(os.path.join(REF_DATA, "ForFeatureDetector/frontendParams-noNMS.yaml"))
+    f = _frame("ForStereoFrame/left_fisheye_img_0.png")
+    ofe.FeatureDetector(p).feature_detection(f, None)
+    assert len(f.keypoints) == 393
+
+
+# tests/testFeatureDetector.cpp:55-80
+def test_detector_no_nms_400():
+    p = FrontendParams.from_yaml(os.path.join(REF_DATA, "ForFeatureDetector/frontendParams-noNMS.yaml"))
+    p.quality_level = 1e-10
+    f = _frame("ForStereoFrame/left_fisheye_img_0.png")
+    ofe.FeatureDetector(p).feature_detection(f, None)
+    assert len(f.keypoints) == 400
+
+
+# tests/testFeatureDetector.cpp:83-106
+def test_detector_topn_300():
+    p = FrontendParams.from_yaml(os.path.join(REF_DATA, "ForFeatureDetector/frontendParams-NMS-TopN.yaml"))
+    f = _frame("ForStereoFrame/left_fisheye_img_0.png")
+    ofe.FeatureDetector(p).feature_detection(f, None)
+    assert len(f.keypoints) == 300
+
+
+# tests/testFeatureDetector.cpp:109-150
+def test_detector_binning_20():
+    p = FrontendParams.from_yaml(os.path.join(REF_DATA, "ForFeatureDetector/frontendParams-NMS-Binning.yaml"))
+    f = _frame("ForStereoFrame/left_fisheye_img_0.png")
+    ofe.FeatureDetector(p).feature_detection(f, None)
+    assert len(f.keypoints) == 20
+    assert np.all(_bins(f, p) == 1)
+
+
+# tests/testFeatureDetector.cpp:153-200
+def test_detector_binning_200():
+    p = FrontendParams.from_yaml(os.path.join(REF_DATA, "ForFeatureDetector/frontendParams-NMS-Binning.yaml"))
+    p.max_features_per_frame = 200
+    p.quality_level = 1e-10
+    p.enable_subpixel_corner_refinement = False
+    f = _frame("ForStereoFrame/left_fisheye_img_0.png")
+    ofe.FeatureDetector(p).feature_detection(f, None)
+    assert len(f.keypoints) == 200
+    assert np.all(_bins(f, p) == 10)
+
+
+# tests/testFeatureDetector.cpp:203-258
+def test_detector_binning_mask_140():
+    p = FrontendParams.from_yaml(os.path.join(REF_DATA, "ForFeatureDetector/frontendParams-NMS-Binning2.yaml"))
+    p.quality_level = 1e-10
+    p.enable_subpixel_corner_refinement = False
+    f = _frame("ForStereoFrame/left_fisheye_img_0.png")
+    ofe.FeatureDetector(p).feature_detection(f, None)
+    assert len(f.keypoints) == 140
+    cnt = _bins(f, p)
+    assert np.all(cnt[p.binning_mask == 1] == 10) and np.all(cnt[p.binning_mask == 0] == 0)
+
+
+# tests/testStereoMatcher.cpp:148 (baseline) -- Euroc rig
+def test_rig_baseline_euroc():
+    rig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    assert abs(rig.baseline - 0.110078) < 1e-4
+    # tests/testStereoCamera.cpp:374-440: P2[0,3] = -fx * b
+    assert abs(rig.P2[0, 3] + rig.fx * rig.baseline) < 1e-9
+
+
+# tests/testStereoMatcher.cpp:272-388 -- getRightKeypointsRectified on a synthetically shifted image
+def test_stereo_matcher_shifted_849_of_900():
+    d = os.path.join(REF_DATA, "ForStereoFrame")
+    left = CameraParams.from_yaml(os.path.join(d, "sensorLeft.yaml"))
+    right = CameraParams.from_yaml(os.path.join(d, "sensorRight.yaml"))
+    rig = StereoRig(left, right)
+    assert abs(rig.baseline - 0.110078) < 1e-4            # tests/testStereoMatcher.cpp:148
+    p = FrontendParams()                                  # struct defaults, as in the fixture
+    m = ofe.StereoMatcher(p, rig)
+    img = cv2.imread(os.path.join(d, "left_img_0.png"), cv2.IMREAD_GRAYSCALE)
+    corners = cv2.goodFeaturesToTrack(img, 100, 0.01, 10, blockSize=3, useHarrisDetector=False, k=0.04)
+    corners = corners.reshape(-1, 2)
+    count_valid = total = 0
+    for offset in (-20, -10, -5):
+        M = np.eye(3)
+        M[0, 2] = offset
+        right_img = cv2.warpPerspective(img, M, (img.shape[1], img.shape[0]), flags=cv2.INTER_NEAREST)
+        lk = []
+        for t in range(2):
+            if t == 1:
+                lk += [(ofe.KP_VALID, (np.float32(ofe.c_round(x)), np.float32(ofe.c_round(y)))) for x, y in corners]
+            else:
+                lk += [(ofe.KP_VALID, (np.float32(x), np.float32(y))) for x, y in corners]
+            rk = m.get_right_keypoints_rectified(img, right_img, lk, 458.654, rig.baseline)
+            for (ls, lp), (rs_, rp) in zip(lk, rk):
+                total += 1
+                y_left, x_exp, x_act = float(lp[1]), float(lp[0]) + offset, float(rp[0])
+                stripe_rows = 11 + 4
+                if y_left <= (stripe_rows - 1) // 2 or y_left + (stripe_rows - 1) // 2 >= img.shape[0]:
+                    assert rs_ == ofe.KP_NO_RIGHT_RECT
+                elif x_exp >= 50 and x_exp + 50 < img.shape[1]:
+                    assert rs_ == ofe.KP_VALID
+                    assert abs(x_exp - x_act) <= 0.5
+                    assert abs(float(lp[1]) - float(rp[1])) <= 0.5
+                    count_valid += 1
+    assert count_valid == 849
+    assert total == 900
+
+
+# tests/testStereoVisionImuFrontend.cpp:455-661 -- processFirstFrame on the 35-corner synthetic pair
+def test_process_first_frame_35_corners():
+    d = os.path.join(REF_DATA, "ForStereoTracker")
+    left = CameraParams.from_yaml(os.path.join(d, "camLeft.yaml"))
+    right = CameraParams.from_yaml(os.path.join(d, "camRight.yaml"))
+    rig = StereoRig(left, right)
+    p = FrontendParams()                       # struct defaults
+    p.min_distance = int(0.05)                 # the test assigns 0.05 to an int member
+    p.quality_level = 0.1
+    p.max_point_dist = 500
+    p.templ_cols = 9
+    p.subpixel_refinement_stereo = True
+    imgl = cv2.imread(os.path.join(d, "img_distort_left.png"), cv2.IMREAD_GRAYSCALE)
+    imgr = cv2.imread(os.path.join(d, "img_distort_right.png"), cv2.IMREAD_GRAYSCALE)
+
+    def load(path):
+        vals = open(path).read().split()
+        n = int(vals[0])
+        return np.array([float(v) for v in vals[1:]]).reshape(n, -1)
+
+    gl, gr = load(os.path.join(d, "corners_normal_left.txt")), load(os.path.join(d, "corners_normal_right.txt"))
+    depth = load(os.path.join(d, "depth_left.txt")).reshape(-1)
+    fe = ofe.StereoFrontend(p, rig)
+    out = fe.spin(ofe.StereoFrame.make(0, 0, imgl, imgr, rig), np.eye(3))
+    sf = out.frame
+    n = len(sf.left_frame.keypoints)
+    assert n == len(sf.left_frame.landmarks) == len(sf.left_frame.versors) > 0
+    assert all(a == 1 for a in sf.left_frame.landmarks_age)
+    assert sf.is_keyframe and sf.is_rectified
+    for i in range(n):
+        kp = np.array(sf.left_frame.keypoints[i], float)
+        dist = np.abs(gl - kp).max(axis=1)
+        j = int(np.argmin(dist))
+        assert dist[j] < 3                      # findPointInVector tolerance
+        assert np.all(np.abs(gl[j] - kp) <= 2)
+        assert np.all(np.abs(gr[j] - np.array(sf.right_frame.keypoints[i], float)) <= 2)
+        assert sf.left_keypoints_rectified[i][0] == ofe.KP_VALID
+        assert sf.right_keypoints_rectified[i][0] == ofe.KP_VALID
+        assert abs(depth[j] - sf.keypoints_3d[i][2]) <= 4
