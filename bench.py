@@ -1,0 +1,344 @@
+#!/usr/bin/env python
+"""bench.py -- stereo front-end frame-pairs/s on synthetic 752x480 Euroc-shaped input.
+
+  python bench.py --gpus N --steps K --warmup W          (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                   (the reference's OpenCV CPU path: oracle/)
+
+A "step" = one pass of the whole hot path over one batch of `--batch` (default 32) stereo
+frame-pairs, one per independent camera stream (BASELINE.json configs[1]).  `value` is measured
+with the batch already resident in HBM (kvfe_frontend_step_dev); `e2e` goes through the
+reference-facing C-ABI call with HOST buffers (kvfe_frontend_step: H2D of both images of every
+pair, D2H of every output packet inside the timed region).  Streams shard across ranks with no
+data-path collective (weak scaling: the per-GPU batch is fixed).
+"""
+from __future__ import annotations
+
+import argparse
+import ctypes as C
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from kimera_vio_b200.params import CameraParams, FrontendParams  # noqa: E402
+from kimera_vio_b200.rig import StereoRigSetup  # noqa: E402
+from kimera_vio_b200.synth import SynthStream  # noqa: E402
+
+W, H, N_FEATS = 752, 480, 300
+POOL_STREAMS = 4              # distinct synthetic streams; batch slot b replays stream b % POOL_STREAMS
+DT_NS = 50_000_000
+
+
+def frame_pool(n_frames: int, rig: StereoRigSetup):
+    """POOL_STREAMS synthetic sequences of n_frames pairs, cached under /tmp (generation is numpy)."""
+    cache = "/tmp/kvfe_bench_pool_%dx%d_%d_%d.npz" % (W, H, POOL_STREAMS, n_frames)
+    if os.path.exists(cache):
+        z = np.load(cache)
+        return z["left"], z["right"], z["rot"]
+    left = np.zeros((POOL_STREAMS, n_frames, H, W), np.uint8)
+    right = np.zeros_like(left)
+    rot = np.zeros((POOL_STREAMS, n_frames, n_frames, 3, 3))     # rot[s, lkf, k]
+    for s in range(POOL_STREAMS):
+        st = SynthStream(CameraParams.euroc_left(), CameraParams.euroc_right(), rig.R1, seed=20240 + 1000 * s)
+        for k in range(n_frames):
+            f = st.frame(k)
+            left[s, k], right[s, k] = f.left, f.right
+        for a in range(n_frames):
+            for k in range(n_frames):
+                rot[s, a, k] = st.kf_rotation(a, k)
+    try:
+        np.savez(cache, left=left, right=right, rot=rot)
+    except Exception:
+        pass
+    return left, right, rot
+
+
+def slot_timestamp(b: int, k: int) -> int:
+    # staggers the keyframe cadence across batch slots: slot b's first gap is (1 + b % 4) periods
+    return 1403715273262142976 + (k + (b % 4 if k >= 1 else 0)) * DT_NS
+
+
+class ClockSampler:
+    def __init__(self, gpu_index: int):
+        self.rows, self.stop = [], False
+        self.idx = gpu_index
+        self.t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+             "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+             "clocks_event_reasons.sw_power_cap")
+        while not self.stop:
+            try:
+                o = subprocess.run(["nvidia-smi", "-i", str(self.idx), "--query-gpu=" + q, "--format=csv,noheader,nounits"],
+                                   capture_output=True, text=True, timeout=5).stdout.strip()
+                if o:
+                    self.rows.append([c.strip() for c in o.split(",")])
+            except Exception:
+                pass
+            time.sleep(0.1)
+
+    def __enter__(self):
+        self.t.start()
+        return self
+
+    def __exit__(self, *a):
+        self.stop = True
+        self.t.join(timeout=6)
+
+    def summary(self):
+        if not self.rows:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": []}
+        sm = sorted(float(r[0]) for r in self.rows)
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        reasons = [n for i, n in enumerate(names) if any(r[3 + i].lower().startswith("active") for r in self.rows)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.rows[0][1]), "reasons": reasons,
+                "samples": len(self.rows)}
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        return json.load(open(p)), "measured"
+    return {"hbm_gbs": 6650.0}, "fallback"
+
+
+# ------------------------------------------------------------------------------------------------
+# the oracle front-end as the timed CPU baseline (cv2 == the reference's OpenCV code path)
+# ------------------------------------------------------------------------------------------------
+def _oracle_worker(args):
+    stream_id, n_warm, n_timed, threads = args
+    import cv2
+    from oracle import frontend as ofe
+    from oracle.rig import StereoRig
+    cv2.setNumThreads(threads)
+    rig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    setup = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
+    left, right, rot = frame_pool(n_warm + n_timed, setup)
+    s = stream_id % POOL_STREAMS
+    fe = ofe.StereoFrontend(FrontendParams.euroc(), rig)
+    lkf = 0
+    t0 = None
+    n_kf = 0
+    for k in range(n_warm + n_timed):
+        if k == n_warm:
+            t0 = time.perf_counter()
+        sf = ofe.StereoFrame.make(k, slot_timestamp(stream_id, k), left[s, k], right[s, k], rig)
+        o = fe.spin(sf, rot[s, lkf, k])
+        if o.is_keyframe:
+            lkf = k
+            n_kf += k >= n_warm
+    return time.perf_counter() - t0, n_timed, n_kf
+
+
+def cpu_baseline_single(n_warm: int, n_timed: int):
+    dt, n, n_kf = _oracle_worker((0, n_warm, n_timed, 1))
+    return {"value": n / dt, "unit": "frame-pairs/s", "cores": 1, "kind": "port",
+            "sample": "oracle (cv2 4.13 + numpy RANSAC), 1 stream, %d timed pairs after %d warm-up, %d keyframes, "
+                      "cv2.setNumThreads(1)" % (n, n_warm, n_kf)}
+
+
+def run_reference(args):
+    """--impl reference: the reference's own CPU implementation of the path (the oracle: same OpenCV
+    calls), one single-threaded process per host core, one camera stream each."""
+    import multiprocessing as mp
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    ncores = len(os.sched_getaffinity(0))
+    nproc = max(1, min(ncores, 32))
+    setup = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
+    frame_pool(args.warmup + args.steps, setup)          # build the cache once
+    t0 = time.perf_counter()
+    with mp.get_context("fork").Pool(nproc) as pool:
+        res = pool.map(_oracle_worker, [(i, args.warmup, args.steps, 1) for i in range(nproc)])
+    wall = max(r[0] for r in res)
+    total = sum(r[1] for r in res)
+    value = total / wall
+    line = {
+        "impl": "reference", "metric": "stereo front-end frame-pairs/sec @ 752x480", "value": value,
+        "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "u8/int32/f32/f64 (OpenCV CPU)", "data": "synthetic",
+        "config": {"workload": "Euroc stereo 752x480, 300 feats, %d independent streams on %d host processes "
+                               "(1 thread each), oracle = cv2 CPU front-end" % (nproc, nproc)},
+        "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": nproc, "kind": "port",
+                         "sample": "%d streams x %d timed pairs, one single-threaded process per core" % (nproc, args.steps)},
+        "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0, "host_cores_available": ncores, "wall_s_incl_setup": time.perf_counter() - t0,
+    }
+    print(json.dumps(line))
+
+
+# ------------------------------------------------------------------------------------------------
+def run_gpu(args):
+    import torch
+    import torch.distributed as dist
+    from kimera_vio_b200 import lib as kl
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    B, K, Wm = args.batch, args.steps, args.warmup
+    n_frames = Wm + K
+    rig = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
+    left, right, rot = frame_pool(n_frames, rig)
+    p = FrontendParams.euroc()
+    cfg = kl.make_config(p, W, H, batch=B)
+    ctx = kl.Context(cfg, rig.to_c())
+    stream = torch.cuda.ExternalStream(kl.load().kvfe_cuda_stream(ctx.h))
+
+    # IMU rotations need the last-keyframe index per slot, which depends on the device-side keyframe
+    # decisions: run the sequence once (untimed, host path) to learn the keyframe schedule.
+    def host_ptrs(k):
+        lp = (C.c_void_p * B)(*[left[b % POOL_STREAMS, k].ctypes.data for b in range(B)])
+        rp = (C.c_void_p * B)(*[right[b % POOL_STREAMS, k].ctypes.data for b in range(B)])
+        return lp, rp
+    ts_all = np.array([[slot_timestamp(rank * B + b, k) for b in range(B)] for k in range(n_frames)], np.int64)
+    lkf = np.zeros(B, np.int64)
+    R_all = np.zeros((n_frames, B, 9))
+    kf_sched = np.zeros((n_frames, B), bool)
+    pk_buf = np.empty(B * ctx.packet_bytes, np.uint8)
+    for k in range(n_frames):
+        for b in range(B):
+            R_all[k, b] = rot[b % POOL_STREAMS, lkf[b], k].reshape(9)
+        lp, rp = host_ptrs(k)
+        rc = ctx.step_raw(lp, rp, W, ts_all[k], R_all[k], pk_buf)
+        assert rc == 0, kl.load().kvfe_last_error(ctx.h)
+        for b, pk in enumerate(ctx.parse_packets(pk_buf)):
+            if pk["is_keyframe"]:
+                lkf[b] = k
+                kf_sched[k, b] = True
+    n_kp_mean = float(np.mean([pk["n"] for pk in ctx.parse_packets(pk_buf)]))
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---------------- device-resident measurement (value) ----------------
+    dL = torch.empty((n_frames, B, H, W), dtype=torch.uint8, device="cuda")
+    dR = torch.empty_like(dL)
+    for k in range(n_frames):
+        for b in range(B):
+            dL[k, b].copy_(torch.from_numpy(left[b % POOL_STREAMS, k]))
+            dR[k, b].copy_(torch.from_numpy(right[b % POOL_STREAMS, k]))
+    torch.cuda.synchronize()
+
+    def run_dev(k0, k1):
+        for k in range(k0, k1):
+            rc = ctx.step_dev(dL[k].data_ptr(), dR[k].data_ptr(), W, ts_all[k], R_all[k])
+            assert rc == 0
+
+    sampler = ClockSampler(local)
+    ctx.reset()
+    run_dev(0, Wm)
+    barrier()
+    launches0 = ctx.launches
+    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with sampler:
+        ev0.record(stream)
+        run_dev(Wm, n_frames)
+        ev1.record(stream)
+        barrier()
+    dev_ms = ev0.elapsed_time(ev1)
+    launches = ctx.launches - launches0
+    clocks = sampler.summary()
+
+    # ---------------- end-to-end measurement through host buffers (e2e) ----------------
+    import ctypes
+    pinL = torch.empty((n_frames, B, H, W), dtype=torch.uint8).pin_memory()
+    pinR = torch.empty_like(pinL).pin_memory()
+    for k in range(n_frames):
+        for b in range(B):
+            pinL[k, b].copy_(torch.from_numpy(left[b % POOL_STREAMS, k]))
+            pinR[k, b].copy_(torch.from_numpy(right[b % POOL_STREAMS, k]))
+    pk_pin = torch.empty(B * ctx.packet_bytes, dtype=torch.uint8).pin_memory()
+    pk_np = pk_pin.numpy()
+    ptrs = [((C.c_void_p * B)(*[pinL[k, b].data_ptr() for b in range(B)]),
+             (C.c_void_p * B)(*[pinR[k, b].data_ptr() for b in range(B)])) for k in range(n_frames)]
+
+    def run_host(k0, k1):
+        for k in range(k0, k1):
+            rc = ctx.step_raw(ptrs[k][0], ptrs[k][1], W, ts_all[k], R_all[k], pk_np)
+            assert rc == 0
+
+    ctx.reset()
+    run_host(0, Wm)
+    barrier()
+    t0 = time.perf_counter()
+    run_host(Wm, n_frames)
+    barrier()
+    e2e_s = time.perf_counter() - t0
+
+    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(times, op=dist.ReduceOp.MAX)
+    dev_ms, e2e_ms = float(times[0]), float(times[1])
+
+    if rank == 0:
+        pairs = world * B * K
+        value = pairs / (dev_ms * 1e-3)
+        e2e_value = pairs / (e2e_ms * 1e-3)
+        rho = float(kf_sched[Wm:].mean())
+        b_alg = (1 - rho) * W * H + rho * 4 * W * H + 112 * n_kp_mean      # SURVEY 8(d), measured rho
+        peaks, which = measured_peaks()
+        achieved = b_alg * (B * K / (dev_ms * 1e-3)) / 1e9              # per GPU
+        line = {
+            "metric": "stereo front-end frame-pairs/sec @ 752x480", "value": value, "unit": "frame-pairs/s",
+            "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 images, f32 LK+response, f64 geometry",
+            "data": "synthetic",
+            "config": {"workload": "Euroc stereo 752x480, %d feats, 1xB200 batch=%d frame-pairs per step "
+                                   "(BASELINE.json configs[1]); %d independent streams per GPU" % (N_FEATS, B, B),
+                       "batch_per_gpu": B, "keyframe_ratio": rho, "mean_keypoints": n_kp_mean,
+                       "timing": "CUDA events on the library stream, max over ranks; every step reads fresh "
+                                 "device-resident inputs (%d MB per rank > L2), no L2 flush" %
+                                 (2 * n_frames * B * H * W // 2 ** 20)},
+            "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": e2e_ms / K,
+                    "h2d_bytes_per_step": int(2 * B * W * H + B * 80),
+                    "d2h_bytes_per_step": int(B * ctx.packet_bytes)},
+            "gpu_launches": int(launches),
+            "clocks": clocks,
+            "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": None, "peak_source": which,
+                         "algorithmic_bytes_per_frame_pair": b_alg,
+                         "note": "whole-step figure; per-kernel roofline in profiles/"},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline_single(4, 24)
+        print(json.dumps(line))
+    ctx.close()
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=16)
+    ap.add_argument("--warmup", type=int, default=4)
+    ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--impl", default="kvfe", choices=["kvfe", "reference"])
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3:
+        args.warmup = 3
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_gpu(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,271 @@
+/* kvfe.h -- C-ABI of libkvfe.so: the B200-native stereo visual front-end hot path of Kimera-VIO.
+ *
+ * Every entry point replaces one method (or a sequence of methods) of the reference's C++ classes;
+ * the reference interface each one stands in for is cited as file:line relative to the reference
+ * tree.  Only plain pointers, sizes and POD structs cross this boundary (no torch / cv / gtsam
+ * types).  All functions return 0 on success and a negative kvfe_status on failure; the reason is
+ * available through kvfe_last_error().  Nothing here ever falls back to a CPU implementation: if
+ * no CUDA device is usable kvfe_create() fails with KVFE_ERR_NO_DEVICE.
+ *
+ * Conventions: images are 8-bit, row-major, `pitch` bytes per row, HOST pointers unless the
+ * function name ends in `_dev`.  Keypoint arrays are SoA (separate x / y arrays) exactly like the
+ * reference's parallel std::vectors (include/kimera-vio/frontend/Frame.h:160-186,
+ * StereoFrame.h:141-171).  Rotation matrices and camera matrices are row-major doubles.
+ */
+#ifndef KVFE_H_
+#define KVFE_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define KVFE_VERSION 1
+
+typedef struct kvfe_ctx kvfe_ctx;
+
+typedef enum {
+  KVFE_OK = 0,
+  KVFE_ERR_INVALID_ARG = -1,
+  KVFE_ERR_NO_DEVICE = -2,
+  KVFE_ERR_CUDA = -3,
+  KVFE_ERR_CAPACITY = -4,
+  KVFE_ERR_STATE = -5
+} kvfe_status;
+
+/* KeypointStatus -- include/kimera-vio/common/vio_types.h:38-44 */
+typedef enum {
+  KVFE_KP_VALID = 0,
+  KVFE_KP_NO_LEFT_RECT = 1,
+  KVFE_KP_NO_RIGHT_RECT = 2,
+  KVFE_KP_NO_DEPTH = 3,
+  KVFE_KP_FAILED_ARUN = 4
+} kvfe_keypoint_status;
+
+/* TrackingStatus -- include/kimera-vio/frontend/Tracker-definitions.h:124-130 */
+typedef enum {
+  KVFE_TRK_VALID = 0,
+  KVFE_TRK_LOW_DISPARITY = 1,
+  KVFE_TRK_FEW_MATCHES = 2,
+  KVFE_TRK_INVALID = 3,
+  KVFE_TRK_DISABLED = 4
+} kvfe_tracking_status;
+
+/* Mirrors the YAML keys parsed by TrackerParams (src/frontend/VisionImuTrackerParams.cpp:84-135),
+ * FeatureDetectorParams (src/frontend/feature-detector/FeatureDetectorParams.cpp:105-222),
+ * StereoMatchingParams (src/frontend/StereoMatchingParams.cpp:80-90) and FrontendParams
+ * (src/frontend/VisionImuFrontendParams.cpp:80-112). */
+typedef struct {
+  /* geometry of the batch */
+  int32_t width, height;          /* image size (all streams) */
+  int32_t batch;                  /* number of independent camera-stream slots */
+  int32_t max_keypoints;          /* capacity of every per-frame keypoint array; 0 = derive */
+  /* tracker */
+  int32_t klt_win_size, klt_max_iter, klt_max_level;
+  double klt_eps;
+  int32_t max_feature_track_age;
+  int32_t min_nr_mono_inliers, min_nr_stereo_inliers;
+  double ransac_threshold_mono, ransac_threshold_stereo;
+  int32_t ransac_max_iterations;
+  double ransac_probability;
+  int32_t ransac_randomize;             /* must be 0: deterministic seed 12345 (Euroc default) */
+  int32_t ransac_use_1point_stereo, ransac_use_2point_mono;
+  int32_t pose_2d2d_algorithm;          /* 1 = NISTER (only value on the graded path) */
+  int32_t optical_flow_predictor_type;  /* 0 static, 1 rotational */
+  double disparity_threshold;
+  int32_t rnd_libstdcxx;                /* 0: libstdc++ >= 11 (Lemire), 1: libstdc++ < 11 */
+  /* detector */
+  int32_t max_features_per_frame;
+  int32_t enable_subpixel_corner_refinement;
+  int32_t subpix_max_iters;
+  double subpix_epsilon;
+  int32_t subpix_window_size, subpix_zero_zone;
+  int32_t enable_non_max_suppression;
+  int32_t non_max_suppression_type;     /* 0 TopN, 6 Binning (others: KVFE_ERR_INVALID_ARG) */
+  int32_t min_distance;
+  int32_t max_nr_keypoints_before_anms;
+  int32_t nr_horizontal_bins, nr_vertical_bins;
+  uint8_t binning_mask[64];             /* row-major nr_vertical_bins x nr_horizontal_bins, 0/1 */
+  double quality_level;
+  int32_t block_size;                   /* 3 only */
+  int32_t use_harris_detector;          /* 0 only */
+  double k;
+  int32_t sobel_cpu_tail_start;         /* first column where the reference host's scalar Sobel
+                                           tail (non-FMA) applies; -1 = none */
+  /* stereo matching */
+  double tolerance_template_matching;
+  int32_t templ_cols, templ_rows, stripe_extra_rows;
+  double min_point_dist, max_point_dist;
+  int32_t subpixel_refinement_stereo;
+  /* front-end FSM */
+  int64_t min_intra_keyframe_time_ns, max_intra_keyframe_time_ns;
+  int32_t min_number_features;
+  int32_t use_stereo_tracking, use_ransac;
+  double max_disparity_since_lkf;
+} kvfe_config;
+
+/* Stereo rig after cv::stereoRectify -- what StereoCamera::StereoCamera hands to its two
+ * UndistorterRectifiers (src/frontend/StereoCamera.cpp:34-94,
+ * src/frontend/UndistorterRectifier.cpp:26-31, :230-292). Radial-tangential pinhole only. */
+typedef struct {
+  double K_left[9], K_right[9];
+  double D_left[4], D_right[4];   /* k1 k2 p1 p2 */
+  double R1[9], R2[9];
+  double P1[12], P2[12];
+  double baseline;                /* 1 / Q(3,2), StereoCamera.cpp:70-72 */
+} kvfe_rig;
+
+/* Fills every field with the reference's struct defaults / the Euroc YAML. */
+void kvfe_config_default(kvfe_config* cfg);
+
+int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx** out);
+void kvfe_destroy(kvfe_ctx* ctx);
+const char* kvfe_last_error(const kvfe_ctx* ctx);   /* ctx may be NULL: last create() error */
+int kvfe_max_keypoints(const kvfe_ctx* ctx);
+int kvfe_kernel_launches(const kvfe_ctx* ctx);       /* kernels launched by this ctx so far */
+
+/* ---------------------------------------------------------------------------------------------
+ * Stage-level entry points (one camera stream; host buffers; synchronous).
+ * ------------------------------------------------------------------------------------------- */
+
+/* UndistorterRectifier::undistortRectifyImage x2 == StereoCamera::undistortRectifyStereoFrame
+ * (src/frontend/UndistorterRectifier.cpp:115-128, src/frontend/StereoCamera.cpp:269-290).
+ * cv::remap INTER_LINEAR / BORDER_REPLICATE with the float maps recomputed in registers. */
+int kvfe_rectify_pair(kvfe_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                      uint8_t* left_rect, uint8_t* right_rect, size_t out_pitch);
+
+/* The CV_32FC1 maps of UndistorterRectifier::initUndistortRectifyMaps (UndistorterRectifier.cpp:
+ * 230-292) for camera `cam` (0 left, 1 right), written densely (width floats per row). */
+int kvfe_rectify_maps(kvfe_ctx* ctx, int cam, float* map_x, float* map_y);
+
+/* cv::buildOpticalFlowPyramid as used inside cv::calcOpticalFlowPyrLK (Tracker.cpp:137-146):
+ * returns levels 1..klt_max_level densely packed one after the other (diagnostics / tests). */
+int kvfe_pyramid(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* levels_out,
+                 size_t levels_out_bytes, int* n_levels);
+
+/* cv::cornerMinEigenVal(img, blockSize 3, ksize 3) -- the response map inside
+ * cv::goodFeaturesToTrack (FeatureDetector.cpp:165-172); diagnostics / tests. */
+int kvfe_min_eigen_response(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, float* response);
+
+/* FeatureDetector::featureDetection(const Frame&, int need_n_corners)
+ * (src/frontend/feature-detector/FeatureDetector.cpp:174-299): mask of tracked keypoints,
+ * GFTT, non-max suppression (NonMaximumSuppression.cpp:33-169), cv::cornerSubPix.
+ * existing_*: the frame's current keypoints_ / landmarks_ (landmark -1 = not masked). */
+int kvfe_detect(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* existing_x,
+                const float* existing_y, const int64_t* existing_lmk, int n_existing, int need,
+                float* out_x, float* out_y, int* n_out);
+/* Same, but stops after cv::GFTTDetector::detect (FeatureDetector::rawFeatureDetection,
+ * FeatureDetector.cpp:165-172): corners in descending-response order. */
+int kvfe_detect_raw(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* existing_x,
+                    const float* existing_y, const int64_t* existing_lmk, int n_existing,
+                    float* out_x, float* out_y, float* out_response, int* n_out);
+
+/* The optical-flow half of Tracker::featureTracking (src/frontend/Tracker.cpp:117-148):
+ * RotationalOpticalFlowPredictor::predictSparseFlow (optical-flow/OpticalFlowPredictor.cpp:70-126)
+ * followed by cv::calcOpticalFlowPyrLK with OPTFLOW_USE_INITIAL_FLOW.  ref_R_cur row-major 3x3. */
+int kvfe_track(kvfe_ctx* ctx, const uint8_t* ref_img, const uint8_t* cur_img, size_t pitch,
+               const double* ref_R_cur, const float* ref_x, const float* ref_y, int n,
+               float* pred_x, float* pred_y, float* cur_x, float* cur_y, uint8_t* status);
+
+/* UndistorterRectifier::UndistortRectifyKeypoints (UndistorterRectifier.cpp:33-68).
+ * cam: 0 left, 1 right; use_R / use_P select R1|R2 and P1|P2 or identity. */
+int kvfe_undistort_keypoints(kvfe_ctx* ctx, int cam, int use_R, int use_P, const float* x,
+                             const float* y, int n, float* out_x, float* out_y);
+/* UndistorterRectifier::GetBearingVector (UndistorterRectifier.cpp:73-113), left camera, R = R1. */
+int kvfe_bearing_vectors(kvfe_ctx* ctx, const float* x, const float* y, int n, double* versors);
+
+/* StereoMatcher::sparseStereoReconstruction(StereoFrame*) (src/frontend/StereoMatcher.cpp:123-175):
+ * rectify both images, StereoCamera::undistortRectifyLeftKeypoints (StereoCamera.cpp:236-260),
+ * getRightKeypointsRectified (:196-281), getDepthFromRectifiedMatches (:425-483),
+ * distortUnrectifyRightKeypoints (StereoCamera.cpp:262-267), keypoints_3d (:157-174). */
+typedef struct {
+  int32_t* left_status;  float* left_rect_x;  float* left_rect_y;
+  int32_t* right_status; float* right_rect_x; float* right_rect_y;
+  double* depth;         /* n   */
+  double* points_3d;     /* n*3 */
+  float* right_x;  float* right_y;   /* right_frame_.keypoints_ */
+} kvfe_stereo_out;
+int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                       const float* kp_x, const float* kp_y, const double* versors, int n,
+                       kvfe_stereo_out* out, uint8_t* left_rect, uint8_t* right_rect,
+                       size_t rect_pitch);
+
+/* Tracker::geometricOutlierRejection2d2d (src/frontend/Tracker.cpp:213-319) on matched bearing
+ * pairs: 2-point (TranslationOnlySacProblem, R12 given) or 5-point Nister (R12 == NULL).
+ * inliers: ascending match indices; pose: row-major 3x4 [R|t]; status: kvfe_tracking_status. */
+int kvfe_ransac_mono(kvfe_ctx* ctx, const double* f_ref, const double* f_cur, int n,
+                     const double* R12, int32_t* inliers, int* n_inliers, double* pose,
+                     int* status);
+/* Tracker::geometricOutlierRejection3d3dGivenRotation (Tracker.cpp:382-632): 1-point voting. */
+int kvfe_ransac_stereo_1pt(kvfe_ctx* ctx, const float* ref_left_xy, const float* ref_right_xy,
+                           const float* cur_left_xy, const float* cur_right_xy,
+                           const double* ref_3d, const double* cur_3d, int n, const double* R,
+                           int32_t* inliers, int* n_inliers, double* pose, double* info,
+                           int* status);
+/* Tracker::geometricOutlierRejection3d3d (Tracker.cpp:667-742): 3-point Arun. */
+int kvfe_ransac_stereo_3pt(kvfe_ctx* ctx, const double* ref_3d, const double* cur_3d, int n,
+                           int32_t* inliers, int* n_inliers, double* pose, int* status);
+
+/* ---------------------------------------------------------------------------------------------
+ * Frame-level entry points: the whole hot path for `batch` independent streams per call, with
+ * the per-stream front-end state (previous pyramid, km1 / lkf keypoint SoA, landmark-id counter)
+ * resident in HBM.  One call == VisionImuFrontend::spinOnce for every stream
+ * (src/frontend/VisionImuFrontend.cpp:50-64 -> StereoVisionImuFrontend.cpp:67-100 / :283-481).
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+  int32_t n;                 /* keypoints in the output StereoFrame */
+  int32_t is_keyframe;
+  int32_t mono_status, stereo_status;      /* TrackerStatusSummary (kvfe_tracking_status) */
+  int32_t n_smart;           /* smart stereo measurements (keyframes only) */
+  int32_t nr_tracked;        /* DebugTrackerInfo::nrTrackerFeatures_ */
+  int32_t nr_mono_putatives, nr_mono_inliers, nr_stereo_putatives, nr_stereo_inliers;
+  int32_t nr_valid_rkp, nr_no_left_rect_rkp, nr_no_right_rect_rkp, nr_no_depth_rkp,
+      nr_failed_arun_rkp;    /* StereoFrame::checkStatusRightKeypoints (StereoFrame.cpp:106-143) */
+  int32_t mode;              /* 0 bootstrap, 1 nominal non-keyframe, 2 keyframe, 3 all tracks lost */
+  int64_t frame_id, timestamp;
+  double lkf_T_k_mono[12], lkf_T_k_stereo[12], info_stereo[9];
+  double median_disparity;
+} kvfe_packet_header;
+
+/* Byte layout of one stream's packet in the flat output buffer (cap = kvfe_max_keypoints()):
+ * header, then arrays in this order (each `cap` entries):
+ *   kp_x f32, kp_y f32, landmark i64, age i32, score f64 (always 0), versor f64 x3,
+ *   left_status i32, left_rect_x f32, left_rect_y f32, right_status i32, right_rect_x f32,
+ *   right_rect_y f32, depth f64, point3d f64 x3, right_x f32, right_y f32,
+ *   smart_lmk i64, smart_uL f64, smart_uR f64, smart_v f64.
+ * kvfe_packet_bytes() gives the stride; kvfe_packet_offsets() the offsets in that order. */
+size_t kvfe_packet_bytes(const kvfe_ctx* ctx);
+int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries);
+
+int kvfe_frontend_reset(kvfe_ctx* ctx);
+
+/* Host-buffer step: copies the batch's images H2D, runs the step, copies the packets (and, when
+ * rect_left/right are non-NULL, the rectified images of keyframes) D2H.  left/right: `batch`
+ * pointers; timestamps: batch; keyframe_R_cur: batch x 9 (camLrectLkf_R_camLrectK from the IMU,
+ * StereoVisionImuFrontend.cpp:149-150); packets: batch * kvfe_packet_bytes(). */
+int kvfe_frontend_step(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right,
+                       size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
+                       uint8_t* packets, uint8_t* const* rect_left, uint8_t* const* rect_right,
+                       size_t rect_pitch);
+
+/* Device-resident step: images already in HBM (batch-major, `pitch` bytes per row, one image
+ * after the other); packets stay in HBM until kvfe_frontend_read_packets. Asynchronous on the
+ * context's stream; kvfe_sync() waits. */
+int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev,
+                           size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur);
+int kvfe_frontend_read_packets(kvfe_ctx* ctx, uint8_t* packets);
+int kvfe_frontend_read_rectified(kvfe_ctx* ctx, int stream, uint8_t* rect_left,
+                                 uint8_t* rect_right, size_t rect_pitch);
+int kvfe_sync(kvfe_ctx* ctx);
+void* kvfe_cuda_stream(kvfe_ctx* ctx);   /* cudaStream_t the context launches on */
+
+/* Debug taps of the last step for parity tests (stream-major, cap entries per stream). */
+int kvfe_debug_lk(kvfe_ctx* ctx, int stream, float* pred_x, float* pred_y, float* next_x,
+                  float* next_y, uint8_t* status, int* n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* KVFE_H_ */

@@ -1,0 +1,873 @@
+// api.cu -- the C-ABI of libkvfe.so (include/kvfe.h): context set-up, host-side constant tables
+// and the kernel sequences behind every entry point.  No CPU compute path exists here: every
+// function either launches the CUDA kernels or fails.
+#include <algorithm>
+#include <cmath>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <numeric>
+#include <random>
+#include <vector>
+
+#include "kvfe_internal.h"
+
+static thread_local char g_create_err[512] = "";
+
+static int set_err(kvfe_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CU(call)                                                                              \
+  do {                                                                                        \
+    cudaError_t e_ = (call);                                                                  \
+    if (e_ != cudaSuccess)                                                                    \
+      return set_err(ctx, KVFE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_), \
+                     __FILE__, __LINE__);                                                     \
+  } while (0)
+
+template <typename T>
+static cudaError_t dmalloc(T** p, size_t n) {
+  cudaError_t e = cudaMalloc((void**)p, n * sizeof(T));
+  if (e == cudaSuccess) e = cudaMemset(*p, 0, n * sizeof(T));
+  return e;
+}
+
+extern "C" void kvfe_config_default(kvfe_config* c) {
+  memset(c, 0, sizeof(*c));
+  c->width = 752; c->height = 480; c->batch = 1; c->max_keypoints = 0;
+  // params/Euroc/FrontendParams.yaml
+  c->klt_win_size = 24; c->klt_max_iter = 30; c->klt_max_level = 4; c->klt_eps = 0.1;
+  c->max_feature_track_age = 25;
+  c->min_nr_mono_inliers = 10; c->min_nr_stereo_inliers = 5;
+  c->ransac_threshold_mono = 1e-6; c->ransac_threshold_stereo = 1.0;
+  c->ransac_max_iterations = 100; c->ransac_probability = 0.995; c->ransac_randomize = 0;
+  c->ransac_use_1point_stereo = 1; c->ransac_use_2point_mono = 1; c->pose_2d2d_algorithm = 1;
+  c->optical_flow_predictor_type = 1; c->disparity_threshold = 0.5; c->rnd_libstdcxx = 0;
+  c->max_features_per_frame = 300; c->enable_subpixel_corner_refinement = 1;
+  c->subpix_max_iters = 40; c->subpix_epsilon = 0.001; c->subpix_window_size = 10; c->subpix_zero_zone = -1;
+  c->enable_non_max_suppression = 1; c->non_max_suppression_type = 6; c->min_distance = 20;
+  c->max_nr_keypoints_before_anms = 2000; c->nr_horizontal_bins = 7; c->nr_vertical_bins = 5;
+  for (int i = 0; i < 64; ++i) c->binning_mask[i] = 1;
+  c->quality_level = 0.001; c->block_size = 3; c->use_harris_detector = 0; c->k = 0.04;
+  c->sobel_cpu_tail_start = -1;
+  c->tolerance_template_matching = 0.15; c->templ_cols = 101; c->templ_rows = 11; c->stripe_extra_rows = 0;
+  c->min_point_dist = 0.5; c->max_point_dist = 10.0; c->subpixel_refinement_stereo = 0;
+  c->min_intra_keyframe_time_ns = 200000000LL; c->max_intra_keyframe_time_ns = 5000000000LL;
+  c->min_number_features = 0; c->use_stereo_tracking = 1; c->use_ransac = 1;
+  c->max_disparity_since_lkf = 1000.0;
+}
+
+static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
+
+// P[:, :3] * R with cv::gemm's 3x3 path, then cv::invert's 3x3 cofactor formula
+static void make_cam(CamModel& c, const double* K, const double* D, const double* R, const double* P) {
+  c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
+  c.k1 = D[0]; c.k2 = D[1]; c.p1 = D[2]; c.p2 = D[3];
+  for (int i = 0; i < 9; ++i) c.R[i] = R[i];
+  for (int i = 0; i < 12; ++i) c.P[i] = P[i];
+  for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) c.PP[3 * i + j] = P[4 * i + j];
+  for (int i = 0; i < 3; ++i)
+    for (int j = 0; j < 3; ++j)
+      c.RP[3 * i + j] = (c.PP[3 * i] * R[j] + c.PP[3 * i + 1] * R[3 + j]) + c.PP[3 * i + 2] * R[6 + j];
+  const double* S = c.RP;
+  double d = S[0] * (S[4] * S[8] - S[5] * S[7]) - S[1] * (S[3] * S[8] - S[5] * S[6]) + S[2] * (S[3] * S[7] - S[4] * S[6]);
+  d = 1.0 / d;
+  double* t = c.iR;
+  t[0] = (S[4] * S[8] - S[5] * S[7]) * d; t[1] = (S[2] * S[7] - S[1] * S[8]) * d; t[2] = (S[1] * S[5] - S[2] * S[4]) * d;
+  t[3] = (S[5] * S[6] - S[3] * S[8]) * d; t[4] = (S[0] * S[8] - S[2] * S[6]) * d; t[5] = (S[2] * S[3] - S[0] * S[5]) * d;
+  t[6] = (S[3] * S[7] - S[4] * S[6]) * d; t[7] = (S[1] * S[6] - S[0] * S[7]) * d; t[8] = (S[0] * S[4] - S[1] * S[3]) * d;
+}
+
+static void packet_layout(int cap, size_t* off, size_t* total) {
+  const size_t sz[20] = {4, 4, 8, 4, 8, 24, 4, 4, 4, 4, 4, 4, 8, 24, 4, 4, 8, 8, 8, 8};
+  size_t o = round_up(sizeof(kvfe_packet_header), 16);
+  for (int i = 0; i < 20; ++i) { off[i] = o; o = round_up(o + sz[i] * (size_t)cap, 16); }
+  *total = o;
+}
+
+static std::vector<float> subpix_mask_table(int win) {
+  // cv::cornerSubPix: mask[i][j] = (float)(exp(-y*y) * exp(-x*x)), float math (host libm expf)
+  int ww = 2 * win + 1;
+  std::vector<float> m((size_t)ww * ww);
+  for (int i = 0; i < ww; ++i) {
+    float y = (float)(i - win) / win;
+    float vy = std::exp(-y * y);
+    for (int j = 0; j < ww; ++j) {
+      float x = (float)(j - win) / win;
+      m[(size_t)i * ww + j] = (float)(vy * std::exp(-x * x));
+    }
+  }
+  return m;
+}
+
+static std::vector<int> circle_half_widths(int r) {
+  // cv::circle(..., FILLED) raster (FillCircle / Circle with fill): per-row half width
+  std::vector<int> hw(2 * r + 1, -1);
+  int err = 0, dx = r, dy = 0, plus = 1, minus = (r << 1) - 1;
+  while (dx >= dy) {
+    hw[r + dy] = std::max(hw[r + dy], dx); hw[r - dy] = std::max(hw[r - dy], dx);
+    hw[r + dx] = std::max(hw[r + dx], dy); hw[r - dx] = std::max(hw[r - dx], dy);
+    dy++; err += plus; plus += 2;
+    int mask = (err <= 0) - 1;
+    err -= minus & mask; dx += mask; minus -= mask & 2;
+  }
+  return hw;
+}
+
+extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx** out) {
+  kvfe_ctx* ctx = nullptr;
+  if (!cfg || !rig || !out) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "null argument");
+  *out = nullptr;
+  int ndev = 0;
+  if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+    return set_err(nullptr, KVFE_ERR_NO_DEVICE, "no CUDA device: libkvfe has no CPU path");
+  const kvfe_config& c = *cfg;
+  if (c.width < 64 || c.height < 64 || c.batch < 1) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "bad geometry");
+  if (c.klt_win_size < 3 || c.klt_win_size > 32) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "klt_win_size must be in [3,32]");
+  if (c.block_size != 3 || c.use_harris_detector) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "only GFTT min-eigenvalue, block_size 3");
+  if (c.enable_non_max_suppression && c.non_max_suppression_type != 0 && c.non_max_suppression_type != 6)
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "non_max_suppression_type must be 0 (TopN) or 6 (Binning)");
+  if (c.nr_horizontal_bins * c.nr_vertical_bins > 64 || c.nr_horizontal_bins < 1 || c.nr_vertical_bins < 1)
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "at most 64 bins");
+  if (c.ransac_randomize) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "ransac_randomize must be 0");
+  if (!c.ransac_use_2point_mono) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "5-point mono RANSAC not built in this round");
+  if (c.enable_subpixel_corner_refinement && (c.subpix_window_size < 1 || c.subpix_window_size > 12 || c.subpix_zero_zone >= 0))
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "subpix window must be in [1,12], zero zone -1");
+  if (c.max_nr_keypoints_before_anms < 1 || c.max_nr_keypoints_before_anms > 4096)
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "max_nr_keypoints_before_anms must be in [1,4096]");
+  if (c.ransac_max_iterations < 1 || c.ransac_max_iterations > KVFE_MAX_RANSAC_ITERS)
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "ransac_max_iterations out of range");
+  if ((c.templ_cols & 1) == 0 || (c.templ_rows & 1) == 0) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "template size must be odd");
+
+  ctx = new kvfe_ctx();
+  memset(ctx, 0, sizeof(*ctx));
+  ctx->cfg = c; ctx->rig = *rig;
+  DevCfg& dc = ctx->dc;
+  DevBuf& db = ctx->db;
+  dc.W = c.width; dc.H = c.height; dc.pitch = (int)round_up(c.width, 16); dc.B = c.batch;
+  const int nbins = c.nr_horizontal_bins * c.nr_vertical_bins;
+  int cap = c.max_keypoints;
+  if (cap <= 0) {
+    cap = c.enable_non_max_suppression ? c.max_features_per_frame + nbins + 16
+                                       : std::max(c.max_nr_keypoints_before_anms, c.max_features_per_frame) + 16;
+  }
+  cap = (int)round_up(cap, 32);
+  dc.cap = cap;
+  // pyramid geometry (cv::buildOpticalFlowPyramid stopping rule)
+  {
+    int w = dc.W, h = dc.H, lv = 0;
+    size_t off = 0;
+    for (int level = 0; level <= c.klt_max_level && level < KVFE_MAX_LEVELS; ++level) {
+      dc.lvl_w[level] = w; dc.lvl_h[level] = h; dc.lvl_pitch[level] = (int)round_up(w, 16);
+      dc.lvl_off[level] = off;
+      off = round_up(off + (size_t)dc.lvl_pitch[level] * h, 256);
+      lv = level + 1;
+      w = (w + 1) / 2; h = (h + 1) / 2;
+      if (w <= c.klt_win_size || h <= c.klt_win_size) break;
+    }
+    dc.n_levels = lv;
+    dc.pyr_stride = off;
+  }
+  dc.img_stride = round_up((size_t)dc.pitch * dc.H, 256);
+  dc.win = c.klt_win_size;
+  dc.max_iter = std::min(std::max(c.klt_max_iter, 0), 100);
+  { double e = std::min(std::max(c.klt_eps, 0.), 10.); dc.eps2 = e * e; }
+  dc.min_eig_thr = (float)1e-4;
+  dc.max_age = c.max_feature_track_age; dc.pred_type = c.optical_flow_predictor_type;
+  dc.max_features = c.max_features_per_frame; dc.max_before_anms = c.max_nr_keypoints_before_anms;
+  dc.min_distance = c.min_distance; dc.nms_enabled = c.enable_non_max_suppression; dc.nms_type = c.non_max_suppression_type;
+  dc.hbins = c.nr_horizontal_bins; dc.vbins = c.nr_vertical_bins; dc.n_active_bins = 0;
+  for (int i = 0; i < 64; ++i) { dc.bin_mask[i] = i < nbins ? c.binning_mask[i] : 0; if (i < nbins && c.binning_mask[i]) dc.n_active_bins++; }
+  dc.quality = (float)c.quality_level;   // GFTTDetector stores a double; the product is formed in double
+  dc.subpix_enabled = c.enable_subpixel_corner_refinement; dc.subpix_win = c.subpix_window_size;
+  dc.subpix_iters = std::min(std::max(c.subpix_max_iters, 1), 100); dc.subpix_zero = c.subpix_zero_zone;
+  { double e = std::max(c.subpix_epsilon, 0.); dc.subpix_eps2 = e * e; }
+  dc.sobel_tail_start = c.sobel_cpu_tail_start;
+  { size_t want = (size_t)dc.W * dc.H / 8; size_t p = 8192; while (p < want) p <<= 1; dc.cand_cap = (int)p; }
+  // rectified calibration: Cal3_S2Stereo from P1 (StereoCamera.cpp:75-82)
+  dc.fx = rig->P1[0]; dc.fy = rig->P1[5]; dc.cxr = rig->P1[2]; dc.cyr = rig->P1[6]; dc.baseline = rig->baseline;
+  // stereo stripe geometry (StereoMatcher.cpp:214-231)
+  dc.templ_cols = c.templ_cols; dc.templ_rows = c.templ_rows;
+  dc.stripe_rows = c.templ_rows + c.stripe_extra_rows;
+  {
+    int sc = (int)std::round(dc.fx * dc.baseline / c.min_point_dist) + c.templ_cols + 4;
+    if (sc % 2 != 1) sc += 1;
+    if (sc > dc.W) sc = dc.W;
+    dc.stripe_cols = sc;
+  }
+  if (dc.stripe_cols < dc.templ_cols || dc.stripe_rows < dc.templ_rows) {
+    delete ctx; return set_err(nullptr, KVFE_ERR_INVALID_ARG, "stripe smaller than template");
+  }
+  dc.min_depth = c.min_point_dist; dc.max_depth = c.max_point_dist; dc.fx_b = dc.fx * dc.baseline;
+  dc.tol_templ = (float)c.tolerance_template_matching; dc.subpix_stereo = c.subpixel_refinement_stereo;
+  dc.ransac_iters = c.ransac_max_iterations; dc.thr_mono = c.ransac_threshold_mono; dc.thr_stereo = c.ransac_threshold_stereo;
+  dc.ransac_prob = c.ransac_probability; dc.min_mono_inl = c.min_nr_mono_inliers; dc.min_stereo_inl = c.min_nr_stereo_inliers;
+  dc.use_2pt = c.ransac_use_2point_mono; dc.use_1pt = c.ransac_use_1point_stereo; dc.use_ransac = c.use_ransac;
+  dc.use_stereo_tracking = c.use_stereo_tracking; dc.disparity_thr = c.disparity_threshold; dc.max_disparity = c.max_disparity_since_lkf;
+  dc.min_kf_ns = c.min_intra_keyframe_time_ns; dc.max_kf_ns = c.max_intra_keyframe_time_ns; dc.min_features = c.min_number_features;
+
+  make_cam(ctx->cam[0], rig->K_left, rig->D_left, rig->R1, rig->P1);
+  make_cam(ctx->cam[1], rig->K_right, rig->D_right, rig->R2, rig->P2);
+
+  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  const size_t B = dc.B;
+  CU(dmalloc(&ctx->d_cam, 2));
+  CU(cudaMemcpy(ctx->d_cam, ctx->cam, sizeof(CamModel) * 2, cudaMemcpyHostToDevice));
+  for (int k = 0; k < 2; ++k) CU(dmalloc(&db.pyr[k], B * dc.pyr_stride));
+  CU(dmalloc(&db.right_raw, B * dc.img_stride));
+  CU(dmalloc(&db.rectL, B * dc.img_stride));
+  CU(dmalloc(&db.rectR, B * dc.img_stride));
+  CU(dmalloc(&db.mask, B * dc.img_stride));
+  CU(dmalloc(&db.eig, B * (size_t)dc.W * dc.H));
+  CU(dmalloc(&db.eig_max, B));
+  CU(dmalloc(&db.cand, B * (size_t)dc.cand_cap));
+  CU(dmalloc(&db.cand_n, B));
+  CU(dmalloc(&db.corner_idx, B * (size_t)dc.max_before_anms));
+  CU(dmalloc(&db.corner_n, B));
+  CU(dmalloc(&db.new_x, B * cap)); CU(dmalloc(&db.new_y, B * cap)); CU(dmalloc(&db.new_n, B));
+  {
+    int cell = std::max(dc.min_distance, 1);
+    size_t ncells = (size_t)((dc.W + cell - 1) / cell) * ((dc.H + cell - 1) / cell);
+    db.scratch_stride = round_up(3 * (size_t)dc.cand_cap + ncells + 64 + 5 * (size_t)(dc.ransac_iters + 1) + cap, 64);
+    CU(dmalloc(&db.scratch_i, B * db.scratch_stride));
+  }
+  // all-equal-keys std::sort permutations (cv::sortIdx descending): perm(N) at offset N(N-1)/2
+  {
+    int M = dc.max_before_anms;
+    std::vector<unsigned short> tab((size_t)M * (M + 1) / 2 + 1);
+    std::vector<int> keys, idx;
+    for (int N = 1; N <= M; ++N) {
+      keys.assign(N, 0); idx.resize(N);
+      std::iota(idx.begin(), idx.end(), 0);
+      std::sort(idx.begin(), idx.end(), [&](int a, int b) { return keys[a] < keys[b]; });
+      std::reverse(idx.begin(), idx.end());
+      for (int i = 0; i < N; ++i) tab[(size_t)N * (N - 1) / 2 + i] = (unsigned short)idx[i];
+    }
+    CU(dmalloc(&db.sort_perm, tab.size()));
+    CU(cudaMemcpy(db.sort_perm, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+  }
+  // OpenGV rnd(): uniform_int_distribution<int>(0, INT_MAX)(mt19937(12345)), both libstdc++ algorithms
+  {
+    int n = 8 * (dc.ransac_iters + 1) * 12 + 64;
+    std::vector<int> tab(n);
+    std::mt19937 alg; alg.seed(12345u);
+    for (int i = 0; i < n;) {
+      unsigned int r = alg();
+      if (c.rnd_libstdcxx == 0) tab[i++] = (int)(r >> 1);
+      else if (r < 0x80000000u) tab[i++] = (int)r;
+    }
+    db.rnd_n = n;
+    CU(dmalloc(&db.rnd_table, n));
+    CU(cudaMemcpy(db.rnd_table, tab.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  {
+    std::vector<float> m = subpix_mask_table(std::max(dc.subpix_win, 1));
+    CU(dmalloc(&db.subpix_mask, m.size()));
+    CU(cudaMemcpy(db.subpix_mask, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice));
+    std::vector<float> m2 = subpix_mask_table(10);
+    CU(dmalloc(&db.subpix_mask_stereo, m2.size()));
+    CU(cudaMemcpy(db.subpix_mask_stereo, m2.data(), m2.size() * sizeof(float), cudaMemcpyHostToDevice));
+  }
+  {
+    int r = std::max(dc.min_distance, 0);
+    std::vector<int> hw = circle_half_widths(r);
+    ctx->circle_r = r;
+    CU(dmalloc(&ctx->circle_hw, hw.size()));
+    CU(cudaMemcpy(ctx->circle_hw, hw.data(), hw.size() * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  CU(dmalloc(&db.lk_px, B * cap)); CU(dmalloc(&db.lk_py, B * cap));
+  CU(dmalloc(&db.lk_qx, B * cap)); CU(dmalloc(&db.lk_qy, B * cap));
+  CU(dmalloc(&db.lk_pred_x, B * cap)); CU(dmalloc(&db.lk_pred_y, B * cap));
+  CU(dmalloc(&db.lk_src, B * cap)); CU(dmalloc(&db.lk_status, B * cap));
+  CU(dmalloc(&db.m_ref, B * cap)); CU(dmalloc(&db.m_cur, B * cap)); CU(dmalloc(&db.m_n, B));
+  CU(dmalloc(&db.inl, B * cap)); CU(dmalloc(&db.inl_n, B));
+  db.rs_stride = round_up(6 * (size_t)cap + 12 * (size_t)(dc.ransac_iters + 1) + 16 * (size_t)cap, 32);
+  CU(dmalloc(&db.rs_d, B * db.rs_stride));
+  {
+    FrameSoA& f = db.fr;
+    size_t n = B * 3 * cap;
+    CU(dmalloc(&f.n, B * 3)); CU(dmalloc(&f.timestamp, B * 3)); CU(dmalloc(&f.frame_id, B * 3));
+    CU(dmalloc(&f.kx, n)); CU(dmalloc(&f.ky, n)); CU(dmalloc(&f.lmk, n)); CU(dmalloc(&f.age, n));
+    CU(dmalloc(&f.versor, 3 * n)); CU(dmalloc(&f.lstat, n)); CU(dmalloc(&f.lrx, n)); CU(dmalloc(&f.lry, n));
+    CU(dmalloc(&f.rstat, n)); CU(dmalloc(&f.rrx, n)); CU(dmalloc(&f.rry, n)); CU(dmalloc(&f.depth, n));
+    CU(dmalloc(&f.p3d, 3 * n)); CU(dmalloc(&f.rkx, n)); CU(dmalloc(&f.rky, n));
+  }
+  CU(dmalloc(&db.st, B));
+  packet_layout(cap, db.pk_off, &db.packet_bytes);
+  CU(dmalloc(&db.packets, B * db.packet_bytes));
+  CU(cudaMallocHost((void**)&ctx->h_stage, 2 * B * dc.img_stride));
+  CU(cudaMallocHost((void**)&ctx->h_packets, B * db.packet_bytes));
+  CU(cudaMallocHost((void**)&ctx->h_ts, KVFE_IN_SLOTS * B * sizeof(long long)));
+  CU(cudaMallocHost((void**)&ctx->h_Rin, KVFE_IN_SLOTS * B * 9 * sizeof(double)));
+  for (int i = 0; i < KVFE_IN_SLOTS; ++i) CU(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
+  CU(dmalloc(&ctx->d_ts, B)); CU(dmalloc(&ctx->d_Rin, B * 9));
+  ctx->launches += launch_reset(dc, db, ctx->stream);
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->cur_slot = 0;
+  *out = ctx;
+  return KVFE_OK;
+}
+
+extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
+  if (!ctx) return;
+  cudaStreamSynchronize(ctx->stream);
+  DevBuf& db = ctx->db;
+  void* ptrs[] = {ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
+                  db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
+                  db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
+                  db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
+                  db.m_cur, db.m_n, db.inl, db.inl_n, db.rs_d, db.fr.n, db.fr.timestamp, db.fr.frame_id, db.fr.kx,
+                  db.fr.ky, db.fr.lmk, db.fr.age, db.fr.versor, db.fr.lstat, db.fr.lrx, db.fr.lry, db.fr.rstat,
+                  db.fr.rrx, db.fr.rry, db.fr.depth, db.fr.p3d, db.fr.rkx, db.fr.rky, db.st, db.packets, ctx->d_ts,
+                  ctx->d_Rin};
+  for (void* p : ptrs) if (p) cudaFree(p);
+  if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
+  if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
+  if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
+  if (ctx->h_Rin) cudaFreeHost(ctx->h_Rin);
+  for (int i = 0; i < KVFE_IN_SLOTS; ++i) if (ctx->in_ev[i]) cudaEventDestroy(ctx->in_ev[i]);
+  cudaStreamDestroy(ctx->stream);
+  delete ctx;
+}
+
+extern "C" const char* kvfe_last_error(const kvfe_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
+extern "C" int kvfe_max_keypoints(const kvfe_ctx* ctx) { return ctx ? ctx->dc.cap : 0; }
+extern "C" int kvfe_kernel_launches(const kvfe_ctx* ctx) { return ctx ? (int)ctx->launches : 0; }
+extern "C" size_t kvfe_packet_bytes(const kvfe_ctx* ctx) { return ctx ? ctx->db.packet_bytes : 0; }
+extern "C" int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries) {
+  if (!ctx || !offsets) return KVFE_ERR_INVALID_ARG;
+  int n = std::min(max_entries, 20);
+  for (int i = 0; i < n; ++i) offsets[i] = ctx->db.pk_off[i];
+  return n;
+}
+extern "C" void* kvfe_cuda_stream(kvfe_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int kvfe_sync(kvfe_ctx* ctx) {
+  if (!ctx) return KVFE_ERR_INVALID_ARG;
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+// ---- helpers for the stage-level calls: they drive stream 0 with an explicit mode ----------------
+static int set_stage_state(kvfe_ctx* ctx, int mode, int need, int n_frame) {
+  StreamState st;
+  memset(&st, 0, sizeof(st));
+  st.mode = mode; st.slot_k = 0; st.slot_km1 = 1; st.slot_lkf = 1; st.need = need; st.frame_count = 1;
+  for (int i = 0; i < 9; ++i) { st.kf_R_ref[i] = st.kf_R_cur[i] = st.ref_R_cur[i] = (i % 4 == 0) ? 1.0 : 0.0; }
+  CU(cudaMemcpyAsync(ctx->db.st, &st, sizeof(st), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->db.fr.n, &n_frame, sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));   // st / n_frame live on this stack frame
+  return KVFE_OK;
+}
+// every other stream must be idle (mode with no stage bit set) during a stage call
+static int park_other_streams(kvfe_ctx* ctx) {
+  if (ctx->dc.B <= 1) return KVFE_OK;
+  std::vector<StreamState> h(ctx->dc.B);
+  CU(cudaMemcpy(h.data(), ctx->db.st, sizeof(StreamState) * ctx->dc.B, cudaMemcpyDeviceToHost));
+  for (int b = 1; b < ctx->dc.B; ++b) h[b].mode = 7;
+  CU(cudaMemcpy(ctx->db.st, h.data(), sizeof(StreamState) * ctx->dc.B, cudaMemcpyHostToDevice));
+  return KVFE_OK;
+}
+
+static int upload_image(kvfe_ctx* ctx, unsigned char* dst, int dst_pitch, const uint8_t* src, size_t pitch) {
+  CU(cudaMemcpy2DAsync(dst, dst_pitch, src, pitch, ctx->dc.W, ctx->dc.H, cudaMemcpyHostToDevice, ctx->stream));
+  return KVFE_OK;
+}
+static int download_image(kvfe_ctx* ctx, uint8_t* dst, size_t pitch, const unsigned char* src, int src_pitch) {
+  CU(cudaMemcpy2DAsync(dst, pitch, src, src_pitch, ctx->dc.W, ctx->dc.H, cudaMemcpyDeviceToHost, ctx->stream));
+  return KVFE_OK;
+}
+#define RET(call) do { int r_ = (call); if (r_ != KVFE_OK) return r_; } while (0)
+#define CHECK_LAUNCH() CU(cudaGetLastError())
+
+extern "C" int kvfe_rectify_pair(kvfe_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                 uint8_t* left_rect, uint8_t* right_rect, size_t out_pitch) {
+  if (!ctx || !left || !right || !left_rect || !right_rect) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  unsigned char* L = db.pyr[0] + dc.lvl_off[0];
+  RET(upload_image(ctx, L, dc.pitch, left, pitch));
+  RET(upload_image(ctx, db.right_raw, dc.pitch, right, pitch));
+  ctx->launches += launch_rectify(dc, ctx->d_cam, 0, L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  CHECK_LAUNCH();
+  RET(download_image(ctx, left_rect, out_pitch, db.rectL, dc.pitch));
+  RET(download_image(ctx, right_rect, out_pitch, db.rectR, dc.pitch));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_rectify_maps(kvfe_ctx* ctx, int cam, float* map_x, float* map_y) {
+  if (!ctx || !map_x || !map_y || cam < 0 || cam > 1) return set_err(ctx, KVFE_ERR_INVALID_ARG, "bad argument");
+  const DevCfg& dc = ctx->dc;
+  size_t n = (size_t)dc.W * dc.H;
+  float* d = ctx->db.eig;    // reuse the response buffer (W*H floats per stream) + a temporary
+  float* d2 = nullptr;
+  CU(cudaMalloc((void**)&d2, n * sizeof(float)));
+  ctx->launches += launch_maps(dc, ctx->d_cam, cam, d, d2, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(map_x, d, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(map_y, d2, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d2);
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_pyramid(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* levels_out,
+                            size_t levels_out_bytes, int* n_levels) {
+  if (!ctx || !img || !levels_out || !n_levels) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  RET(upload_image(ctx, db.pyr[0] + dc.lvl_off[0], dc.pitch, img, pitch));
+  ctx->launches += launch_pyramid(dc, db.pyr[0], 1, ctx->stream);
+  CHECK_LAUNCH();
+  size_t o = 0;
+  for (int l = 1; l < dc.n_levels; ++l) {
+    size_t sz = (size_t)dc.lvl_w[l] * dc.lvl_h[l];
+    if (o + sz > levels_out_bytes) return set_err(ctx, KVFE_ERR_CAPACITY, "levels_out too small");
+    CU(cudaMemcpy2DAsync(levels_out + o, dc.lvl_w[l], db.pyr[0] + dc.lvl_off[l], dc.lvl_pitch[l], dc.lvl_w[l],
+                         dc.lvl_h[l], cudaMemcpyDeviceToHost, ctx->stream));
+    o += sz;
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  *n_levels = dc.n_levels;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_min_eigen_response(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, float* response) {
+  if (!ctx || !img || !response) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  RET(park_other_streams(ctx));
+  RET(set_stage_state(ctx, 2, 0, 0));
+  unsigned char* I = db.pyr[0] + dc.lvl_off[0];
+  RET(upload_image(ctx, I, dc.pitch, img, pitch));
+  ctx->launches += launch_min_eig(dc, db, I, dc.pyr_stride, 1 << 2, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(response, db.eig, (size_t)dc.W * dc.H * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+static int load_existing(kvfe_ctx* ctx, const float* x, const float* y, const int64_t* lmk, int n) {
+  DevBuf& db = ctx->db;
+  if (n > ctx->dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "n_existing %d exceeds capacity %d", n, ctx->dc.cap);
+  if (n > 0) {
+    CU(cudaMemcpyAsync(db.fr.kx, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(db.fr.ky, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpyAsync(db.fr.lmk, lmk, n * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  }
+  return KVFE_OK;
+}
+
+static int detect_common(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* ex, const float* ey,
+                         const int64_t* el, int n_existing, int need, bool raw) {
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  RET(park_other_streams(ctx));
+  RET(set_stage_state(ctx, 2, need, n_existing));
+  RET(load_existing(ctx, ex, ey, el, n_existing));
+  unsigned char* I = db.pyr[0] + dc.lvl_off[0];
+  RET(upload_image(ctx, I, dc.pitch, img, pitch));
+  ctx->launches += launch_gftt(dc, db, I, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, 1 << 2, ctx->stream);
+  if (!raw) ctx->launches += launch_select(dc, db, I, dc.pyr_stride, ctx->d_cam, 1 << 2, 0, ctx->stream);
+  CHECK_LAUNCH();
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_detect(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* existing_x,
+                           const float* existing_y, const int64_t* existing_lmk, int n_existing, int need,
+                           float* out_x, float* out_y, int* n_out) {
+  if (!ctx || !img || !out_x || !out_y || !n_out) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  RET(detect_common(ctx, img, pitch, existing_x, existing_y, existing_lmk, n_existing, need, false));
+  int n = 0;
+  CU(cudaMemcpyAsync(&n, ctx->db.new_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (n > 0) {
+    CU(cudaMemcpy(out_x, ctx->db.new_x, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_y, ctx->db.new_y, n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  *n_out = n;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_detect_raw(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* existing_x,
+                               const float* existing_y, const int64_t* existing_lmk, int n_existing,
+                               float* out_x, float* out_y, float* out_response, int* n_out) {
+  if (!ctx || !img || !out_x || !out_y || !n_out) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  RET(detect_common(ctx, img, pitch, existing_x, existing_y, existing_lmk, n_existing, 0, true));
+  const DevCfg& dc = ctx->dc;
+  int n = 0;
+  CU(cudaMemcpyAsync(&n, ctx->db.corner_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  std::vector<int> idx(std::max(n, 1));
+  std::vector<float> eig((size_t)dc.W * dc.H);
+  if (n > 0) CU(cudaMemcpy(idx.data(), ctx->db.corner_idx, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (out_response) CU(cudaMemcpy(eig.data(), ctx->db.eig, eig.size() * sizeof(float), cudaMemcpyDeviceToHost));
+  for (int i = 0; i < n; ++i) {
+    out_x[i] = (float)(idx[i] % dc.W); out_y[i] = (float)(idx[i] / dc.W);
+    if (out_response) out_response[i] = eig[idx[i]];
+  }
+  *n_out = n;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_track(kvfe_ctx* ctx, const uint8_t* ref_img, const uint8_t* cur_img, size_t pitch,
+                          const double* ref_R_cur, const float* ref_x, const float* ref_y, int n,
+                          float* pred_x, float* pred_y, float* cur_x, float* cur_y, uint8_t* status) {
+  if (!ctx || !ref_img || !cur_img || !ref_R_cur || !cur_x || !cur_y || !status)
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  if (n > dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, dc.cap);
+  RET(park_other_streams(ctx));
+  // frame slot 1 (km1) holds the reference keypoints; prep computes the homography from
+  // keyframe_R_ref = I, keyframe_R_cur = ref_R_cur
+  StreamState st;
+  memset(&st, 0, sizeof(st));
+  st.frame_count = 1; st.slot_km1 = 1; st.slot_lkf = 1; st.slot_k = 0; st.mode = 1;
+  for (int i = 0; i < 9; ++i) st.kf_R_ref[i] = (i % 4 == 0) ? 1.0 : 0.0;
+  CU(cudaMemcpy(db.st, &st, sizeof(st), cudaMemcpyHostToDevice));
+  std::vector<long long> lm(std::max(n, 1));
+  std::iota(lm.begin(), lm.end(), 0LL);
+  std::vector<int> age(std::max(n, 1), 1);
+  int ns[3] = {0, n, 0};
+  CU(cudaMemcpy(db.fr.n, ns, sizeof(ns), cudaMemcpyHostToDevice));
+  if (n > 0) {
+    CU(cudaMemcpy(db.fr.kx + dc.cap, ref_x, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db.fr.ky + dc.cap, ref_y, n * sizeof(float), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db.fr.lmk + dc.cap, lm.data(), n * sizeof(long long), cudaMemcpyHostToDevice));
+    CU(cudaMemcpy(db.fr.age + dc.cap, age.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+  }
+  long long ts = 0;
+  CU(cudaMemcpy(ctx->d_ts, &ts, sizeof(ts), cudaMemcpyHostToDevice));
+  CU(cudaMemcpy(ctx->d_Rin, ref_R_cur, 9 * sizeof(double), cudaMemcpyHostToDevice));
+  RET(upload_image(ctx, db.pyr[0] + dc.lvl_off[0], dc.pitch, ref_img, pitch));
+  RET(upload_image(ctx, db.pyr[1] + dc.lvl_off[0], dc.pitch, cur_img, pitch));
+  ctx->launches += launch_pyramid(dc, db.pyr[0], 1, ctx->stream);
+  ctx->launches += launch_pyramid(dc, db.pyr[1], 1, ctx->stream);
+  ctx->launches += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, ctx->stream);
+  ctx->launches += launch_track_pre(dc, db, ctx->stream);
+  ctx->launches += launch_lk(dc, db, 0, 1, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (n > 0) {
+    if (pred_x) CU(cudaMemcpy(pred_x, db.lk_pred_x, n * sizeof(float), cudaMemcpyDeviceToHost));
+    if (pred_y) CU(cudaMemcpy(pred_y, db.lk_pred_y, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cur_x, db.lk_qx, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(cur_y, db.lk_qy, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(status, db.lk_status, n, cudaMemcpyDeviceToHost));
+  }
+  ctx->launches += launch_reset(dc, db, ctx->stream);
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_undistort_keypoints(kvfe_ctx* ctx, int cam, int use_R, int use_P, const float* x,
+                                        const float* y, int n, float* out_x, float* out_y) {
+  if (!ctx || !x || !y || !out_x || !out_y || cam < 0 || cam > 1) return set_err(ctx, KVFE_ERR_INVALID_ARG, "bad argument");
+  if (n <= 0) return KVFE_OK;
+  float* d = nullptr;
+  CU(cudaMalloc((void**)&d, 4 * (size_t)n * sizeof(float)));
+  CU(cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_undistort(ctx->dc, ctx->d_cam, cam, use_R, use_P, d, d + n, n, d + 2 * n, d + 3 * n, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(out_x, d + 2 * n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_y, d + 3 * n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d);
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_bearing_vectors(kvfe_ctx* ctx, const float* x, const float* y, int n, double* versors) {
+  if (!ctx || !x || !y || !versors) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (n <= 0) return KVFE_OK;
+  float* d = nullptr; double* dv = nullptr;
+  CU(cudaMalloc((void**)&d, 2 * (size_t)n * sizeof(float)));
+  CU(cudaMalloc((void**)&dv, 3 * (size_t)n * sizeof(double)));
+  CU(cudaMemcpyAsync(d, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + n, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_bearing(ctx->dc, ctx->d_cam, d, d + n, n, dv, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(versors, dv, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  cudaFree(d); cudaFree(dv);
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint8_t* right, size_t pitch,
+                                  const float* kp_x, const float* kp_y, const double* versors, int n,
+                                  kvfe_stereo_out* out, uint8_t* left_rect, uint8_t* right_rect, size_t rect_pitch) {
+  if (!ctx || !left || !right || !kp_x || !kp_y || !versors || !out) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  if (n > dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, dc.cap);
+  if (n <= 0) return set_err(ctx, KVFE_ERR_INVALID_ARG, "Call feature detection on left frame first...");
+  RET(park_other_streams(ctx));
+  RET(set_stage_state(ctx, 2, 0, n));
+  CU(cudaMemcpyAsync(db.fr.kx, kp_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(db.fr.ky, kp_y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(db.fr.versor, versors, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  unsigned char* L = db.pyr[0] + dc.lvl_off[0];
+  RET(upload_image(ctx, L, dc.pitch, left, pitch));
+  RET(upload_image(ctx, db.right_raw, dc.pitch, right, pitch));
+  ctx->launches += launch_rectify(dc, ctx->d_cam, 0, L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_sparse_stereo(dc, db, ctx->d_cam, 1 << 2, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaStreamSynchronize(ctx->stream));
+  const FrameSoA& f = db.fr;
+  if (out->left_status) CU(cudaMemcpy(out->left_status, f.lstat, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (out->left_rect_x) CU(cudaMemcpy(out->left_rect_x, f.lrx, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out->left_rect_y) CU(cudaMemcpy(out->left_rect_y, f.lry, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out->right_status) CU(cudaMemcpy(out->right_status, f.rstat, n * sizeof(int), cudaMemcpyDeviceToHost));
+  if (out->right_rect_x) CU(cudaMemcpy(out->right_rect_x, f.rrx, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out->right_rect_y) CU(cudaMemcpy(out->right_rect_y, f.rry, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out->depth) CU(cudaMemcpy(out->depth, f.depth, n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out->points_3d) CU(cudaMemcpy(out->points_3d, f.p3d, 3 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost));
+  if (out->right_x) CU(cudaMemcpy(out->right_x, f.rkx, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (out->right_y) CU(cudaMemcpy(out->right_y, f.rky, n * sizeof(float), cudaMemcpyDeviceToHost));
+  if (left_rect) RET(download_image(ctx, left_rect, rect_pitch, db.rectL, dc.pitch));
+  if (right_rect) RET(download_image(ctx, right_rect, rect_pitch, db.rectR, dc.pitch));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+// ---- RANSAC stage calls ---------------------------------------------------------------------------
+struct DevScratch {
+  void* p = nullptr;
+  ~DevScratch() { if (p) cudaFree(p); }
+};
+
+static int compact_inliers(const std::vector<int>& flags, int n, int32_t* inliers, int* n_inliers) {
+  int m = 0;
+  for (int i = 0; i < n; ++i) if (flags[i]) inliers[m++] = i;
+  *n_inliers = m;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_ransac_mono(kvfe_ctx* ctx, const double* f_ref, const double* f_cur, int n, const double* R12,
+                                int32_t* inliers, int* n_inliers, double* pose, int* status) {
+  if (!ctx || !f_ref || !f_cur || !inliers || !n_inliers || !pose || !status) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc;
+  if (n > dc.cap || n < 0) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, dc.cap);
+  if (n == 0) { *n_inliers = 0; *status = KVFE_TRK_INVALID; for (int i = 0; i < 12; ++i) pose[i] = (i % 5 == 0); return KVFE_OK; }
+  DevScratch sc;
+  size_t bytes = sizeof(double) * (6 * (size_t)n + 9 + 12) + sizeof(int) * ((size_t)n + 2);
+  CU(cudaMalloc(&sc.p, bytes));
+  double* d_a = (double*)sc.p; double* d_b = d_a + 3 * n; double* d_R = d_b + 3 * n; double* d_pose = d_R + 9;
+  int* d_inl = (int*)(d_pose + 12); int* d_n = d_inl + n; int* d_st = d_n + 1;
+  CU(cudaMemcpyAsync(d_a, f_ref, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_b, f_cur, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  if (R12) CU(cudaMemcpyAsync(d_R, R12, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_ransac_mono_raw(dc, ctx->db, d_a, d_b, n, R12 ? d_R : nullptr, 1, d_inl, d_n, d_pose, d_st, ctx->stream);
+  CHECK_LAUNCH();
+  std::vector<int> flags(n);
+  CU(cudaMemcpyAsync(flags.data(), d_inl, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(pose, d_pose, 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(status, d_st, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return compact_inliers(flags, n, inliers, n_inliers);
+}
+
+extern "C" int kvfe_ransac_stereo_3pt(kvfe_ctx* ctx, const double* ref_3d, const double* cur_3d, int n,
+                                      int32_t* inliers, int* n_inliers, double* pose, int* status) {
+  if (!ctx || !ref_3d || !cur_3d || !inliers || !n_inliers || !pose || !status) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc;
+  if (n > dc.cap || n < 0) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, dc.cap);
+  if (n == 0) { *n_inliers = 0; *status = KVFE_TRK_INVALID; for (int i = 0; i < 12; ++i) pose[i] = (i % 5 == 0); return KVFE_OK; }
+  DevScratch sc;
+  size_t bytes = sizeof(double) * (6 * (size_t)n + 12) + sizeof(int) * ((size_t)n + 2);
+  CU(cudaMalloc(&sc.p, bytes));
+  double* d_a = (double*)sc.p; double* d_b = d_a + 3 * n; double* d_pose = d_b + 3 * n;
+  int* d_inl = (int*)(d_pose + 12); int* d_n = d_inl + n; int* d_st = d_n + 1;
+  CU(cudaMemcpyAsync(d_a, ref_3d, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_b, cur_3d, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_ransac_3pt_raw(dc, ctx->db, d_a, d_b, n, d_inl, d_n, d_pose, d_st, ctx->stream);
+  CHECK_LAUNCH();
+  std::vector<int> flags(n);
+  CU(cudaMemcpyAsync(flags.data(), d_inl, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(pose, d_pose, 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(status, d_st, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return compact_inliers(flags, n, inliers, n_inliers);
+}
+
+extern "C" int kvfe_ransac_stereo_1pt(kvfe_ctx* ctx, const float* ref_left_xy, const float* ref_right_xy,
+                                      const float* cur_left_xy, const float* cur_right_xy, const double* ref_3d,
+                                      const double* cur_3d, int n, const double* R, int32_t* inliers,
+                                      int* n_inliers, double* pose, double* info, int* status) {
+  if (!ctx || !ref_left_xy || !ref_right_xy || !cur_left_xy || !cur_right_xy || !ref_3d || !cur_3d || !R || !inliers ||
+      !n_inliers || !pose || !info || !status)
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc;
+  if (n > dc.cap || n < 0) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, dc.cap);
+  if (n == 0) { *n_inliers = 0; *status = KVFE_TRK_INVALID; for (int i = 0; i < 12; ++i) pose[i] = (i % 5 == 0); for (int i = 0; i < 9; ++i) info[i] = 0; return KVFE_OK; }
+  DevScratch sc;
+  size_t bytes = sizeof(double) * (6 * (size_t)n + 9 + 12 + 9) + sizeof(float) * 8 * (size_t)n + sizeof(int) * ((size_t)n + 2);
+  CU(cudaMalloc(&sc.p, bytes));
+  double* d_a = (double*)sc.p; double* d_b = d_a + 3 * n; double* d_R = d_b + 3 * n; double* d_pose = d_R + 9; double* d_info = d_pose + 12;
+  float* d_rl = (float*)(d_info + 9); float* d_rr = d_rl + 2 * n; float* d_cl = d_rr + 2 * n; float* d_cr = d_cl + 2 * n;
+  int* d_inl = (int*)(d_cr + 2 * n); int* d_n = d_inl + n; int* d_st = d_n + 1;
+  CU(cudaMemcpyAsync(d_a, ref_3d, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_b, cur_3d, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_R, R, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_rl, ref_left_xy, 2 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_rr, ref_right_xy, 2 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_cl, cur_left_xy, 2 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d_cr, cur_right_xy, 2 * (size_t)n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_ransac_1pt_raw(dc, ctx->db, d_rl, d_rr, d_cl, d_cr, d_a, d_b, n, d_R, d_inl, d_n, d_pose, d_info, d_st, ctx->stream);
+  CHECK_LAUNCH();
+  std::vector<int> flags(n);
+  CU(cudaMemcpyAsync(flags.data(), d_inl, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(pose, d_pose, 12 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(info, d_info, 9 * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(status, d_st, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return compact_inliers(flags, n, inliers, n_inliers);
+}
+
+// ---- frame-level step ---------------------------------------------------------------------------
+extern "C" int kvfe_frontend_reset(kvfe_ctx* ctx) {
+  if (!ctx) return KVFE_ERR_INVALID_ARG;
+  ctx->launches += launch_reset(ctx->dc, ctx->db, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(ctx->stream));
+  ctx->cur_slot = 0;
+  return KVFE_OK;
+}
+
+// the fixed kernel sequence of one step; images of the current frame already sit in
+// pyr[cur_slot] level 0 (left) and right_raw (right).
+static int enqueue_step(kvfe_ctx* ctx) {
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
+  const int cur = ctx->cur_slot, prev = cur ^ 1;
+  const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
+  unsigned char* Lcur = db.pyr[cur] + dc.lvl_off[0];
+  long long n = 0;
+  n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, s);
+  n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
+  n += launch_track_pre(dc, db, s);
+  n += launch_lk(dc, db, prev, cur, s);
+  n += launch_track_post(dc, db, ctx->d_cam, s);
+  n += launch_decide(dc, db, s);
+  // keyframe: mono RANSAC -> sparse stereo -> stereo RANSAC
+  n += launch_ransac_mono(dc, db, M_KF, s);
+  n += launch_rectify(dc, ctx->d_cam, 0, Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_KF, s);
+  n += launch_ransac_stereo(dc, db, M_KF, s);
+  // detection (bootstrap, keyframe, all-tracks-lost)
+  n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, s);
+  n += launch_gftt(dc, db, Lcur, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, M_BOOT | M_KF | M_LOST, s);
+  n += launch_select(dc, db, Lcur, dc.pyr_stride, ctx->d_cam, M_BOOT | M_KF | M_LOST, 1, s);
+  // sparse stereo over all keypoints incl. the new ones (the second remap of the reference is
+  // idempotent -- same raw images, same maps -- and is therefore not repeated)
+  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, s);
+  n += launch_finalize(dc, db, s);
+  ctx->launches += n;
+  CU(cudaGetLastError());
+  ctx->cur_slot ^= 1;
+  return KVFE_OK;
+}
+
+// Step inputs (timestamps, rotations) go through a ring of pinned slots so that consecutive steps
+// can be enqueued without waiting for the previous one (no host sync on the steady-state path).
+static int stage_inputs(kvfe_ctx* ctx, const int64_t* timestamps, const double* keyframe_R_cur) {
+  const size_t B = ctx->dc.B;
+  const int slot = ctx->in_slot;
+  ctx->in_slot = (slot + 1) % KVFE_IN_SLOTS;
+  if (ctx->in_used[slot]) CU(cudaEventSynchronize(ctx->in_ev[slot]));
+  long long* hts = ctx->h_ts + (size_t)slot * B;
+  double* hR = ctx->h_Rin + (size_t)slot * B * 9;
+  memcpy(hts, timestamps, B * sizeof(long long));
+  memcpy(hR, keyframe_R_cur, B * 9 * sizeof(double));
+  CU(cudaMemcpyAsync(ctx->d_ts, hts, B * sizeof(long long), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ctx->d_Rin, hR, B * 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaEventRecord(ctx->in_ev[slot], ctx->stream));
+  ctx->in_used[slot] = 1;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, size_t pitch,
+                                      const int64_t* timestamps, const double* keyframe_R_cur) {
+  if (!ctx || !left_dev || !right_dev || !timestamps || !keyframe_R_cur) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
+  const size_t B = dc.B;
+  RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
+  // device-to-device placement into the pyramid slot / right buffer (strided destination)
+  for (size_t b = 0; b < B; ++b) {
+    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
+                         left_dev + b * pitch * dc.H, pitch, dc.W, dc.H, cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpy2DAsync(db.right_raw + b * dc.img_stride, dc.pitch, right_dev + b * pitch * dc.H, pitch, dc.W, dc.H,
+                         cudaMemcpyDeviceToDevice, s));
+  }
+  return enqueue_step(ctx);
+}
+
+extern "C" int kvfe_frontend_step(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right, size_t pitch,
+                                  const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets,
+                                  uint8_t* const* rect_left, uint8_t* const* rect_right, size_t rect_pitch) {
+  if (!ctx || !left || !right || !timestamps || !keyframe_R_cur || !packets) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
+  const size_t B = dc.B;
+  RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
+  for (size_t b = 0; b < B; ++b) {
+    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch, left[b], pitch, dc.W,
+                         dc.H, cudaMemcpyHostToDevice, s));
+    CU(cudaMemcpy2DAsync(db.right_raw + b * dc.img_stride, dc.pitch, right[b], pitch, dc.W, dc.H,
+                         cudaMemcpyHostToDevice, s));
+  }
+  RET(enqueue_step(ctx));
+  CU(cudaMemcpyAsync(ctx->h_packets, db.packets, B * db.packet_bytes, cudaMemcpyDeviceToHost, s));
+  CU(cudaStreamSynchronize(s));
+  memcpy(packets, ctx->h_packets, B * db.packet_bytes);
+  if (rect_left && rect_right) {
+    for (size_t b = 0; b < B; ++b) {
+      const kvfe_packet_header* h = reinterpret_cast<const kvfe_packet_header*>(ctx->h_packets + b * db.packet_bytes);
+      if (!h->is_keyframe || !rect_left[b] || !rect_right[b]) continue;
+      CU(cudaMemcpy2DAsync(rect_left[b], rect_pitch, db.rectL + b * dc.img_stride, dc.pitch, dc.W, dc.H, cudaMemcpyDeviceToHost, s));
+      CU(cudaMemcpy2DAsync(rect_right[b], rect_pitch, db.rectR + b * dc.img_stride, dc.pitch, dc.W, dc.H, cudaMemcpyDeviceToHost, s));
+    }
+    CU(cudaStreamSynchronize(s));
+  }
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_read_packets(kvfe_ctx* ctx, uint8_t* packets) {
+  if (!ctx || !packets) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const size_t bytes = (size_t)ctx->dc.B * ctx->db.packet_bytes;
+  CU(cudaMemcpyAsync(ctx->h_packets, ctx->db.packets, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  memcpy(packets, ctx->h_packets, bytes);
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_read_rectified(kvfe_ctx* ctx, int stream, uint8_t* rect_left, uint8_t* rect_right, size_t rect_pitch) {
+  if (!ctx || !rect_left || !rect_right || stream < 0 || stream >= ctx->dc.B) return set_err(ctx, KVFE_ERR_INVALID_ARG, "bad argument");
+  const DevCfg& dc = ctx->dc;
+  RET(download_image(ctx, rect_left, rect_pitch, ctx->db.rectL + (size_t)stream * dc.img_stride, dc.pitch));
+  RET(download_image(ctx, rect_right, rect_pitch, ctx->db.rectR + (size_t)stream * dc.img_stride, dc.pitch));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_debug_lk(kvfe_ctx* ctx, int stream, float* pred_x, float* pred_y, float* next_x, float* next_y,
+                             uint8_t* status, int* n) {
+  if (!ctx || stream < 0 || stream >= ctx->dc.B || !n) return set_err(ctx, KVFE_ERR_INVALID_ARG, "bad argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  CU(cudaStreamSynchronize(ctx->stream));
+  StreamState st;
+  CU(cudaMemcpy(&st, db.st + stream, sizeof(st), cudaMemcpyDeviceToHost));
+  int m = st.n_ref;
+  size_t o = (size_t)stream * dc.cap;
+  if (m > 0) {
+    if (pred_x) CU(cudaMemcpy(pred_x, db.lk_pred_x + o, m * sizeof(float), cudaMemcpyDeviceToHost));
+    if (pred_y) CU(cudaMemcpy(pred_y, db.lk_pred_y + o, m * sizeof(float), cudaMemcpyDeviceToHost));
+    if (next_x) CU(cudaMemcpy(next_x, db.lk_qx + o, m * sizeof(float), cudaMemcpyDeviceToHost));
+    if (next_y) CU(cudaMemcpy(next_y, db.lk_qy + o, m * sizeof(float), cudaMemcpyDeviceToHost));
+    if (status) CU(cudaMemcpy(status, db.lk_status + o, m, cudaMemcpyDeviceToHost));
+  }
+  *n = m;
+  return KVFE_OK;
+}

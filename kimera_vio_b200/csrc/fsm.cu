@@ -1,0 +1,390 @@
+// fsm.cu -- the per-stream front-end state machine, device resident: one CTA (or one thread) per
+// camera stream per stage, no host round trip inside a step.
+//   prep         StereoVisionImuFrontend::processStereoFrame preamble (reference
+//                src/frontend/StereoVisionImuFrontend.cpp:283-310): frame slot for k, ref_R_cur,
+//                RotationalOpticalFlowPredictor homography (optical-flow/OpticalFlowPredictor.cpp:70-92)
+//   track_pre    Tracker::featureTracking :102-129 (valid reference keypoints + predicted flow)
+//   track_post   Tracker::featureTracking :162-189 (survivors, landmark invalidation in the ref frame,
+//                bearing vectors)
+//   decide       VisionImuFrontend::shouldBeKeyframe (src/frontend/VisionImuFrontend.cpp:175-232) and
+//                the "all tracks lost" branch (StereoVisionImuFrontend.cpp:312-323)
+//   detect_pre   FeatureDetector::featureDetection(Frame*, R) :98-115 (ages, n_existing, need)
+//   finalize     slot rotation, keyframe_R_ref_frame_ update (:462-475), getSmartStereoMeasurements
+//                (:485-531), StereoFrame::checkStatusRightKeypoints (StereoFrame.cpp:106-143), packing.
+#include "common.cuh"
+#include "matches.cuh"
+
+
+__global__ void reset_kernel(DevCfg dc, DevBuf db) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= dc.B) return;
+  StreamState& s = db.st[b];
+  s.frame_count = 0; s.slot_km1 = 0; s.slot_lkf = 0; s.slot_k = 0; s.mode = 0;
+  s.mono_status = KVFE_TRK_INVALID; s.stereo_status = KVFE_TRK_INVALID;
+  s.lmk_next = 0; s.need = 0; s.n_existing = 0; s.n_ref = 0; s.n_new = 0; s.use_pred = 0; s.given_rot = 0;
+  s.nr_tracked = s.nr_mono_put = s.nr_mono_inl = s.nr_stereo_put = s.nr_stereo_inl = 0;
+  s.median_disparity = 0;
+  for (int i = 0; i < 9; ++i) { s.kf_R_ref[i] = (i % 4 == 0) ? 1.0 : 0.0; s.info_stereo[i] = 0; }
+  for (int i = 0; i < 12; ++i) { s.pose_mono[i] = (i % 5 == 0) ? 1.0 : 0.0; s.pose_stereo[i] = s.pose_mono[i]; }
+  for (int k = 0; k < 3; ++k) db.fr.n[b * 3 + k] = 0;
+}
+
+__global__ void prep_kernel(DevCfg dc, DevBuf db, const CamModel* __restrict__ cams,
+                            const long long* __restrict__ ts, const double* __restrict__ Rin) {
+  int b = blockIdx.x * blockDim.x + threadIdx.x;
+  if (b >= dc.B) return;
+  StreamState& s = db.st[b];
+  s.timestamp = ts[b];
+  for (int i = 0; i < 9; ++i) s.kf_R_cur[i] = Rin[9 * b + i];
+  s.n_ref = 0; s.n_new = 0;
+  if (s.frame_count == 0) {
+    s.mode = 0; s.slot_k = 0; s.slot_km1 = 0; s.slot_lkf = 0;
+    s.use_pred = 0; s.given_rot = 0;
+  } else {
+    int k = 0;
+    while (k == s.slot_km1 || k == s.slot_lkf) ++k;
+    s.slot_k = k;
+    s.mode = 1;
+    // ref_frame_R_cur_frame = keyframe_R_ref_frame_.inverse().compose(keyframe_R_cur_frame)
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j)
+        s.ref_R_cur[3 * i + j] = s.kf_R_ref[i] * s.kf_R_cur[j] +
+                                 (s.kf_R_ref[3 + i] * s.kf_R_cur[3 + j] + s.kf_R_ref[6 + i] * s.kf_R_cur[6 + j]);
+    // given_rot = !keyframe_R_cur_frame.equals(Rot3(), 1e-9)
+    bool ident = true;
+    for (int i = 0; i < 9; ++i) {
+      double e = (i % 4 == 0) ? 1.0 : 0.0;
+      if (!(fabs(s.kf_R_cur[i] - e) <= 1e-9)) ident = false;
+    }
+    s.given_rot = ident ? 0 : 1;
+    // Eigen::Quaterniond(R).w()
+    const double* R = s.ref_R_cur;
+    double t = R[0] + (R[4] + R[8]);
+    double qw;
+    if (t > 0) qw = 0.5 * sqrt(t + 1.0);
+    else {
+      int i = 0;
+      if (R[4] > R[0]) i = 1;
+      if (R[8] > R[4 * i]) i = 2;
+      int j = (i + 1) % 3, kk = (i + 2) % 3;
+      double tt = sqrt(R[4 * i] - R[4 * j] - R[4 * kk] + 1.0);
+      qw = (R[3 * kk + j] - R[3 * j + kk]) * (0.5 / tt);
+    }
+    s.use_pred = (dc.pred_type == 1) && !(fabs(1.0 - fabs(qw)) < 1e-4);
+    // H = K * R^T * K^-1 in float (cv::Matx33f): s = 0; s += a(i,k) * b(k,j)
+    float K[9] = {(float)cams[0].fx, 0.f, (float)cams[0].cx, 0.f, (float)cams[0].fy, (float)cams[0].cy, 0.f, 0.f, 1.f};
+    float Rt[9];
+    for (int i = 0; i < 3; ++i) for (int j = 0; j < 3; ++j) Rt[3 * i + j] = (float)R[3 * j + i];
+    float Ki[9];
+    {
+      const float* a = K;
+      float d = a[0] * (a[4] * a[8] - a[7] * a[5]) - a[1] * (a[3] * a[8] - a[6] * a[5]) + a[2] * (a[3] * a[7] - a[6] * a[4]);
+      d = 1.f / d;
+      Ki[0] = (a[4] * a[8] - a[5] * a[7]) * d; Ki[1] = (a[2] * a[7] - a[1] * a[8]) * d; Ki[2] = (a[1] * a[5] - a[2] * a[4]) * d;
+      Ki[3] = (a[5] * a[6] - a[3] * a[8]) * d; Ki[4] = (a[0] * a[8] - a[2] * a[6]) * d; Ki[5] = (a[2] * a[3] - a[0] * a[5]) * d;
+      Ki[6] = (a[3] * a[7] - a[4] * a[6]) * d; Ki[7] = (a[1] * a[6] - a[0] * a[7]) * d; Ki[8] = (a[0] * a[4] - a[1] * a[3]) * d;
+    }
+    float T[9];
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float acc = 0.f;
+        for (int q = 0; q < 3; ++q) acc += K[3 * i + q] * Rt[3 * q + j];
+        T[3 * i + j] = acc;
+      }
+    for (int i = 0; i < 3; ++i)
+      for (int j = 0; j < 3; ++j) {
+        float acc = 0.f;
+        for (int q = 0; q < 3; ++q) acc += T[3 * i + q] * Ki[3 * q + j];
+        s.H[3 * i + j] = acc;
+      }
+  }
+  const int fs = b * 3 + s.slot_k;
+  db.fr.n[fs] = 0;
+  db.fr.timestamp[fs] = ts[b];
+  db.fr.frame_id[fs] = s.frame_count;
+}
+
+// CTA-wide ordered compaction helper: returns the output position of `keep` elements (or -1)
+__device__ __forceinline__ int block_compact_pos(int keep, int* s_total, int* wsum, int* s_chunk) {
+  unsigned bal = __ballot_sync(KVFE_FULL_MASK, keep);
+  int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane == 0) wsum[warp] = __popc(bal);
+  __syncthreads();
+  if (warp == 0) {
+    int v = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0, incl = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      int t = __shfl_up_sync(KVFE_FULL_MASK, incl, o);
+      if (lane >= o) incl += t;
+    }
+    wsum[lane] = incl - v;
+    if (lane == 31) *s_chunk = incl;
+  }
+  __syncthreads();
+  int pos = *s_total + wsum[warp] + __popc(bal & ((1u << lane) - 1));
+  __syncthreads();
+  if (threadIdx.x == 0) *s_total += *s_chunk;
+  __syncthreads();
+  return keep ? pos : -1;
+}
+
+__global__ void __launch_bounds__(256) track_pre_kernel(DevCfg dc, DevBuf db) {
+  const int b = blockIdx.x;
+  StreamState& s = db.st[b];
+  if (s.mode == 0) return;
+  __shared__ int s_total, s_chunk, wsum[32];
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  const int fs = b * 3 + s.slot_km1;
+  const int n = db.fr.n[fs];
+  const float Wf = (float)dc.W, Hf = (float)dc.H;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int keep = (i < n) && db.fr.lmk[(size_t)fs * dc.cap + i] != -1;
+    int pos = block_compact_pos(keep, &s_total, wsum, &s_chunk);
+    if (keep) {
+      size_t g = (size_t)b * dc.cap + pos;
+      float x = db.fr.kx[(size_t)fs * dc.cap + i], y = db.fr.ky[(size_t)fs * dc.cap + i];
+      db.lk_px[g] = x; db.lk_py[g] = y; db.lk_src[g] = i;
+      float nx = x, ny = y;
+      if (s.use_pred) {
+        const float* H = s.H;
+        float p0 = 0.f, p1 = 0.f, p2 = 0.f;
+        p0 += H[0] * x; p0 += H[1] * y; p0 += H[2] * 1.0f;
+        p1 += H[3] * x; p1 += H[4] * y; p1 += H[5] * 1.0f;
+        p2 += H[6] * x; p2 += H[7] * y; p2 += H[8] * 1.0f;
+        float qx = x, qy = y;
+        if (p2 > 0.0f) { qx = p0 / p2; qy = p1 / p2; }
+        if (qx >= 0.f && qx < Wf && qy >= 0.f && qy < Hf) { nx = qx; ny = qy; }
+      }
+      db.lk_qx[g] = nx; db.lk_qy[g] = ny;
+      db.lk_pred_x[g] = nx; db.lk_pred_y[g] = ny;
+    }
+  }
+  if (threadIdx.x == 0) s.n_ref = s_total;
+}
+
+__global__ void __launch_bounds__(256) track_post_kernel(DevCfg dc, DevBuf db, const CamModel* __restrict__ cams) {
+  const int b = blockIdx.x;
+  StreamState& s = db.st[b];
+  if (s.mode == 0) return;
+  __shared__ int s_total, s_chunk, wsum[32];
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  const int fr = b * 3 + s.slot_km1, fk = b * 3 + s.slot_k;
+  const int n = s.n_ref;
+  for (int base = 0; base < n; base += blockDim.x) {
+    int j = base + threadIdx.x;
+    int keep = 0, src = 0;
+    size_t g = (size_t)b * dc.cap + j;
+    if (j < n) {
+      src = db.lk_src[g];
+      size_t kr = (size_t)fr * dc.cap + src;
+      if (!db.lk_status[g] || db.fr.age[kr] > dc.max_age) db.fr.lmk[kr] = -1;   // Tracker.cpp:174-179
+      else keep = 1;
+    }
+    int pos = block_compact_pos(keep, &s_total, wsum, &s_chunk);
+    if (keep) {
+      size_t kr = (size_t)fr * dc.cap + src, kk = (size_t)fk * dc.cap + pos;
+      float x = db.lk_qx[g], y = db.lk_qy[g];
+      db.fr.lmk[kk] = db.fr.lmk[kr];
+      db.fr.age[kk] = db.fr.age[kr];
+      db.fr.kx[kk] = x; db.fr.ky[kk] = y;
+      float ux, uy;
+      undistort_point(cams[0], x, y, 1, &ux, &uy);
+      double v0 = (double)ux, v1 = (double)uy, v2 = 1.0;
+      double n2 = v0 * v0 + (v1 * v1 + v2 * v2);
+      double nrm = sqrt(n2);
+      if (n2 > 0) { v0 = v0 / nrm; v1 = v1 / nrm; v2 = v2 / nrm; }
+      db.fr.versor[3 * kk] = v0; db.fr.versor[3 * kk + 1] = v1; db.fr.versor[3 * kk + 2] = v2;
+      // stereo fields of frame k are undefined until sparseStereoReconstruction runs
+      db.fr.lstat[kk] = KVFE_KP_VALID; db.fr.rstat[kk] = KVFE_KP_NO_RIGHT_RECT;
+    }
+  }
+  if (threadIdx.x == 0) { db.fr.n[fk] = s_total; s.nr_tracked = s_total; }
+}
+
+__global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db) {
+  const int b = blockIdx.x;
+  StreamState& s = db.st[b];
+  if (s.mode == 0) return;
+  const int fk = b * 3 + s.slot_k, fl = b * 3 + s.slot_lkf;
+  const int nk = db.fr.n[fk];
+  if (nk == 0) {                       // StereoVisionImuFrontend.cpp:312-323
+    if (threadIdx.x == 0) s.mode = 3;
+    return;
+  }
+  int* m_ref = db.m_ref + (size_t)b * dc.cap;
+  int* m_cur = db.m_cur + (size_t)b * dc.cap;
+  const int nm = block_find_matches(dc, db, fl, fk, false, m_ref, m_cur);
+  double* tmp = db.rs_d + (size_t)b * db.rs_stride;
+  double med = block_median_disparity(dc, db, fl, fk, m_ref, m_cur, nullptr, nm, tmp);
+  // nr valid keypoints of frame k
+  __shared__ int s_valid;
+  if (threadIdx.x == 0) s_valid = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < nk; i += blockDim.x) c += db.fr.lmk[(size_t)fk * dc.cap + i] != -1;
+  if (c) atomicAdd(&s_valid, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double disparity = med < 0.0 ? 0.0 : med;
+    s.median_disparity = disparity;
+    long long kf_diff = db.fr.timestamp[fk] - db.fr.timestamp[fl];
+    bool min_time = kf_diff >= dc.min_kf_ns, max_time = kf_diff >= dc.max_kf_ns;
+    bool nr_low = s_valid <= dc.min_features;
+    bool is_low = disparity < dc.disparity_thr;
+    bool low_first = is_low && !(s.mono_status == KVFE_TRK_LOW_DISPARITY);
+    bool enough = !is_low;
+    bool max_disp = disparity > dc.max_disparity;
+    bool flipped = (enough || low_first) && min_time;
+    bool kf = max_time || max_disp || flipped || nr_low;
+    s.mode = kf ? 2 : 1;
+    if (kf) {
+      // StereoVisionImuFrontend.cpp:345-346, :402-404
+      s.mono_status = dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED;
+      s.stereo_status = dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED;
+    }
+  }
+}
+
+__global__ void __launch_bounds__(256) detect_pre_kernel(DevCfg dc, DevBuf db, int mode_mask) {
+  const int b = blockIdx.x;
+  StreamState& s = db.st[b];
+  if (!mode_on(s.mode, mode_mask)) return;
+  const int fk = b * 3 + s.slot_k;
+  const int n = db.fr.n[fk];
+  __shared__ int s_cnt;
+  if (threadIdx.x == 0) s_cnt = 0;
+  __syncthreads();
+  int c = 0;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) {
+    size_t k = (size_t)fk * dc.cap + i;
+    c += db.fr.lmk[k] != -1;
+    db.fr.age[k] += 1;
+  }
+  if (c) atomicAdd(&s_cnt, c);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    s.n_existing = s_cnt;
+    int need = dc.max_features - s_cnt;
+    s.need = need > 0 ? need : 0;
+  }
+}
+
+__global__ void __launch_bounds__(256) finalize_kernel(DevCfg dc, DevBuf db) {
+  const int b = blockIdx.x;
+  StreamState& s = db.st[b];
+  const int fk = b * 3 + s.slot_k;
+  const int n = db.fr.n[fk];
+  const int mode = s.mode;
+  const bool is_kf = (mode == 0 || mode == 2);
+  unsigned char* pk = db.packets + (size_t)b * db.packet_bytes;
+  kvfe_packet_header* h = reinterpret_cast<kvfe_packet_header*>(pk);
+  const size_t* off = db.pk_off;
+  float* o_kx = (float*)(pk + off[0]); float* o_ky = (float*)(pk + off[1]);
+  long long* o_lmk = (long long*)(pk + off[2]); int* o_age = (int*)(pk + off[3]);
+  double* o_score = (double*)(pk + off[4]); double* o_ver = (double*)(pk + off[5]);
+  int* o_ls = (int*)(pk + off[6]); float* o_lx = (float*)(pk + off[7]); float* o_ly = (float*)(pk + off[8]);
+  int* o_rs = (int*)(pk + off[9]); float* o_rx = (float*)(pk + off[10]); float* o_ry = (float*)(pk + off[11]);
+  double* o_depth = (double*)(pk + off[12]); double* o_p3d = (double*)(pk + off[13]);
+  float* o_rkx = (float*)(pk + off[14]); float* o_rky = (float*)(pk + off[15]);
+  long long* o_sl = (long long*)(pk + off[16]); double* o_suL = (double*)(pk + off[17]);
+  double* o_suR = (double*)(pk + off[18]); double* o_sv = (double*)(pk + off[19]);
+  __shared__ int cnt[5];
+  __shared__ int s_total, s_chunk, wsum[32];
+  if (threadIdx.x < 5) cnt[threadIdx.x] = 0;
+  if (threadIdx.x == 0) s_total = 0;
+  __syncthreads();
+  const bool stereo_valid = (mode == 0 || mode == 2);
+  for (int base = 0; base < n; base += blockDim.x) {
+    int i = base + threadIdx.x;
+    int keep = 0;
+    size_t k = (size_t)fk * dc.cap + i;
+    if (i < n) {
+      o_kx[i] = db.fr.kx[k]; o_ky[i] = db.fr.ky[k]; o_lmk[i] = db.fr.lmk[k]; o_age[i] = db.fr.age[k];
+      o_score[i] = 0.0;
+      o_ver[3 * i] = db.fr.versor[3 * k]; o_ver[3 * i + 1] = db.fr.versor[3 * k + 1]; o_ver[3 * i + 2] = db.fr.versor[3 * k + 2];
+      if (stereo_valid) {
+        int rs = db.fr.rstat[k];
+        o_ls[i] = db.fr.lstat[k]; o_lx[i] = db.fr.lrx[k]; o_ly[i] = db.fr.lry[k];
+        o_rs[i] = rs; o_rx[i] = db.fr.rrx[k]; o_ry[i] = db.fr.rry[k];
+        o_depth[i] = db.fr.depth[k];
+        o_p3d[3 * i] = db.fr.p3d[3 * k]; o_p3d[3 * i + 1] = db.fr.p3d[3 * k + 1]; o_p3d[3 * i + 2] = db.fr.p3d[3 * k + 2];
+        o_rkx[i] = db.fr.rkx[k]; o_rky[i] = db.fr.rky[k];
+        if (rs >= 0 && rs < 5) atomicAdd(&cnt[rs], 1);
+        keep = (mode == 2) && db.fr.lmk[k] != -1;      // smart measurements: keyframes of the nominal spin
+      } else {
+        o_ls[i] = -1; o_rs[i] = -1; o_lx[i] = o_ly[i] = o_rx[i] = o_ry[i] = 0.f; o_depth[i] = 0.0;
+        o_p3d[3 * i] = o_p3d[3 * i + 1] = o_p3d[3 * i + 2] = 0.0; o_rkx[i] = o_rky[i] = 0.f;
+      }
+    }
+    int pos = block_compact_pos(keep, &s_total, wsum, &s_chunk);
+    if (keep) {
+      o_sl[pos] = db.fr.lmk[k];
+      o_suL[pos] = (double)db.fr.lrx[k];
+      o_sv[pos] = (double)db.fr.lry[k];
+      o_suR[pos] = (dc.use_stereo_tracking && db.fr.rstat[k] == KVFE_KP_VALID) ? (double)db.fr.rrx[k]
+                                                                                : __longlong_as_double(0x7ff8000000000000LL);
+    }
+  }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    h->n = n; h->is_keyframe = is_kf ? 1 : 0;
+    h->mono_status = s.mono_status; h->stereo_status = s.stereo_status;
+    h->n_smart = s_total;
+    h->nr_tracked = (mode == 0) ? 0 : s.nr_tracked;
+    h->nr_mono_putatives = s.nr_mono_put; h->nr_mono_inliers = s.nr_mono_inl;
+    h->nr_stereo_putatives = s.nr_stereo_put; h->nr_stereo_inliers = s.nr_stereo_inl;
+    h->nr_valid_rkp = cnt[0]; h->nr_no_left_rect_rkp = cnt[1]; h->nr_no_right_rect_rkp = cnt[2];
+    h->nr_no_depth_rkp = cnt[3]; h->nr_failed_arun_rkp = cnt[4];
+    h->mode = mode;
+    h->frame_id = s.frame_count; h->timestamp = s.timestamp;
+    for (int i = 0; i < 12; ++i) { h->lkf_T_k_mono[i] = s.pose_mono[i]; h->lkf_T_k_stereo[i] = s.pose_stereo[i]; }
+    for (int i = 0; i < 9; ++i) h->info_stereo[i] = s.info_stereo[i];
+    h->median_disparity = s.median_disparity;
+    // state update (StereoVisionImuFrontend.cpp:268-271, :317-319, :447-475)
+    if (mode == 0) { s.slot_km1 = s.slot_k; s.slot_lkf = s.slot_k; }
+    else if (mode == 3) { s.slot_km1 = s.slot_k; }
+    else {
+      if (mode == 2) {
+        s.slot_lkf = s.slot_k;
+        for (int i = 0; i < 9; ++i) s.kf_R_ref[i] = (i % 4 == 0) ? 1.0 : 0.0;
+      } else {
+        for (int i = 0; i < 9; ++i) s.kf_R_ref[i] = s.kf_R_cur[i];
+      }
+      s.slot_km1 = s.slot_k;
+    }
+    s.frame_count += 1;
+  }
+}
+
+int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
+  reset_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db);
+  return 1;
+}
+int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const long long* ts,
+                const double* Rin, cudaStream_t s) {
+  prep_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, d_cam, ts, Rin);
+  return 1;
+}
+int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
+  track_pre_kernel<<<dc.B, 256, 0, s>>>(dc, db);
+  return 1;
+}
+int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, cudaStream_t s) {
+  track_post_kernel<<<dc.B, 256, 0, s>>>(dc, db, d_cam);
+  return 1;
+}
+int launch_decide(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
+  decide_kernel<<<dc.B, 256, 0, s>>>(dc, db);
+  return 1;
+}
+int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s) {
+  detect_pre_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask);
+  return 1;
+}
+int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
+  finalize_kernel<<<dc.B, 256, 0, s>>>(dc, db);
+  return 1;
+}

@@ -1,0 +1,206 @@
+// kvfe_internal.h -- device-side data layout and kernel launchers shared by the .cu files.
+//
+// Data layout in HBM (one context, B streams, cap = keypoint capacity):
+//   * image pyramids: 2 slots (previous / current frame) x B streams; each stream-slot is one
+//     contiguous block holding levels 0..L (level l at lvl_off[l], row pitch lvl_pitch[l]).
+//   * right raw image, rectified left/right images, GFTT response map, detection mask: B images.
+//   * frame SoA: 3 frame slots per stream (km1, lkf, k may alias), every field a flat array
+//     indexed by (stream*3 + slot)*cap + i.
+//   * per-stream FSM state (StreamState) and the packed output packets.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/kvfe.h"
+
+#define KVFE_MAX_LEVELS 8
+#define KVFE_MAX_RANSAC_ITERS 1024
+#define KVFE_IN_SLOTS 8
+
+struct CamModel {        // one camera of the rig, everything the kernels need (f64)
+  double fx, fy, cx, cy;
+  double k1, k2, p1, p2;
+  double R[9];           // rectification rotation (R1 / R2)
+  double P[12];          // new projection (P1 / P2)
+  double PP[9];          // P[:, :3]
+  double RP[9];          // P[:, :3] * R   (cv::gemm 3x3 fast path: (a0*b0 + a1*b1) + a2*b2)
+  double iR[9];          // inv(RP), cv::invert 3x3 cofactor formula -- for map recomputation
+};
+
+struct FrameSoA {        // flat arrays, index (stream*3 + slot)*cap + i
+  int* n;                // [B*3]
+  float *kx, *ky;
+  long long* lmk;
+  int* age;
+  double* versor;        // *3
+  int* lstat; float *lrx, *lry;
+  int* rstat; float *rrx, *rry;
+  double* depth;
+  double* p3d;           // *3
+  float *rkx, *rky;
+  long long* timestamp;  // [B*3]
+  long long* frame_id;   // [B*3]
+};
+
+struct StreamState {     // one per stream, device resident
+  int frame_count;
+  int slot_km1, slot_lkf, slot_k;
+  int mode;              // 0 bootstrap, 1 nominal non-KF, 2 keyframe, 3 all tracks lost
+  int mono_status, stereo_status;
+  int need;              // corners needed by the detector this step
+  int n_existing;
+  int use_pred;          // rotational prediction active this step
+  int n_ref;             // keypoints fed to LK
+  int n_new;             // corners appended by the detector
+  long long lmk_next;    // FeatureDetector.cpp:141 static counter (one per stream == per process)
+  long long timestamp;
+  double kf_R_ref[9];    // keyframe_R_ref_frame_
+  double kf_R_cur[9];    // input of this step
+  double ref_R_cur[9];
+  float H[9];            // K * R^T * K^-1 (float, cv::Matx33f semantics)
+  double pose_mono[12], pose_stereo[12], info_stereo[9];
+  double median_disparity;
+  int given_rot;
+  int nr_tracked, nr_mono_put, nr_mono_inl, nr_stereo_put, nr_stereo_inl;
+};
+
+struct DevCfg {          // passed by value to kernels
+  int W, H, pitch;       // level-0 geometry; pitch in bytes (multiple of 16)
+  int B, cap;
+  int n_levels;          // pyramid levels actually used by LK (maxLevel + 1)
+  int lvl_w[KVFE_MAX_LEVELS], lvl_h[KVFE_MAX_LEVELS], lvl_pitch[KVFE_MAX_LEVELS];
+  size_t lvl_off[KVFE_MAX_LEVELS];
+  size_t pyr_stride;     // bytes per stream-slot pyramid
+  size_t img_stride;     // bytes per full-res u8 image (pitch * H)
+  // tracker
+  int win, max_iter; double eps2; float min_eig_thr;
+  int max_age;
+  int pred_type;
+  // detector
+  int max_features, max_before_anms, min_distance, nms_enabled, nms_type;
+  int hbins, vbins; unsigned char bin_mask[64]; int n_active_bins;
+  float quality;
+  int subpix_enabled, subpix_win, subpix_iters, subpix_zero; double subpix_eps2;
+  int sobel_tail_start;
+  int cand_cap;          // candidate list capacity per stream
+  // stereo
+  int templ_cols, templ_rows, stripe_cols, stripe_rows;
+  double min_depth, max_depth, fx_b; float tol_templ;
+  int subpix_stereo;
+  // ransac / fsm
+  int ransac_iters; double thr_mono, thr_stereo, ransac_prob;
+  int min_mono_inl, min_stereo_inl, use_2pt, use_1pt, use_ransac, use_stereo_tracking;
+  double disparity_thr, max_disparity;
+  long long min_kf_ns, max_kf_ns; int min_features;
+  // rectified calibration
+  double fx, fy, cxr, cyr, baseline;
+};
+
+struct DevBuf {
+  unsigned char* pyr[2];       // B * pyr_stride each
+  unsigned char* right_raw;    // B * img_stride
+  unsigned char* rectL;        // B * img_stride
+  unsigned char* rectR;
+  unsigned char* mask;         // B * img_stride (u8 0/255)
+  float* eig;                  // B * W*H
+  unsigned int* eig_max;       // B (ordered-int encoded float)
+  unsigned long long* cand;    // B * cand_cap  (float bits << 32 | pixel index)
+  int* cand_n;                 // B
+  int* corner_idx;             // B * max_before_anms: accepted GFTT corners (pixel index), in order
+  int* corner_n;               // B
+  float *new_x, *new_y;        // B * cap: corners after NMS / subpix
+  int* new_n;                  // B
+  int* scratch_i;              // B * scratch_stride ints (cell lists, states, ...)
+  size_t scratch_stride;
+  unsigned short* sort_perm;   // all-equal-keys std::sort permutations, triangular: perm(N) at N*(N-1)/2
+  int* rnd_table;              // OpenGV rnd() sequence
+  int rnd_n;
+  // LK staging
+  float *lk_px, *lk_py;        // ref points fed to LK   (B*cap)
+  float *lk_qx, *lk_qy;        // predicted / tracked    (B*cap)
+  float *lk_pred_x, *lk_pred_y;
+  int* lk_src;                 // index in the ref frame (B*cap)
+  unsigned char* lk_status;    // B*cap
+  // matches / ransac staging
+  int *m_ref, *m_cur;          // B*cap
+  int* m_n;                    // B
+  int* inl;                    // B*cap (inlier flags / lists)
+  int* inl_n;                  // B
+  float* subpix_mask;          // (2*win+1)^2 Gaussian weights of cv::cornerSubPix (host expf)
+  float* subpix_mask_stereo;   // same for the hard-coded stereo refinement window (10)
+  double* rs_d;                // B * rs_stride doubles
+  size_t rs_stride;
+  FrameSoA fr;
+  StreamState* st;             // B
+  unsigned char* packets;      // B * packet_bytes
+  size_t packet_bytes;
+  size_t pk_off[32];
+};
+
+struct kvfe_ctx {
+  kvfe_config cfg;
+  kvfe_rig rig;
+  DevCfg dc;
+  DevBuf db;
+  CamModel cam[2];
+  CamModel* d_cam;             // device copy [2]
+  cudaStream_t stream;
+  int cur_slot;                // pyramid slot of the frame being processed
+  long long launches;
+  char err[512];
+  // pinned staging for the host-buffer step
+  unsigned char* h_stage;      // 2 * B * img_stride
+  unsigned char* h_packets;
+  long long* d_ts; double* d_Rin;        // step inputs
+  long long* h_ts; double* h_Rin;        // KVFE_IN_SLOTS pinned slots each
+  cudaEvent_t in_ev[KVFE_IN_SLOTS]; int in_used[KVFE_IN_SLOTS]; int in_slot;
+  int* circle_hw;              // device: half widths of the filled-circle raster rows (2r+1)
+  int circle_r;
+};
+
+// ---- launchers (each returns the number of kernels it launched) ------------------------------
+// rectify.cu
+int launch_rectify(const DevCfg& dc, const CamModel* d_cam, int cam, const unsigned char* src,
+                   size_t src_stride, unsigned char* dst, size_t dst_stride, int nimg,
+                   const StreamState* st, int mode_mask, cudaStream_t s);
+int launch_maps(const DevCfg& dc, const CamModel* d_cam, int cam, float* mx, float* my, cudaStream_t s);
+// pyramid.cu
+int launch_pyramid(const DevCfg& dc, unsigned char* pyr, int nimg, cudaStream_t s);
+// lk.cu
+int launch_lk(const DevCfg& dc, const DevBuf& db, int prev_slot, int cur_slot, cudaStream_t s);
+// gftt.cu
+int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
+                const int* circle_hw, int circle_r, int mode_mask, cudaStream_t s);
+int launch_min_eig(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
+                   int mode_mask, cudaStream_t s);
+// select.cu (ANMS + subpix + append)
+int launch_select(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
+                  const CamModel* d_cam, int mode_mask, int append, cudaStream_t s);
+// stereo.cu
+int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, int mode_mask,
+                         cudaStream_t s);
+int launch_undistort(const DevCfg& dc, const CamModel* d_cam, int cam, int use_R, int use_P,
+                     const float* x, const float* y, int n, float* ox, float* oy, cudaStream_t s);
+int launch_bearing(const DevCfg& dc, const CamModel* d_cam, const float* x, const float* y, int n,
+                   double* versors, cudaStream_t s);
+// ransac.cu
+int launch_ransac_mono(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s);
+int launch_ransac_stereo(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s);
+int launch_ransac_mono_raw(const DevCfg& dc, const DevBuf& db, const double* f_ref, const double* f_cur,
+                           int n, const double* R12, int use_2pt, int* inl, int* n_inl, double* pose,
+                           int* status, cudaStream_t s);
+int launch_ransac_1pt_raw(const DevCfg& dc, const DevBuf& db, const float* rl, const float* rr,
+                          const float* cl, const float* cr, const double* p_ref, const double* p_cur,
+                          int n, const double* R, int* inl, int* n_inl, double* pose, double* info,
+                          int* status, cudaStream_t s);
+int launch_ransac_3pt_raw(const DevCfg& dc, const DevBuf& db, const double* p_ref, const double* p_cur,
+                          int n, int* inl, int* n_inl, double* pose, int* status, cudaStream_t s);
+// fsm.cu
+int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const long long* ts,
+                const double* Rin, cudaStream_t s);
+int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
+int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, cudaStream_t s);
+int launch_decide(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
+int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s);
+int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
+int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s);

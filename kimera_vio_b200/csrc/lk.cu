@@ -1,0 +1,194 @@
+// lk.cu -- row a9: cv::calcOpticalFlowPyrLK as called by Tracker::featureTracking
+// (reference src/frontend/Tracker.cpp:117-148; winSize 24, maxLevel 4, criteria(COUNT+EPS, 30, 0.1),
+// OPTFLOW_USE_INITIAL_FLOW, minEigThreshold 1e-4).
+//
+// One warp per keypoint, levels maxLevel..0 inside the kernel.  Per level:
+//   1. a (win+3)^2 patch of the PREVIOUS image level (BORDER_REFLECT_101 padding semantics) is
+//      staged in shared memory; Scharr derivatives are computed from it on the fly (zero outside
+//      the image, like the zero-padded derivative buffer of OpenCV) -- no derivative image is ever
+//      written to HBM;
+//   2. the fixed-point window I / Ix / Iy (14-bit bilinear weights) and the structure tensor are
+//      formed (integer sums are exact: accumulated in int64, OpenCV accumulates in float);
+//   3. <= maxCount Gauss-Newton iterations, each staging a (win+1)^2 patch of the NEXT image level.
+// All float scalar arithmetic follows LKTrackerInvoker's scalar code path operation by operation.
+#include "common.cuh"
+
+#define LK_MAX_WIN 32
+#define LK_WARPS 4
+
+// per-warp shared-memory carve-up (sizes depend on the runtime window):
+//   P (win+3)^2 u8 | J (win+1)^2 u8 | Dx, Dy (win+1)^2 i16 | I, Ix, Iy win^2 i16
+struct LkSmem {
+  unsigned char* P; unsigned char* J;
+  short *Dx, *Dy, *I, *Ix, *Iy;
+};
+__host__ __device__ inline size_t lk_warp_bytes(int win) {
+  size_t a = ((size_t)(win + 3) * (win + 3) + 15) & ~(size_t)15;
+  size_t b = ((size_t)(win + 1) * (win + 1) + 15) & ~(size_t)15;
+  size_t d = (2 * (size_t)(win + 1) * (win + 1) + 15) & ~(size_t)15;
+  size_t w = (2 * (size_t)win * win + 15) & ~(size_t)15;
+  return a + b + 2 * d + 3 * w;
+}
+
+__device__ __forceinline__ int descale(int x, int n) { return (x + (1 << (n - 1))) >> n; }
+
+// grid (ceil(cap / LK_WARPS), B)
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db, int prev_slot, int cur_slot) {
+  extern __shared__ __align__(16) unsigned char lk_smem_raw[];
+  const int b = blockIdx.y;
+  const StreamState& st = db.st[b];
+  if (st.mode == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pt = blockIdx.x * LK_WARPS + warp;
+  if (pt >= st.n_ref) return;
+  LkSmem s;
+  {
+    const int w_ = dc.win;
+    unsigned char* base = lk_smem_raw + (size_t)warp * lk_warp_bytes(w_);
+    size_t a = ((size_t)(w_ + 3) * (w_ + 3) + 15) & ~(size_t)15;
+    size_t bq = ((size_t)(w_ + 1) * (w_ + 1) + 15) & ~(size_t)15;
+    size_t d = (2 * (size_t)(w_ + 1) * (w_ + 1) + 15) & ~(size_t)15;
+    size_t ww = (2 * (size_t)w_ * w_ + 15) & ~(size_t)15;
+    s.P = base; s.J = base + a;
+    s.Dx = reinterpret_cast<short*>(base + a + bq); s.Dy = reinterpret_cast<short*>(base + a + bq + d);
+    s.I = reinterpret_cast<short*>(base + a + bq + 2 * d);
+    s.Ix = reinterpret_cast<short*>(base + a + bq + 2 * d + ww);
+    s.Iy = reinterpret_cast<short*>(base + a + bq + 2 * d + 2 * ww);
+  }
+  const size_t gi = (size_t)b * dc.cap + pt;
+  const unsigned char* prevPyr = db.pyr[prev_slot] + (size_t)b * dc.pyr_stride;
+  const unsigned char* nextPyr = db.pyr[cur_slot] + (size_t)b * dc.pyr_stride;
+  const int win = dc.win;
+  const float halfWin = (win - 1) * 0.5f;
+  const float px0 = db.lk_px[gi], py0 = db.lk_py[gi];
+  float nx = db.lk_qx[gi], ny = db.lk_qy[gi];     // running nextPts[ptidx]
+  bool status = true;
+  const int maxLevel = dc.n_levels - 1;
+  const float FLT_SCALE = 1.f / (1 << 20);
+  const int pw = win + 3, jw = win + 1, dw = win + 1;
+
+  for (int level = maxLevel; level >= 0; --level) {
+    const int cols = dc.lvl_w[level], rows = dc.lvl_h[level], pitch = dc.lvl_pitch[level];
+    const unsigned char* I = prevPyr + dc.lvl_off[level];
+    const unsigned char* Jimg = nextPyr + dc.lvl_off[level];
+    const float scl = (float)(1. / (1 << level));
+    float ppx = px0 * scl, ppy = py0 * scl;
+    if (level == maxLevel) { nx = nx * scl; ny = ny * scl; }   // OPTFLOW_USE_INITIAL_FLOW
+    else { nx = nx * 2.f; ny = ny * 2.f; }
+    ppx -= halfWin; ppy -= halfWin;
+    const int ipx = cv_floor(ppx), ipy = cv_floor(ppy);
+    if (ipx < -win || ipx >= cols || ipy < -win || ipy >= rows) {
+      if (level == 0) status = false;
+      continue;
+    }
+    // ---- stage prev patch rows ipy-1 .. ipy+win+1, cols ipx-1 .. ipx+win+1 (reflect101 padding)
+    for (int i = lane; i < pw * pw; i += 32) {
+      int r = i / pw, c = i - r * pw;
+      int yy = reflect101(ipy - 1 + r, rows), xx = reflect101(ipx - 1 + c, cols);
+      s.P[i] = I[(size_t)yy * pitch + xx];
+    }
+    __syncwarp();
+    // ---- Scharr derivatives at the (win+1)^2 tap positions; zero outside the image
+    for (int i = lane; i < dw * dw; i += 32) {
+      int r = i / dw, c = i - r * dw;
+      int X = ipx + c, Y = ipy + r;
+      short dx = 0, dy = 0;
+      if (X >= 0 && X < cols && Y >= 0 && Y < rows) {
+        const unsigned char* p = s.P + (r + 1) * pw + (c + 1);
+        int a00 = p[-pw - 1], a01 = p[-pw], a02 = p[-pw + 1];
+        int a10 = p[-1], a12 = p[1];
+        int a20 = p[pw - 1], a21 = p[pw], a22 = p[pw + 1];
+        dx = (short)(3 * (a02 - a00) + 10 * (a12 - a10) + 3 * (a22 - a20));
+        dy = (short)(3 * (a20 - a00) + 10 * (a21 - a01) + 3 * (a22 - a02));
+      }
+      s.Dx[i] = dx; s.Dy[i] = dy;
+    }
+    __syncwarp();
+    // ---- window of I, Ix, Iy with 14-bit bilinear weights; structure tensor
+    float a = ppx - ipx, bb = ppy - ipy;
+    int iw00 = cv_round((1.f - a) * (1.f - bb) * (1 << 14));
+    int iw01 = cv_round(a * (1.f - bb) * (1 << 14));
+    int iw10 = cv_round((1.f - a) * bb * (1 << 14));
+    int iw11 = (1 << 14) - iw00 - iw01 - iw10;
+    long long sA11 = 0, sA12 = 0, sA22 = 0;
+    for (int i = lane; i < win * win; i += 32) {
+      int y = i / win, x = i - y * win;
+      const unsigned char* p = s.P + (y + 1) * pw + (x + 1);
+      int ival = descale(p[0] * iw00 + p[1] * iw01 + p[pw] * iw10 + p[pw + 1] * iw11, 14 - 5);
+      const short* d = s.Dx + y * dw + x;
+      int ixval = descale(d[0] * iw00 + d[1] * iw01 + d[dw] * iw10 + d[dw + 1] * iw11, 14);
+      d = s.Dy + y * dw + x;
+      int iyval = descale(d[0] * iw00 + d[1] * iw01 + d[dw] * iw10 + d[dw + 1] * iw11, 14);
+      s.I[i] = (short)ival; s.Ix[i] = (short)ixval; s.Iy[i] = (short)iyval;
+      sA11 += (long long)(ixval * ixval);
+      sA12 += (long long)(ixval * iyval);
+      sA22 += (long long)(iyval * iyval);
+    }
+    sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
+    __syncwarp();
+    float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+    float D = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
+    if (minEig < dc.min_eig_thr || D < 1.1920929e-07f) {
+      if (level == 0) status = false;
+      continue;
+    }
+    D = 1.f / D;
+    float qx = nx - halfWin, qy = ny - halfWin;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < dc.max_iter; ++j) {
+      const int iqx = cv_floor(qx), iqy = cv_floor(qy);
+      if (iqx < -win || iqx >= cols || iqy < -win || iqy >= rows) {
+        if (level == 0) status = false;
+        break;
+      }
+      a = qx - iqx; bb = qy - iqy;
+      iw00 = cv_round((1.f - a) * (1.f - bb) * (1 << 14));
+      iw01 = cv_round(a * (1.f - bb) * (1 << 14));
+      iw10 = cv_round((1.f - a) * bb * (1 << 14));
+      iw11 = (1 << 14) - iw00 - iw01 - iw10;
+      for (int i = lane; i < jw * jw; i += 32) {
+        int r = i / jw, c = i - r * jw;
+        int yy = reflect101(iqy + r, rows), xx = reflect101(iqx + c, cols);
+        s.J[i] = Jimg[(size_t)yy * pitch + xx];
+      }
+      __syncwarp();
+      long long sb1 = 0, sb2 = 0;
+      for (int i = lane; i < win * win; i += 32) {
+        int y = i / win, x = i - y * win;
+        const unsigned char* p = s.J + y * jw + x;
+        int diff = descale(p[0] * iw00 + p[1] * iw01 + p[jw] * iw10 + p[jw + 1] * iw11, 14 - 5) - s.I[i];
+        sb1 += (long long)(diff * s.Ix[i]);
+        sb2 += (long long)(diff * s.Iy[i]);
+      }
+      sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
+      __syncwarp();
+      float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+      float dxv = (float)((A12 * b2 - A22 * b1) * D);
+      float dyv = (float)((A12 * b1 - A11 * b2) * D);
+      qx += dxv; qy += dyv;
+      nx = qx + halfWin; ny = qy + halfWin;
+      if ((double)dxv * (double)dxv + (double)dyv * (double)dyv <= (double)dc.eps2) break;
+      if (j > 0 && fabsf(dxv + pdx) < 0.01 && fabsf(dyv + pdy) < 0.01) {
+        nx -= dxv * 0.5f; ny -= dyv * 0.5f;
+        break;
+      }
+      pdx = dxv; pdy = dyv;
+    }
+  }
+  if (lane == 0) {
+    db.lk_qx[gi] = nx; db.lk_qy[gi] = ny;
+    db.lk_status[gi] = status ? 1 : 0;
+  }
+}
+
+int launch_lk(const DevCfg& dc, const DevBuf& db, int prev_slot, int cur_slot, cudaStream_t s) {
+  size_t sm = LK_WARPS * lk_warp_bytes(dc.win);
+  static size_t attr = 0;
+  if (sm > 48 * 1024 && sm > attr) {
+    cudaFuncSetAttribute(lk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+    attr = sm;
+  }
+  lk_kernel<<<dim3((dc.cap + LK_WARPS - 1) / LK_WARPS, dc.B), LK_WARPS * 32, sm, s>>>(dc, db, prev_slot, cur_slot);
+  return 1;
+}

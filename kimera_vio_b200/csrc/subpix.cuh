@@ -1,0 +1,98 @@
+// subpix.cuh -- cv::cornerSubPix / cv::getRectSubPix device code shared by the detector
+// (FeatureDetector.cpp:283-296) and the optional stereo refinement (StereoMatcher.cpp:404-413).
+#pragma once
+#include "common.cuh"
+
+#define SUBPIX_MAX_WIN 12   // window half-size supported (Euroc: 10 -> 21x21 window, 23x23 patch)
+#define SUBPIX_PATCH ((2 * SUBPIX_MAX_WIN + 3) * (2 * SUBPIX_MAX_WIN + 3))
+
+// cv::getRectSubPix(u8 -> f32), win (pw x ph), centre (cxf, cyf); one warp cooperatively.
+static __device__ void get_rect_subpix(const unsigned char* __restrict__ img, int pitch, int W, int H, float cxf,
+                                float cyf, int pw, int ph, float* __restrict__ buf, int lane) {
+  float cx = cxf - (pw - 1) * 0.5f, cy = cyf - (ph - 1) * 0.5f;
+  int ipx = cv_floor(cx), ipy = cv_floor(cy);
+  if (0 <= ipx && ipx + pw < W && 0 <= ipy && ipy + ph < H) {
+    float a = cx - ipx, bq = cy - ipy;
+    a = fmaxf(a, 0.0001f);
+    float a12 = a * (1.f - bq), a22 = a * bq, b1 = 1.f - bq, b2 = bq;
+    double s = (1. - a) / a;
+    const unsigned char* src = img + (size_t)ipy * pitch + ipx;
+    for (int i = lane; i < pw * ph; i += 32) {
+      int r = i / pw, j = i - r * pw;
+      const unsigned char* p0 = src + (size_t)r * pitch;
+      const unsigned char* p1 = p0 + pitch;
+      float t = a12 * p0[j + 1] + a22 * p1[j + 1];
+      float prev;
+      if (j == 0) prev = (1 - a) * (b1 * p0[0] + b2 * p1[0]);
+      else { float tp = a12 * p0[j] + a22 * p1[j]; prev = (float)(tp * s); }
+      buf[i] = prev + t;
+    }
+  } else {
+    // generic border path (getRectSubPix_Cn_ + adjustRect): replicate, plain 4-tap float blend
+    float a = cx - ipx, bq = cy - ipy;
+    float a11 = (1.f - a) * (1.f - bq), a12 = a * (1.f - bq), a21 = (1.f - a) * bq, a22 = a * bq;
+    float b1 = 1.f - bq, b2 = bq;
+    int rx, rw, ry, rh;
+    if (ipx >= 0) rx = 0; else { rx = -ipx; if (rx > pw) rx = pw; }
+    if (ipx < W - pw) rw = pw; else { rw = W - ipx - 1; if (rw < 0) rw = 0; }
+    if (ipy >= 0) ry = 0; else ry = -ipy;
+    if (ipy < H - ph) rh = ph; else { rh = H - ipy - 1; if (rh < 0) rh = 0; }
+    for (int i = lane; i < pw * ph; i += 32) {
+      int r = i / pw, j = i - r * pw;
+      int y0 = clampi(ipy + r, 0, H - 1);
+      int y1 = (r < ry || r >= rh) ? y0 : clampi(ipy + r + 1, 0, H - 1);
+      const unsigned char* p0 = img + (size_t)y0 * pitch;
+      const unsigned char* p1 = img + (size_t)y1 * pitch;
+      float v;
+      if (j < rx) { int xc = clampi(ipx + rx, 0, W - 1); v = p0[xc] * b1 + p1[xc] * b2; }
+      else if (j >= rw) { int xc = clampi(ipx + rw, 0, W - 1); v = p0[xc] * b1 + p1[xc] * b2; }
+      else {
+        int x0 = clampi(ipx + j, 0, W - 1), x1 = clampi(ipx + j + 1, 0, W - 1);
+        v = (p0[x0] * a11 + p0[x1] * a12) + (p1[x0] * a21 + p1[x1] * a22);   // order pinned against cv2 (scratch probe: 100% bit-exact)
+      }
+      buf[i] = v;
+    }
+  }
+}
+
+// Refines (x, y) in place; returns through pointers. One warp.
+static __device__ void corner_subpix_warp(const unsigned char* __restrict__ img, int pitch, int W, int H, int win,
+                                   int max_iters, double eps2, const float* __restrict__ gmask,
+                                   float* __restrict__ buf, float* px, float* py, int lane) {
+  const int ww = 2 * win + 1, pw = ww + 2;
+  const float cTx = *px, cTy = *py;
+  float cIx = cTx, cIy = cTy;
+  int iter = 0;
+  double err = 0;
+  do {
+    get_rect_subpix(img, pitch, W, H, cIx, cIy, pw, pw, buf, lane);
+    __syncwarp();
+    double a = 0, bsum = 0, c = 0, bb1 = 0, bb2 = 0;
+    for (int k = lane; k < ww * ww; k += 32) {
+      int i = k / ww, j = k - i * ww;
+      const float* sp = buf + (i + 1) * pw + (j + 1);
+      double m = gmask[k];
+      double tgx = sp[1] - sp[-1];
+      double tgy = sp[pw] - sp[-pw];
+      double gxx = tgx * tgx * m, gxy = tgx * tgy * m, gyy = tgy * tgy * m;
+      double pxx = j - win, pyy = i - win;
+      a += gxx; bsum += gxy; c += gyy;
+      bb1 += gxx * pxx + gxy * pyy;
+      bb2 += gxy * pxx + gyy * pyy;
+    }
+    a = warp_sum_d(a); bsum = warp_sum_d(bsum); c = warp_sum_d(c);
+    bb1 = warp_sum_d(bb1); bb2 = warp_sum_d(bb2);
+    __syncwarp();
+    double det = a * c - bsum * bsum;
+    if (fabs(det) <= 2.220446049250313e-16 * 2.220446049250313e-16) break;
+    double scale = 1.0 / det;
+    float nx = (float)(cIx + c * scale * bb1 - bsum * scale * bb2);
+    float ny = (float)(cIy - bsum * scale * bb1 + a * scale * bb2);
+    err = (nx - cIx) * (nx - cIx) + (ny - cIy) * (ny - cIy);
+    cIx = nx; cIy = ny;
+    if (cIx < 0 || cIx >= W || cIy < 0 || cIy >= H) break;
+  } while (++iter < max_iters && err > eps2);
+  if (fabsf(cIx - cTx) > win || fabsf(cIy - cTy) > win) { cIx = cTx; cIy = cTy; }
+  *px = cIx; *py = cIy;
+}
+

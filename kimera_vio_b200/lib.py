@@ -1,0 +1,428 @@
+"""ctypes binding of libkvfe.so (include/kvfe.h).  There is no fallback: if the library is missing or
+no CUDA device is usable, loading / context creation raises."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+from typing import Optional, Sequence
+
+import numpy as np
+
+from .params import CameraParams, FrontendParams
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libkvfe.so")
+
+
+class KvfeError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [
+        ("width", C.c_int32), ("height", C.c_int32), ("batch", C.c_int32), ("max_keypoints", C.c_int32),
+        ("klt_win_size", C.c_int32), ("klt_max_iter", C.c_int32), ("klt_max_level", C.c_int32),
+        ("klt_eps", C.c_double),
+        ("max_feature_track_age", C.c_int32),
+        ("min_nr_mono_inliers", C.c_int32), ("min_nr_stereo_inliers", C.c_int32),
+        ("ransac_threshold_mono", C.c_double), ("ransac_threshold_stereo", C.c_double),
+        ("ransac_max_iterations", C.c_int32),
+        ("ransac_probability", C.c_double),
+        ("ransac_randomize", C.c_int32),
+        ("ransac_use_1point_stereo", C.c_int32), ("ransac_use_2point_mono", C.c_int32),
+        ("pose_2d2d_algorithm", C.c_int32),
+        ("optical_flow_predictor_type", C.c_int32),
+        ("disparity_threshold", C.c_double),
+        ("rnd_libstdcxx", C.c_int32),
+        ("max_features_per_frame", C.c_int32),
+        ("enable_subpixel_corner_refinement", C.c_int32),
+        ("subpix_max_iters", C.c_int32),
+        ("subpix_epsilon", C.c_double),
+        ("subpix_window_size", C.c_int32), ("subpix_zero_zone", C.c_int32),
+        ("enable_non_max_suppression", C.c_int32),
+        ("non_max_suppression_type", C.c_int32),
+        ("min_distance", C.c_int32),
+        ("max_nr_keypoints_before_anms", C.c_int32),
+        ("nr_horizontal_bins", C.c_int32), ("nr_vertical_bins", C.c_int32),
+        ("binning_mask", C.c_uint8 * 64),
+        ("quality_level", C.c_double),
+        ("block_size", C.c_int32),
+        ("use_harris_detector", C.c_int32),
+        ("k", C.c_double),
+        ("sobel_cpu_tail_start", C.c_int32),
+        ("tolerance_template_matching", C.c_double),
+        ("templ_cols", C.c_int32), ("templ_rows", C.c_int32), ("stripe_extra_rows", C.c_int32),
+        ("min_point_dist", C.c_double), ("max_point_dist", C.c_double),
+        ("subpixel_refinement_stereo", C.c_int32),
+        ("min_intra_keyframe_time_ns", C.c_int64), ("max_intra_keyframe_time_ns", C.c_int64),
+        ("min_number_features", C.c_int32),
+        ("use_stereo_tracking", C.c_int32), ("use_ransac", C.c_int32),
+        ("max_disparity_since_lkf", C.c_double),
+    ]
+
+
+class Rig(C.Structure):
+    _fields_ = [("K_left", C.c_double * 9), ("K_right", C.c_double * 9),
+                ("D_left", C.c_double * 4), ("D_right", C.c_double * 4),
+                ("R1", C.c_double * 9), ("R2", C.c_double * 9),
+                ("P1", C.c_double * 12), ("P2", C.c_double * 12),
+                ("baseline", C.c_double)]
+
+
+class PacketHeader(C.Structure):
+    _fields_ = [("n", C.c_int32), ("is_keyframe", C.c_int32), ("mono_status", C.c_int32),
+                ("stereo_status", C.c_int32), ("n_smart", C.c_int32), ("nr_tracked", C.c_int32),
+                ("nr_mono_putatives", C.c_int32), ("nr_mono_inliers", C.c_int32),
+                ("nr_stereo_putatives", C.c_int32), ("nr_stereo_inliers", C.c_int32),
+                ("nr_valid_rkp", C.c_int32), ("nr_no_left_rect_rkp", C.c_int32),
+                ("nr_no_right_rect_rkp", C.c_int32), ("nr_no_depth_rkp", C.c_int32),
+                ("nr_failed_arun_rkp", C.c_int32), ("mode", C.c_int32),
+                ("frame_id", C.c_int64), ("timestamp", C.c_int64),
+                ("lkf_T_k_mono", C.c_double * 12), ("lkf_T_k_stereo", C.c_double * 12),
+                ("info_stereo", C.c_double * 9), ("median_disparity", C.c_double)]
+
+
+class StereoOut(C.Structure):
+    _fields_ = [("left_status", C.c_void_p), ("left_rect_x", C.c_void_p), ("left_rect_y", C.c_void_p),
+                ("right_status", C.c_void_p), ("right_rect_x", C.c_void_p), ("right_rect_y", C.c_void_p),
+                ("depth", C.c_void_p), ("points_3d", C.c_void_p), ("right_x", C.c_void_p),
+                ("right_y", C.c_void_p)]
+
+
+# packet array names in kvfe_packet_offsets() order, with dtype and per-keypoint width
+PACKET_FIELDS = [("kp_x", np.float32, 1), ("kp_y", np.float32, 1), ("landmark", np.int64, 1),
+                 ("age", np.int32, 1), ("score", np.float64, 1), ("versor", np.float64, 3),
+                 ("left_status", np.int32, 1), ("left_rect_x", np.float32, 1), ("left_rect_y", np.float32, 1),
+                 ("right_status", np.int32, 1), ("right_rect_x", np.float32, 1), ("right_rect_y", np.float32, 1),
+                 ("depth", np.float64, 1), ("point3d", np.float64, 3), ("right_x", np.float32, 1),
+                 ("right_y", np.float32, 1), ("smart_lmk", np.int64, 1), ("smart_uL", np.float64, 1),
+                 ("smart_uR", np.float64, 1), ("smart_v", np.float64, 1)]
+
+_lib = None
+
+
+def load() -> C.CDLL:
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise KvfeError("libkvfe.so not built (run `python -m kimera_vio_b200.build`); there is no CPU fallback")
+    lib = C.CDLL(LIB_PATH)
+    lib.kvfe_last_error.restype = C.c_char_p
+    lib.kvfe_last_error.argtypes = [C.c_void_p]
+    lib.kvfe_packet_bytes.restype = C.c_size_t
+    lib.kvfe_packet_bytes.argtypes = [C.c_void_p]
+    lib.kvfe_cuda_stream.restype = C.c_void_p
+    lib.kvfe_cuda_stream.argtypes = [C.c_void_p]
+    lib.kvfe_config_default.argtypes = [C.POINTER(Config)]
+    lib.kvfe_config_default.restype = None
+    lib.kvfe_destroy.argtypes = [C.c_void_p]
+    lib.kvfe_destroy.restype = None
+    _lib = lib
+    return lib
+
+
+def _p(a: Optional[np.ndarray]):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def make_config(p: FrontendParams, width: int, height: int, batch: int = 1, max_keypoints: int = 0,
+                rnd_libstdcxx: str = "lemire", sobel_cpu_tail_start: int = -1) -> Config:
+    c = Config()
+    load().kvfe_config_default(C.byref(c))
+    c.width, c.height, c.batch, c.max_keypoints = width, height, batch, max_keypoints
+    c.klt_win_size, c.klt_max_iter, c.klt_max_level, c.klt_eps = p.klt_win_size, p.klt_max_iter, p.klt_max_level, p.klt_eps
+    c.max_feature_track_age = p.max_feature_track_age
+    c.min_nr_mono_inliers, c.min_nr_stereo_inliers = p.min_nr_mono_inliers, p.min_nr_stereo_inliers
+    c.ransac_threshold_mono, c.ransac_threshold_stereo = p.ransac_threshold_mono, p.ransac_threshold_stereo
+    c.ransac_max_iterations, c.ransac_probability = p.ransac_max_iterations, p.ransac_probability
+    c.ransac_randomize = int(p.ransac_randomize)
+    c.ransac_use_1point_stereo, c.ransac_use_2point_mono = int(p.ransac_use_1point_stereo), int(p.ransac_use_2point_mono)
+    c.pose_2d2d_algorithm = p.pose_2d2d_algorithm
+    c.optical_flow_predictor_type = p.optical_flow_predictor_type
+    c.disparity_threshold = p.disparity_threshold
+    c.rnd_libstdcxx = 0 if rnd_libstdcxx == "lemire" else 1
+    c.max_features_per_frame = p.max_features_per_frame
+    c.enable_subpixel_corner_refinement = int(p.enable_subpixel_corner_refinement)
+    c.subpix_max_iters, c.subpix_epsilon = p.subpix_max_iters, p.subpix_epsilon
+    c.subpix_window_size, c.subpix_zero_zone = p.subpix_window_size, p.subpix_zero_zone
+    c.enable_non_max_suppression = int(p.enable_non_max_suppression)
+    c.non_max_suppression_type = p.non_max_suppression_type
+    c.min_distance = p.min_distance
+    c.max_nr_keypoints_before_anms = p.max_nr_keypoints_before_anms
+    c.nr_horizontal_bins, c.nr_vertical_bins = p.nr_horizontal_bins, p.nr_vertical_bins
+    m = np.asarray(p.binning_mask, np.float64).reshape(-1)
+    for i in range(64):
+        c.binning_mask[i] = int(m[i]) if i < m.size else 0
+    c.quality_level, c.block_size = p.quality_level, p.block_size
+    c.use_harris_detector, c.k = int(p.use_harris_detector), p.k
+    c.sobel_cpu_tail_start = sobel_cpu_tail_start
+    c.tolerance_template_matching = p.tolerance_template_matching
+    c.templ_cols, c.templ_rows, c.stripe_extra_rows = p.templ_cols, p.templ_rows, p.stripe_extra_rows
+    c.min_point_dist, c.max_point_dist = p.min_point_dist, p.max_point_dist
+    c.subpixel_refinement_stereo = int(p.subpixel_refinement_stereo)
+    c.min_intra_keyframe_time_ns, c.max_intra_keyframe_time_ns = p.min_intra_keyframe_time_ns, p.max_intra_keyframe_time_ns
+    c.min_number_features = p.min_number_features
+    c.use_stereo_tracking, c.use_ransac = int(p.use_stereo_tracking), int(p.use_ransac)
+    c.max_disparity_since_lkf = p.max_disparity_since_lkf
+    return c
+
+
+def make_rig(left: CameraParams, right: CameraParams, R1, R2, P1, P2, baseline: float) -> Rig:
+    r = Rig()
+    r.K_left[:] = list(np.asarray(left.K, np.float64).reshape(-1))
+    r.K_right[:] = list(np.asarray(right.K, np.float64).reshape(-1))
+    r.D_left[:] = list(np.asarray(left.distortion, np.float64)[:4])
+    r.D_right[:] = list(np.asarray(right.distortion, np.float64)[:4])
+    r.R1[:] = list(np.asarray(R1, np.float64).reshape(-1))
+    r.R2[:] = list(np.asarray(R2, np.float64).reshape(-1))
+    r.P1[:] = list(np.asarray(P1, np.float64).reshape(-1))
+    r.P2[:] = list(np.asarray(P2, np.float64).reshape(-1))
+    r.baseline = float(baseline)
+    return r
+
+
+class Context:
+    """Owns a kvfe_ctx*.  All methods map 1:1 onto the C-ABI entry points."""
+
+    def __init__(self, cfg: Config, rig: Rig):
+        self.lib = load()
+        self.cfg = cfg
+        h = C.c_void_p()
+        rc = self.lib.kvfe_create(C.byref(cfg), C.byref(rig), C.byref(h))
+        if rc != 0:
+            raise KvfeError("kvfe_create failed (%d): %s" % (rc, self.lib.kvfe_last_error(None).decode()))
+        self.h = h
+        self.W, self.H, self.B = cfg.width, cfg.height, cfg.batch
+        self.cap = self.lib.kvfe_max_keypoints(self.h)
+        self.packet_bytes = int(self.lib.kvfe_packet_bytes(self.h))
+        offs = (C.c_size_t * 20)()
+        self.lib.kvfe_packet_offsets(self.h, offs, 20)
+        self.packet_offsets = [int(o) for o in offs]
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kvfe_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc != 0:
+            raise KvfeError("libkvfe error %d: %s" % (rc, self.lib.kvfe_last_error(self.h).decode()))
+
+    @property
+    def launches(self) -> int:
+        return int(self.lib.kvfe_kernel_launches(self.h))
+
+    # ---- stage level --------------------------------------------------------------------------
+    def rectify_pair(self, left: np.ndarray, right: np.ndarray):
+        left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+        ol, orr = np.empty_like(left), np.empty_like(right)
+        self._chk(self.lib.kvfe_rectify_pair(self.h, _p(left), _p(right), C.c_size_t(left.strides[0]), _p(ol), _p(orr),
+                                             C.c_size_t(ol.strides[0])))
+        return ol, orr
+
+    def rectify_maps(self, cam: int):
+        mx, my = np.empty((self.H, self.W), np.float32), np.empty((self.H, self.W), np.float32)
+        self._chk(self.lib.kvfe_rectify_maps(self.h, cam, _p(mx), _p(my)))
+        return mx, my
+
+    def pyramid(self, img: np.ndarray):
+        img = np.ascontiguousarray(img)
+        buf = np.empty(self.W * self.H, np.uint8)
+        n = C.c_int()
+        self._chk(self.lib.kvfe_pyramid(self.h, _p(img), C.c_size_t(img.strides[0]), _p(buf), C.c_size_t(buf.size), C.byref(n)))
+        out, o, w, h = [], 0, self.W, self.H
+        for _ in range(1, n.value):
+            w, h = (w + 1) // 2, (h + 1) // 2
+            out.append(buf[o:o + w * h].reshape(h, w).copy())
+            o += w * h
+        return out
+
+    def min_eigen_response(self, img: np.ndarray) -> np.ndarray:
+        img = np.ascontiguousarray(img)
+        out = np.empty((self.H, self.W), np.float32)
+        self._chk(self.lib.kvfe_min_eigen_response(self.h, _p(img), C.c_size_t(img.strides[0]), _p(out)))
+        return out
+
+    def _existing(self, kps, lmks):
+        n = len(lmks)
+        ex = np.ascontiguousarray(np.asarray([k[0] for k in kps], np.float32)) if n else np.zeros(1, np.float32)
+        ey = np.ascontiguousarray(np.asarray([k[1] for k in kps], np.float32)) if n else np.zeros(1, np.float32)
+        el = np.ascontiguousarray(np.asarray(lmks, np.int64)) if n else np.zeros(1, np.int64)
+        return ex, ey, el, n
+
+    def detect(self, img: np.ndarray, kps=(), lmks=(), need: int = 0):
+        img = np.ascontiguousarray(img)
+        ex, ey, el, n = self._existing(kps, lmks)
+        ox, oy = np.empty(self.cap, np.float32), np.empty(self.cap, np.float32)
+        m = C.c_int()
+        self._chk(self.lib.kvfe_detect(self.h, _p(img), C.c_size_t(img.strides[0]), _p(ex), _p(ey), _p(el), n, need,
+                                       _p(ox), _p(oy), C.byref(m)))
+        return np.stack([ox[:m.value], oy[:m.value]], 1)
+
+    def detect_raw(self, img: np.ndarray, kps=(), lmks=()):
+        img = np.ascontiguousarray(img)
+        ex, ey, el, n = self._existing(kps, lmks)
+        cap = self.cfg.max_nr_keypoints_before_anms
+        ox, oy, orr = np.empty(cap, np.float32), np.empty(cap, np.float32), np.empty(cap, np.float32)
+        m = C.c_int()
+        self._chk(self.lib.kvfe_detect_raw(self.h, _p(img), C.c_size_t(img.strides[0]), _p(ex), _p(ey), _p(el), n,
+                                           _p(ox), _p(oy), _p(orr), C.byref(m)))
+        return np.stack([ox[:m.value], oy[:m.value]], 1), orr[:m.value].copy()
+
+    def track(self, ref_img, cur_img, ref_R_cur, ref_xy):
+        ref_img, cur_img = np.ascontiguousarray(ref_img), np.ascontiguousarray(cur_img)
+        xy = np.asarray(ref_xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        rx, ry = np.ascontiguousarray(xy[:, 0]), np.ascontiguousarray(xy[:, 1])
+        R = np.ascontiguousarray(np.asarray(ref_R_cur, np.float64).reshape(9))
+        px, py, cx, cy = (np.zeros(max(n, 1), np.float32) for _ in range(4))
+        st = np.zeros(max(n, 1), np.uint8)
+        self._chk(self.lib.kvfe_track(self.h, _p(ref_img), _p(cur_img), C.c_size_t(ref_img.strides[0]), _p(R), _p(rx),
+                                      _p(ry), n, _p(px), _p(py), _p(cx), _p(cy), _p(st)))
+        return np.stack([px[:n], py[:n]], 1), np.stack([cx[:n], cy[:n]], 1), st[:n].copy()
+
+    def undistort_keypoints(self, cam: int, use_R: bool, use_P: bool, xy):
+        xy = np.asarray(xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        x, y = np.ascontiguousarray(xy[:, 0]), np.ascontiguousarray(xy[:, 1])
+        ox, oy = np.zeros(max(n, 1), np.float32), np.zeros(max(n, 1), np.float32)
+        self._chk(self.lib.kvfe_undistort_keypoints(self.h, cam, int(use_R), int(use_P), _p(x), _p(y), n, _p(ox), _p(oy)))
+        return np.stack([ox[:n], oy[:n]], 1)
+
+    def bearing_vectors(self, xy):
+        xy = np.asarray(xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        x, y = np.ascontiguousarray(xy[:, 0]), np.ascontiguousarray(xy[:, 1])
+        v = np.zeros((max(n, 1), 3), np.float64)
+        self._chk(self.lib.kvfe_bearing_vectors(self.h, _p(x), _p(y), n, _p(v)))
+        return v[:n]
+
+    def sparse_stereo(self, left, right, kps_xy, versors):
+        left, right = np.ascontiguousarray(left), np.ascontiguousarray(right)
+        xy = np.asarray(kps_xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        x, y = np.ascontiguousarray(xy[:, 0]), np.ascontiguousarray(xy[:, 1])
+        vs = np.ascontiguousarray(np.asarray(versors, np.float64).reshape(-1, 3))
+        res = dict(left_status=np.zeros(n, np.int32), left_rect_x=np.zeros(n, np.float32),
+                   left_rect_y=np.zeros(n, np.float32), right_status=np.zeros(n, np.int32),
+                   right_rect_x=np.zeros(n, np.float32), right_rect_y=np.zeros(n, np.float32),
+                   depth=np.zeros(n, np.float64), points_3d=np.zeros((n, 3), np.float64),
+                   right_x=np.zeros(n, np.float32), right_y=np.zeros(n, np.float32))
+        so = StereoOut(*[res[k].ctypes.data for k, _ in StereoOut._fields_])
+        rl, rr = np.empty_like(left), np.empty_like(right)
+        self._chk(self.lib.kvfe_sparse_stereo(self.h, _p(left), _p(right), C.c_size_t(left.strides[0]), _p(x), _p(y),
+                                              _p(vs), n, C.byref(so), _p(rl), _p(rr), C.c_size_t(rl.strides[0])))
+        res["left_rect"], res["right_rect"] = rl, rr
+        return res
+
+    def ransac_mono(self, f_ref, f_cur, R12=None):
+        a = np.ascontiguousarray(np.asarray(f_ref, np.float64).reshape(-1, 3))
+        b = np.ascontiguousarray(np.asarray(f_cur, np.float64).reshape(-1, 3))
+        n = len(a)
+        R = None if R12 is None else np.ascontiguousarray(np.asarray(R12, np.float64).reshape(9))
+        inl = np.zeros(max(n, 1), np.int32)
+        m, st = C.c_int(), C.c_int()
+        pose = np.zeros(12)
+        self._chk(self.lib.kvfe_ransac_mono(self.h, _p(a), _p(b), n, _p(R), _p(inl), C.byref(m), _p(pose), C.byref(st)))
+        return st.value, pose.reshape(3, 4), inl[:m.value].tolist()
+
+    def ransac_stereo_3pt(self, p_ref, p_cur):
+        a = np.ascontiguousarray(np.asarray(p_ref, np.float64).reshape(-1, 3))
+        b = np.ascontiguousarray(np.asarray(p_cur, np.float64).reshape(-1, 3))
+        n = len(a)
+        inl = np.zeros(max(n, 1), np.int32)
+        m, st = C.c_int(), C.c_int()
+        pose = np.zeros(12)
+        self._chk(self.lib.kvfe_ransac_stereo_3pt(self.h, _p(a), _p(b), n, _p(inl), C.byref(m), _p(pose), C.byref(st)))
+        return st.value, pose.reshape(3, 4), inl[:m.value].tolist()
+
+    def ransac_stereo_1pt(self, ref_left, ref_right, cur_left, cur_right, p_ref, p_cur, R):
+        arrs = [np.ascontiguousarray(np.asarray(v, np.float32).reshape(-1, 2)) for v in (ref_left, ref_right, cur_left, cur_right)]
+        a = np.ascontiguousarray(np.asarray(p_ref, np.float64).reshape(-1, 3))
+        b = np.ascontiguousarray(np.asarray(p_cur, np.float64).reshape(-1, 3))
+        n = len(a)
+        Rm = np.ascontiguousarray(np.asarray(R, np.float64).reshape(9))
+        inl = np.zeros(max(n, 1), np.int32)
+        m, st = C.c_int(), C.c_int()
+        pose, info = np.zeros(12), np.zeros(9)
+        self._chk(self.lib.kvfe_ransac_stereo_1pt(self.h, _p(arrs[0]), _p(arrs[1]), _p(arrs[2]), _p(arrs[3]), _p(a), _p(b),
+                                                  n, _p(Rm), _p(inl), C.byref(m), _p(pose), _p(info), C.byref(st)))
+        return st.value, pose.reshape(3, 4), inl[:m.value].tolist(), info.reshape(3, 3)
+
+    # ---- frame level --------------------------------------------------------------------------
+    def reset(self):
+        self._chk(self.lib.kvfe_frontend_reset(self.h))
+
+    def step(self, lefts: Sequence[np.ndarray], rights: Sequence[np.ndarray], timestamps, kf_R_cur,
+             want_rectified: bool = False):
+        """Host-buffer step (kvfe_frontend_step).  Returns the parsed packets (list of dicts)."""
+        B = self.B
+        assert len(lefts) == B and len(rights) == B
+        lp = (C.c_void_p * B)(*[l.ctypes.data for l in lefts])
+        rp = (C.c_void_p * B)(*[r.ctypes.data for r in rights])
+        ts = np.ascontiguousarray(np.asarray(timestamps, np.int64))
+        Rm = np.ascontiguousarray(np.asarray(kf_R_cur, np.float64).reshape(B, 9))
+        buf = np.empty(B * self.packet_bytes, np.uint8)
+        rl = rr = None
+        rlp = rrp = None
+        if want_rectified:
+            rl = [np.zeros((self.H, self.W), np.uint8) for _ in range(B)]
+            rr = [np.zeros((self.H, self.W), np.uint8) for _ in range(B)]
+            rlp = (C.c_void_p * B)(*[a.ctypes.data for a in rl])
+            rrp = (C.c_void_p * B)(*[a.ctypes.data for a in rr])
+        self._chk(self.lib.kvfe_frontend_step(self.h, lp, rp, C.c_size_t(lefts[0].strides[0]), _p(ts), _p(Rm), _p(buf),
+                                              rlp, rrp, C.c_size_t(self.W)))
+        pk = self.parse_packets(buf)
+        if want_rectified:
+            for b in range(B):
+                pk[b]["left_rect"], pk[b]["right_rect"] = rl[b], rr[b]
+        return pk
+
+    def step_raw(self, lp, rp, pitch, ts, Rm, buf):
+        """Zero-overhead variant for benchmarking: pre-built ctypes pointer arrays / numpy buffers."""
+        return self.lib.kvfe_frontend_step(self.h, lp, rp, C.c_size_t(pitch), _p(ts), _p(Rm), _p(buf), None, None,
+                                           C.c_size_t(0))
+
+    def step_dev(self, left_dev_ptr: int, right_dev_ptr: int, pitch: int, ts: np.ndarray, Rm: np.ndarray):
+        return self.lib.kvfe_frontend_step_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr),
+                                               C.c_size_t(pitch), _p(ts), _p(Rm))
+
+    def sync(self):
+        self._chk(self.lib.kvfe_sync(self.h))
+
+    def read_packets(self):
+        buf = np.empty(self.B * self.packet_bytes, np.uint8)
+        self._chk(self.lib.kvfe_frontend_read_packets(self.h, _p(buf)))
+        return self.parse_packets(buf)
+
+    def parse_packets(self, buf: np.ndarray):
+        out = []
+        for b in range(self.B):
+            raw = buf[b * self.packet_bytes:(b + 1) * self.packet_bytes]
+            h = PacketHeader.from_buffer_copy(raw[:C.sizeof(PacketHeader)].tobytes())
+            d = {k: getattr(h, k) for k, _ in PacketHeader._fields_ if not k.startswith("lkf") and k != "info_stereo"}
+            d["lkf_T_k_mono"] = np.array(h.lkf_T_k_mono).reshape(3, 4)
+            d["lkf_T_k_stereo"] = np.array(h.lkf_T_k_stereo).reshape(3, 4)
+            d["info_stereo"] = np.array(h.info_stereo).reshape(3, 3)
+            n = h.n
+            for (name, dt, w), off in zip(PACKET_FIELDS, self.packet_offsets):
+                cnt = (h.n_smart if name.startswith("smart") else n) * w
+                a = np.frombuffer(raw.tobytes(), dtype=dt, count=cnt, offset=off).copy()
+                d[name] = a.reshape(-1, 3) if w == 3 else a
+            out.append(d)
+        return out
+
+    def debug_lk(self, stream: int = 0):
+        px, py, nx, ny = (np.zeros(self.cap, np.float32) for _ in range(4))
+        st = np.zeros(self.cap, np.uint8)
+        n = C.c_int()
+        self._chk(self.lib.kvfe_debug_lk(self.h, stream, _p(px), _p(py), _p(nx), _p(ny), _p(st), C.byref(n)))
+        m = n.value
+        return np.stack([px[:m], py[:m]], 1), np.stack([nx[:m], ny[:m]], 1), st[:m].copy()

@@ -208,7 +208,8 @@ def relpose_score(R12, t12, f1, f2) -> float:
     Rt = R12.T
     tinv = -matvec3(Rt, t12)
     r1 = X
-    r2 = matvec3(Rt, X) + tinv * 1.0
+    # inverseSolution (3x4) * p_hom: Eigen's size-4 redux is (a0 + a1) + (a2 + a3)
+    r2 = np.array([(Rt[k, 0] * X[0] + Rt[k, 1] * X[1]) + (Rt[k, 2] * X[2] + tinv[k] * 1.0) for k in range(3)])
     r1 = r1 / norm3(r1)
     r2 = r2 / norm3(r2)
     return (1.0 - dot3(f1, r1)) + (1.0 - dot3(f2, r2))

@@ -1,0 +1,124 @@
+"""Whole-sequence parity: the device-resident front-end FSM (kvfe_frontend_step, batch of streams)
+against the oracle's StereoFrontend on the same images and IMU rotations -- every output packet
+field, frame by frame (keypoints, landmark ids, ages, versors, stereo statuses, depths, 3-D points,
+tracking statuses, RANSAC inlier counts, keyframe decisions)."""
+import numpy as np
+import pytest
+
+import helpers as H
+from kimera_vio_b200.params import CameraParams, FrontendParams
+from oracle import frontend as ofe
+from oracle.rig import StereoRig
+
+pytestmark = pytest.mark.gpu
+TOL_PX = 1e-3
+
+
+def compare_packet(tag, pk, o, strict=True):
+    """Returns a dict of mismatch counters (all zero == parity)."""
+    fr = o.frame
+    lf = fr.left_frame
+    n = len(lf.keypoints)
+    rec = dict(tag=tag, n_gpu=int(pk["n"]), n_ref=n, kf_gpu=int(pk["is_keyframe"]), kf_ref=int(o.is_keyframe))
+    if pk["n"] != n or bool(pk["is_keyframe"]) != bool(o.is_keyframe):
+        rec["fatal"] = 1
+        return rec
+    kp = np.array(lf.keypoints, np.float32).reshape(-1, 2)
+    g = np.stack([pk["kp_x"], pk["kp_y"]], 1)
+    rec["kp_max_err"] = float(np.abs(g - kp).max()) if n else 0.0
+    rec["kp_over_tol"] = int((np.abs(g - kp).max(axis=1) > TOL_PX).sum()) if n else 0
+    rec["lmk_mismatch"] = int((pk["landmark"] != np.array(lf.landmarks, np.int64)).sum())
+    rec["age_mismatch"] = int((pk["age"] != np.array(lf.landmarks_age)).sum())
+    rec["versor_max_err"] = float(np.abs(pk["versor"] - np.array(lf.versors).reshape(-1, 3)).max()) if n else 0.0
+    rec["mono_status"] = (int(pk["mono_status"]), int(o.mono_status))
+    rec["stereo_status"] = (int(pk["stereo_status"]), int(o.stereo_status))
+    if o.is_keyframe:
+        ls = np.array([s for s, _ in fr.left_keypoints_rectified])
+        lx = np.array([q for _, q in fr.left_keypoints_rectified], np.float32).reshape(-1, 2)
+        rs = np.array([s for s, _ in fr.right_keypoints_rectified])
+        rx = np.array([q for _, q in fr.right_keypoints_rectified], np.float32).reshape(-1, 2)
+        rec["lstat_mismatch"] = int((pk["left_status"] != ls).sum())
+        rec["lrect_max_err"] = float(np.abs(np.stack([pk["left_rect_x"], pk["left_rect_y"]], 1) - lx).max())
+        rec["rstat_mismatch"] = int((pk["right_status"] != rs).sum())
+        rec["rrect_max_err"] = float(np.abs(np.stack([pk["right_rect_x"], pk["right_rect_y"]], 1) - rx).max())
+        d = np.array(fr.keypoints_depth)
+        rec["depth_max_rel"] = float((np.abs(pk["depth"] - d) / np.maximum(np.abs(d), 1e-9)).max())
+        rec["p3d_max_err"] = float(np.abs(pk["point3d"] - np.array(fr.keypoints_3d).reshape(-1, 3)).max())
+        rk = np.array(fr.right_frame.keypoints, np.float32).reshape(-1, 2)
+        rec["right_raw_max_err"] = float(np.abs(np.stack([pk["right_x"], pk["right_y"]], 1) - rk).max())
+        sm = o.smart_measurements
+        rec["n_smart"] = (int(pk["n_smart"]), len(sm))
+        if pk["n_smart"] == len(sm) and len(sm):
+            sl = np.array([m[0] for m in sm], np.int64)
+            rec["smart_lmk_mismatch"] = int((pk["smart_lmk"] != sl).sum())
+            uR = np.array([m[2] for m in sm])
+            rec["smart_nan_mismatch"] = int((np.isnan(pk["smart_uR"]) != np.isnan(uR)).sum())
+    return rec
+
+
+def packet_ok(rec):
+    if rec.get("fatal"):
+        return False
+    ok = rec["kp_over_tol"] == 0 and rec["lmk_mismatch"] == 0 and rec["age_mismatch"] == 0
+    ok &= rec["versor_max_err"] < 1e-5
+    ok &= rec["mono_status"][0] == rec["mono_status"][1] and rec["stereo_status"][0] == rec["stereo_status"][1]
+    if "lstat_mismatch" in rec:
+        ok &= rec["lstat_mismatch"] == 0 and rec["rstat_mismatch"] == 0
+        ok &= rec["lrect_max_err"] <= 2e-3 and rec["rrect_max_err"] <= TOL_PX
+        ok &= rec["depth_max_rel"] < 1e-4 and rec["right_raw_max_err"] <= 2.0
+        ok &= rec["n_smart"][0] == rec["n_smart"][1] and rec.get("smart_lmk_mismatch", 0) == 0
+        ok &= rec.get("smart_nan_mismatch", 0) == 0
+    return bool(ok)
+
+
+def run_sequence(ctx, oracles, frames_per_stream, rots_per_stream, tag):
+    """frames_per_stream[b][k] = (left, right, ts); rots = keyframe_R_cur provider(b, k, lkf_k)."""
+    B = len(oracles)
+    lkf = [0] * B
+    n_frames = len(frames_per_stream[0])
+    all_ok = True
+    for k in range(n_frames):
+        lefts = [frames_per_stream[b][k][0] for b in range(B)]
+        rights = [frames_per_stream[b][k][1] for b in range(B)]
+        ts = [frames_per_stream[b][k][2] for b in range(B)]
+        Rs = [rots_per_stream(b, k, lkf[b]) for b in range(B)]
+        pks = ctx.step(lefts, rights, ts, np.array(Rs))
+        for b in range(B):
+            sf = ofe.StereoFrame.make(k, ts[b], lefts[b], rights[b], oracles[b].rig)
+            o = oracles[b].spin(sf, Rs[b])
+            rec = compare_packet("%s/s%d/f%d" % (tag, b, k), pks[b], o)
+            rec["ok"] = packet_ok(rec)
+            H.diag("sequence", **rec)
+            all_ok &= rec["ok"]
+            if o.is_keyframe:
+                lkf[b] = k
+    return all_ok
+
+
+def test_sequence_golden_euroc():
+    """5 real Euroc pairs (tests/golden), one stream."""
+    p, rig, ctx = H.euroc_setup(batch=1)
+    g, lefts, rights = H.golden()
+    orig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    fe = ofe.StereoFrontend(p, orig)
+    ts = [int(t) for t in g["timestamps"]]
+    frames = [[(lefts[i], rights[i], ts[i]) for i in range(len(lefts))]]
+    ok = run_sequence(ctx, [fe], frames, lambda b, k, l: g["seq_R_%d" % k], "golden")
+    ctx.close()
+    assert ok
+
+
+def test_sequence_synthetic_batch():
+    """Two independent synthetic streams in one batch, 14 frames each (several keyframes)."""
+    B, N = 2, 14
+    p, rig, ctx = H.euroc_setup(batch=B)
+    orig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    streams, frames = [], []
+    for b in range(B):
+        s, fr = H.synth_frames(N, seed=20240 + 1000 * b)
+        streams.append(s)
+        frames.append([(f.left, f.right, f.timestamp) for f in fr])
+    oracles = [ofe.StereoFrontend(p, orig) for _ in range(B)]
+    ok = run_sequence(ctx, oracles, frames, lambda b, k, l: streams[b].kf_rotation(l, k), "synth")
+    ctx.close()
+    assert ok
