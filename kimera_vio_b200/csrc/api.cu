@@ -154,8 +154,10 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   const int nbins = c.nr_horizontal_bins * c.nr_vertical_bins;
   int cap = c.max_keypoints;
   if (cap <= 0) {
-    cap = c.enable_non_max_suppression ? c.max_features_per_frame + nbins + 16
-                                       : std::max(c.max_nr_keypoints_before_anms, c.max_features_per_frame) + 16;
+    // a frame holds the survivors of the previous frame (<= max_features + nbins valid ones, and the
+    // RANSAC outliers stay in place with landmark -1) plus up to need + nbins new corners
+    cap = c.enable_non_max_suppression ? 2 * (c.max_features_per_frame + nbins) + 16
+                                       : 2 * std::max(c.max_nr_keypoints_before_anms, c.max_features_per_frame) + 16;
   }
   cap = (int)round_up(cap, 32);
   dc.cap = cap;

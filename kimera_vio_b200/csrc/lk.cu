@@ -8,7 +8,8 @@
 //      the image, like the zero-padded derivative buffer of OpenCV) -- no derivative image is ever
 //      written to HBM;
 //   2. the fixed-point window I / Ix / Iy (14-bit bilinear weights) and the structure tensor are
-//      formed (integer sums are exact: accumulated in int64, OpenCV accumulates in float);
+//      formed; the float accumulations reproduce OpenCV's SIMD128 lane order exactly (bit-exact
+//      with cv2 for windows that are a multiple of 8, e.g. the Euroc 24);
 //   3. <= maxCount Gauss-Newton iterations, each staging a (win+1)^2 patch of the NEXT image level.
 // All float scalar arithmetic follows LKTrackerInvoker's scalar code path operation by operation.
 #include "common.cuh"
@@ -110,7 +111,6 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
     int iw01 = cv_round(a * (1.f - bb) * (1 << 14));
     int iw10 = cv_round((1.f - a) * bb * (1 << 14));
     int iw11 = (1 << 14) - iw00 - iw01 - iw10;
-    long long sA11 = 0, sA12 = 0, sA22 = 0;
     for (int i = lane; i < win * win; i += 32) {
       int y = i / win, x = i - y * win;
       const unsigned char* p = s.P + (y + 1) * pw + (x + 1);
@@ -120,13 +120,28 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
       d = s.Dy + y * dw + x;
       int iyval = descale(d[0] * iw00 + d[1] * iw01 + d[dw] * iw10 + d[dw + 1] * iw11, 14);
       s.I[i] = (short)ival; s.Ix[i] = (short)ixval; s.Iy[i] = (short)iyval;
-      sA11 += (long long)(ixval * ixval);
-      sA12 += (long long)(ixval * iyval);
-      sA22 += (long long)(iyval * iyval);
     }
-    sA11 = warp_sum_ll(sA11); sA12 = warp_sum_ll(sA12); sA22 = warp_sum_ll(sA22);
     __syncwarp();
-    float A11 = (float)sA11 * FLT_SCALE, A12 = (float)sA12 * FLT_SCALE, A22 = (float)sA22 * FLT_SCALE;
+    // Structure tensor with OpenCV's SIMD128 accumulation order (pinned against cv2: scratch probe,
+    // 2400/2400 points bit-exact): four float lanes, pixel i (row-major) -> lane i % 4, sequential
+    // float accumulation per lane, final (L0 + L2) + (L1 + L3).  Lanes 0..11 = 3 sums x 4 chains.
+    float A11, A12, A22;
+    {
+      float acc = 0.f;
+      const int q = lane >> 2, c = lane & 3;
+      if (lane < 12) {
+        const short* u = (q == 2) ? s.Iy : s.Ix;
+        const short* v = (q == 0) ? s.Ix : s.Iy;
+        for (int i = c; i < win * win; i += 4) acc = acc + (float)((int)u[i] * (int)v[i]);
+      }
+      float l2 = __shfl_down_sync(KVFE_FULL_MASK, acc, 2);
+      float l1 = __shfl_down_sync(KVFE_FULL_MASK, acc, 1);
+      float l3 = __shfl_down_sync(KVFE_FULL_MASK, acc, 3);
+      float tot = (acc + l2) + (l1 + l3);          // valid in lanes 0, 4, 8
+      A11 = __shfl_sync(KVFE_FULL_MASK, tot, 0) * FLT_SCALE;
+      A12 = __shfl_sync(KVFE_FULL_MASK, tot, 4) * FLT_SCALE;
+      A22 = __shfl_sync(KVFE_FULL_MASK, tot, 8) * FLT_SCALE;
+    }
     float D = A11 * A22 - A12 * A12;
     float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * win * win);
     if (minEig < dc.min_eig_thr || D < 1.1920929e-07f) {
@@ -153,17 +168,34 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
         s.J[i] = Jimg[(size_t)yy * pitch + xx];
       }
       __syncwarp();
-      long long sb1 = 0, sb2 = 0;
+      // residuals into shared memory (reuses the Dx tap buffer: (win+1)^2 >= win^2 shorts)
+      short* diffv = s.Dx;
       for (int i = lane; i < win * win; i += 32) {
         int y = i / win, x = i - y * win;
         const unsigned char* p = s.J + y * jw + x;
-        int diff = descale(p[0] * iw00 + p[1] * iw01 + p[jw] * iw10 + p[jw + 1] * iw11, 14 - 5) - s.I[i];
-        sb1 += (long long)(diff * s.Ix[i]);
-        sb2 += (long long)(diff * s.Iy[i]);
+        diffv[i] = (short)(descale(p[0] * iw00 + p[1] * iw01 + p[jw] * iw10 + p[jw + 1] * iw11, 14 - 5) - s.I[i]);
       }
-      sb1 = warp_sum_ll(sb1); sb2 = warp_sum_ll(sb2);
       __syncwarp();
-      float b1 = (float)sb1 * FLT_SCALE, b2 = (float)sb2 * FLT_SCALE;
+      // OpenCV's SIMD128 order for the mismatch vector (pinned against cv2): groups of 8 pixels
+      // (row-major); chain m in 0..3 accumulates float(int32(d[k]*G[k] + d[k+4]*G[k+4])), k = 8g + m;
+      // final (c0 + c2) + (c1 + c3).  Lanes 0..7 = 2 sums x 4 chains.
+      float b1, b2;
+      {
+        float acc = 0.f;
+        if (lane < 8) {
+          const short* G = (lane < 4) ? s.Ix : s.Iy;
+          const int m = lane & 3;
+          for (int k = m; k + 4 < win * win; k += 8)
+            acc = acc + (float)((int)diffv[k] * (int)G[k] + (int)diffv[k + 4] * (int)G[k + 4]);
+        }
+        float l2 = __shfl_down_sync(KVFE_FULL_MASK, acc, 2);
+        float l1 = __shfl_down_sync(KVFE_FULL_MASK, acc, 1);
+        float l3 = __shfl_down_sync(KVFE_FULL_MASK, acc, 3);
+        float tot = (acc + l2) + (l1 + l3);        // valid in lanes 0 and 4
+        b1 = __shfl_sync(KVFE_FULL_MASK, tot, 0) * FLT_SCALE;
+        b2 = __shfl_sync(KVFE_FULL_MASK, tot, 4) * FLT_SCALE;
+      }
+      __syncwarp();
       float dxv = (float)((A12 * b2 - A22 * b1) * D);
       float dyv = (float)((A12 * b1 - A11 * b2) * D);
       qx += dxv; qy += dyv;
