@@ -289,7 +289,7 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CU(dmalloc(&db.lk_src, B * cap)); CU(dmalloc(&db.lk_status, B * cap));
   CU(dmalloc(&db.m_ref, B * cap)); CU(dmalloc(&db.m_cur, B * cap)); CU(dmalloc(&db.m_n, B));
   CU(dmalloc(&db.inl, B * cap)); CU(dmalloc(&db.inl_n, B));
-  db.rs_stride = round_up(6 * (size_t)cap + 12 * (size_t)(dc.ransac_iters + 1) + 16 * (size_t)cap, 32);
+  db.rs_stride = round_up(6 * (size_t)cap + 12 * (size_t)std::max(dc.ransac_iters + 1, 32) + 16 * (size_t)cap, 32);
   CU(dmalloc(&db.rs_d, B * db.rs_stride));
   {
     FrameSoA& f = db.fr;

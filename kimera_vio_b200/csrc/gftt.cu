@@ -29,28 +29,28 @@ __global__ void __launch_bounds__(256) mask_fill_kernel(DevCfg dc, unsigned char
     p[i] = v;
 }
 
-// one CTA per stream; one warp per keypoint; hw[dy + r] = half width of the raster row
+// grid (ceil(cap / 8), B), one warp per keypoint; hw[dy + r] = half width of the raster row
 __global__ void __launch_bounds__(256) mask_circles_kernel(DevCfg dc, DevBuf db, const int* __restrict__ hw, int r,
                                                            int mode_mask) {
-  const int b = blockIdx.x;
+  const int b = blockIdx.y;
   const StreamState& s = db.st[b];
   if (!mode_on(s.mode, mode_mask)) return;
   const int fs = b * 3 + s.slot_k;
   const int n = db.fr.n[fs];
   unsigned char* m = db.mask + (size_t)b * dc.img_stride;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, nw = blockDim.x >> 5;
-  for (int i = warp; i < n; i += nw) {
-    size_t k = (size_t)fs * dc.cap + i;
-    if (db.fr.lmk[k] == -1) continue;
-    // cv::Point(Point2f): saturate_cast<int>(float) == cvRound
-    int cx = cv_round(db.fr.kx[k]), cy = cv_round(db.fr.ky[k]);
-    for (int dy = -r; dy <= r; ++dy) {
-      int y = cy + dy;
-      if (y < 0 || y >= dc.H) continue;
-      int h = hw[dy + r];
-      int xa = max(cx - h, 0), xb = min(cx + h, dc.W - 1);
-      for (int x = xa + lane; x <= xb; x += 32) m[(size_t)y * dc.pitch + x] = 0;
-    }
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int i = blockIdx.x * 8 + warp;
+  if (i >= n) return;
+  size_t k = (size_t)fs * dc.cap + i;
+  if (db.fr.lmk[k] == -1) return;
+  // cv::Point(Point2f): saturate_cast<int>(float) == cvRound
+  int cx = cv_round(db.fr.kx[k]), cy = cv_round(db.fr.ky[k]);
+  for (int dy = -r; dy <= r; ++dy) {
+    int y = cy + dy;
+    if (y < 0 || y >= dc.H) continue;
+    int h = hw[dy + r];
+    int xa = max(cx - h, 0), xb = min(cx + h, dc.W - 1);
+    for (int x = xa + lane; x <= xb; x += 32) m[(size_t)y * dc.pitch + x] = 0;
   }
 }
 
@@ -59,10 +59,7 @@ __global__ void __launch_bounds__(256) mask_circles_kernel(DevCfg dc, DevBuf db,
 // ------------------------------------------------------------------------------------------------
 struct RT { float r, t; };
 
-__device__ __forceinline__ RT row_rt(const unsigned char* __restrict__ img, int pitch, int W, int y, int c,
-                                     float s, float s2, bool tail) {
-  const unsigned char* row = img + (size_t)y * pitch;
-  float im = (float)row[reflect101(c - 1, W)], i0 = (float)row[c], ip = (float)row[reflect101(c + 1, W)];
+__device__ __forceinline__ RT rt_from(float im, float i0, float ip, float s, float s2, bool tail) {
   RT o;
   o.r = ip - im;                                   // exact
   if (!tail) o.t = fmaf(ip, s, fmaf(i0, s2, s * im));
@@ -70,13 +67,21 @@ __device__ __forceinline__ RT row_rt(const unsigned char* __restrict__ img, int 
   return o;
 }
 
-// grid (ceil(ngroups/4), B); block 128 = 4 warps, each warp owns 30 output columns (+2 halo lanes)
+#define MINEIG_ROWS 32     // rows staged per batch
+#define MINEIG_TW 48       // staged tile width in bytes (12 aligned words >= 2 + 34 + 3)
+
+// grid (ceil(ngroups/4), B); block 128 = 4 warps, each warp owns 30 output columns (+2 halo lanes).
+// Each batch of 32 image rows (and the 32 mask rows of the outputs) is first staged into shared
+// memory with one row per lane (12 independent 32-bit loads per lane in flight -> the DRAM/L2 latency
+// is paid once per batch instead of once per row), then the warp marches down the staged rows.
 __global__ void __launch_bounds__(128) mineig_kernel(DevCfg dc, DevBuf db, const unsigned char* __restrict__ imgs,
                                                      size_t img_stride, int mode_mask, int use_mask) {
+  __shared__ __align__(16) unsigned char tile[4][MINEIG_ROWS][MINEIG_TW];
+  __shared__ __align__(16) unsigned char mtile[4][MINEIG_ROWS][MINEIG_TW];
   const int b = blockIdx.y;
   if (!mode_on(db.st[b].mode, mode_mask)) return;
-  const int lane = threadIdx.x & 31;
-  const int group = blockIdx.x * 4 + (threadIdx.x >> 5);
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int group = blockIdx.x * 4 + warp;
   const int x0 = group * 30;
   const int W = dc.W, H = dc.H;
   if (x0 >= W) return;
@@ -86,57 +91,97 @@ __global__ void __launch_bounds__(128) mineig_kernel(DevCfg dc, DevBuf db, const
   const int cx = x0 - 1 + lane;                 // lanes 0 and 31 are halo
   int c = reflect101(cx, W);
   c = clampi(c, 0, W - 1);                      // lanes beyond the reflected border are inactive
+  const int cm = reflect101(c - 1, W), cp = reflect101(c + 1, W);
   const bool writer = lane >= 1 && lane <= 30 && cx < W;
   const float s = (float)(1.0 / 3060.0), s2 = 2.0f * s;
   const bool tail = dc.sobel_tail_start >= 0 && c >= dc.sobel_tail_start;
+  const int pitch = dc.pitch;                   // multiple of 16, rows are 16-byte aligned
+  const int xs = max(x0 - 2, 0) & ~3;           // tile origin (aligned); covers [x0-2, x0+32]
+  // offsets into the staged tile (lanes past the reflected border are inactive: clamp them)
+  const int oc = clampi(c - xs, 0, MINEIG_TW - 1), om = clampi(cm - xs, 0, MINEIG_TW - 1),
+            op = clampi(cp - xs, 0, MINEIG_TW - 1), ox = clampi(cx - xs, 0, MINEIG_TW - 1);
+  unsigned char (*T)[MINEIG_TW] = tile[warp];
+  unsigned char (*M)[MINEIG_TW] = mtile[warp];
 
-  RT a = row_rt(img, dc.pitch, W, reflect101(-1, H), c, s, s2, tail);   // row p-1
-  RT m = row_rt(img, dc.pitch, W, 0, c, s, s2, tail);                   // row p
+  RT a, m;
+  {
+    const unsigned char* r1 = img + (size_t)reflect101(-1, H) * pitch;
+    a = rt_from((float)r1[cm], (float)r1[c], (float)r1[cp], s, s2, tail);       // row p-1
+    m = rt_from((float)img[cm], (float)img[c], (float)img[cp], s, s2, tail);    // row p
+  }
   double sum0 = 0, sum1 = 0, sum2 = 0;             // running column sums (xx, xy, yy)
   double rm2_0 = 0, rm2_1 = 0, rm2_2 = 0;          // R(p-2)
   double rm1_0 = 0, rm1_1 = 0, rm1_2 = 0;          // R(p-1)
   float vmax = -INFINITY;
 
-  for (int p = 0; p <= H; ++p) {
-    double r0, r1, r2;
-    if (p < H) {
-      RT n = row_rt(img, dc.pitch, W, reflect101(p + 1, H), c, s, s2, tail);  // row p+1
-      // cv::Sobel column pass: Dx = fma(r(y-1) + r(y+1), s, (2s) * r(y)); Dy = t(y+1) - t(y-1)
-      float dx = fmaf(a.r + n.r, s, s2 * m.r);
-      float dy = n.t - a.t;
-      float pxx = dx * dx, pxy = dx * dy, pyy = dy * dy;
-      // RowSum<float,double>, ksize 3: (S[x-1] + S[x]) + S[x+1]
-      float l0 = __shfl_up_sync(KVFE_FULL_MASK, pxx, 1), g0 = __shfl_down_sync(KVFE_FULL_MASK, pxx, 1);
-      float l1 = __shfl_up_sync(KVFE_FULL_MASK, pxy, 1), g1 = __shfl_down_sync(KVFE_FULL_MASK, pxy, 1);
-      float l2 = __shfl_up_sync(KVFE_FULL_MASK, pyy, 1), g2 = __shfl_down_sync(KVFE_FULL_MASK, pyy, 1);
-      r0 = ((double)l0 + (double)pxx) + (double)g0;
-      r1 = ((double)l1 + (double)pxy) + (double)g1;
-      r2 = ((double)l2 + (double)pyy) + (double)g2;
-      a = m;
-      m = n;
-    } else {
-      r0 = rm2_0; r1 = rm2_1; r2 = rm2_2;            // R(H) = R(H-2) (reflect)
-    }
-    if (p == 1) {                                    // ColumnSum init: SUM = (0 + R(-1)) + R(0), R(-1) = R(1)
-      sum0 = (0.0 + r0) + rm1_0;
-      sum1 = (0.0 + r1) + rm1_1;
-      sum2 = (0.0 + r2) + rm1_2;
-    }
-    if (p >= 1) {
-      const int y = p - 1;
-      // s0 = SUM + R(y+1); out = (float)s0; SUM = s0 - R(y-1)   (R(-1) = R(1))
-      double s0 = sum0 + r0, s1 = sum1 + r1, s2d = sum2 + r2;
-      double o0 = (y == 0) ? r0 : rm2_0, o1 = (y == 0) ? r1 : rm2_1, o2 = (y == 0) ? r2 : rm2_2;
-      sum0 = s0 - o0; sum1 = s1 - o1; sum2 = s2d - o2;
-      if (writer) {
-        float A = (float)s0 * 0.5f, Bv = (float)s1, C = (float)s2d * 0.5f;
-        float e = (A + C) - sqrtf((A - C) * (A - C) + Bv * Bv);
-        eig[(size_t)y * W + cx] = e;
-        if (!use_mask || msk[(size_t)y * dc.pitch + cx]) vmax = fmaxf(vmax, e);
+  for (int p0 = 0; p0 <= H; p0 += MINEIG_ROWS) {
+    // ---- stage: lane u loads image row reflect(p0+u+1) and mask row (p0+u-1), 12 words each
+    {
+      const int p = p0 + lane;
+      const int yr = reflect101(min(p + 1, H), H);
+      const unsigned int* src = reinterpret_cast<const unsigned int*>(img + (size_t)yr * pitch + xs);
+      const int ym = clampi(p - 1, 0, H - 1);
+      const unsigned int* msrc = reinterpret_cast<const unsigned int*>(msk + (size_t)ym * pitch + xs);
+      const int nw = min(MINEIG_TW / 4, (pitch - xs) / 4);
+      unsigned int v[MINEIG_TW / 4], w[MINEIG_TW / 4];
+#pragma unroll
+      for (int q = 0; q < MINEIG_TW / 4; ++q) {
+        v[q] = (q < nw) ? src[q] : 0u;
+        w[q] = (use_mask && q < nw) ? msrc[q] : 0xffffffffu;
       }
+      __syncwarp();
+#pragma unroll
+      for (int q = 0; q < MINEIG_TW / 4; ++q) {
+        reinterpret_cast<unsigned int*>(T[lane])[q] = v[q];
+        reinterpret_cast<unsigned int*>(M[lane])[q] = w[q];
+      }
+      __syncwarp();
     }
-    rm2_0 = rm1_0; rm2_1 = rm1_1; rm2_2 = rm1_2;
-    rm1_0 = r0; rm1_1 = r1; rm1_2 = r2;
+#pragma unroll 4
+    for (int u = 0; u < MINEIG_ROWS; ++u) {
+      const int p = p0 + u;
+      if (p > H) break;
+      double r0, r1, r2;
+      if (p < H) {
+        RT n = rt_from((float)T[u][om], (float)T[u][oc], (float)T[u][op], s, s2, tail);   // row p+1
+        // cv::Sobel column pass: Dx = fma(r(y-1) + r(y+1), s, (2s) * r(y)); Dy = t(y+1) - t(y-1)
+        float dx = fmaf(a.r + n.r, s, s2 * m.r);
+        float dy = n.t - a.t;
+        float pxx = dx * dx, pxy = dx * dy, pyy = dy * dy;
+        // RowSum<float,double>, ksize 3: (S[x-1] + S[x]) + S[x+1]
+        float l0 = __shfl_up_sync(KVFE_FULL_MASK, pxx, 1), g0 = __shfl_down_sync(KVFE_FULL_MASK, pxx, 1);
+        float l1 = __shfl_up_sync(KVFE_FULL_MASK, pxy, 1), g1 = __shfl_down_sync(KVFE_FULL_MASK, pxy, 1);
+        float l2 = __shfl_up_sync(KVFE_FULL_MASK, pyy, 1), g2 = __shfl_down_sync(KVFE_FULL_MASK, pyy, 1);
+        r0 = ((double)l0 + (double)pxx) + (double)g0;
+        r1 = ((double)l1 + (double)pxy) + (double)g1;
+        r2 = ((double)l2 + (double)pyy) + (double)g2;
+        a = m;
+        m = n;
+      } else {
+        r0 = rm2_0; r1 = rm2_1; r2 = rm2_2;            // R(H) = R(H-2) (reflect)
+      }
+      if (p == 1) {                                    // ColumnSum init: SUM = (0 + R(-1)) + R(0), R(-1) = R(1)
+        sum0 = (0.0 + r0) + rm1_0;
+        sum1 = (0.0 + r1) + rm1_1;
+        sum2 = (0.0 + r2) + rm1_2;
+      }
+      if (p >= 1) {
+        const int y = p - 1;
+        // s0 = SUM + R(y+1); out = (float)s0; SUM = s0 - R(y-1)   (R(-1) = R(1))
+        double s0 = sum0 + r0, s1 = sum1 + r1, s2d = sum2 + r2;
+        double o0 = (y == 0) ? r0 : rm2_0, o1 = (y == 0) ? r1 : rm2_1, o2 = (y == 0) ? r2 : rm2_2;
+        sum0 = s0 - o0; sum1 = s1 - o1; sum2 = s2d - o2;
+        if (writer) {
+          float A = (float)s0 * 0.5f, Bv = (float)s1, C = (float)s2d * 0.5f;
+          float e = (A + C) - sqrtf((A - C) * (A - C) + Bv * Bv);
+          eig[(size_t)y * W + cx] = e;
+          if (M[u][ox]) vmax = fmaxf(vmax, e);
+        }
+      }
+      rm2_0 = rm1_0; rm2_1 = rm1_1; rm2_2 = rm1_2;
+      rm1_0 = r0; rm1_1 = r1; rm1_2 = r2;
+    }
+    __syncwarp();
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(KVFE_FULL_MASK, vmax, o));
@@ -180,7 +225,13 @@ __global__ void __launch_bounds__(256) cand_kernel(DevCfg dc, DevBuf db, int mod
 }
 
 // ------------------------------------------------------------------------------------------------
-// sort (descending 64-bit keys) + greedy min-distance, one CTA per stream
+// greedy min-distance selection, one CTA per stream.  The sequential OpenCV loop accepts a
+// candidate iff no BETTER (higher value, ties: higher address) already-accepted candidate lies in
+// the 3x3 neighbouring cells within minDistance.  "Better" is a comparison of the 64-bit keys, so no
+// global sort is needed for the decision: candidates are bucketed into the cell grid and a parallel
+// fixed point (accept when every better conflicting neighbour is rejected, reject when one is
+// accepted) reproduces the sequential result; only the accepted corners (<= a few thousand) are
+// sorted at the end to produce OpenCV's output order and the maxCorners cut.
 // ------------------------------------------------------------------------------------------------
 __device__ void bitonic_desc(unsigned long long* k, int P) {
   for (int size = 2; size <= P; size <<= 1) {
@@ -197,134 +248,192 @@ __device__ void bitonic_desc(unsigned long long* k, int P) {
   }
 }
 
-__global__ void __launch_bounds__(1024) sort_greedy_kernel(DevCfg dc, DevBuf db, int mode_mask, int smem_keys) {
+#define GREEDY_ACC_MAX 8192
+
+// Layout of the dynamic shared memory: skey[smem_keys] (candidates ordered by (cell, key desc)),
+// then acc[GREEDY_ACC_MAX].  When the candidates do not fit, skey lives in the global candidate
+// buffer instead (same code path, slower).
+__global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf db, int mode_mask, int smem_keys) {
   extern __shared__ unsigned long long skeys[];
   const int b = blockIdx.x;
   if (!mode_on(db.st[b].mode, mode_mask)) return;
   const int W = dc.W, H = dc.H;
-  int n = min(db.cand_n[b], dc.cand_cap);
+  const int n = min(db.cand_n[b], dc.cand_cap);
   unsigned long long* gk = db.cand + (size_t)b * dc.cand_cap;
-  int P = 1;
-  while (P < n) P <<= 1;
-  if (P < 2) P = 2;
-  unsigned long long* k = (P <= smem_keys) ? skeys : gk;     // gk has cand_cap >= P (cand_cap is pow2)
-  for (int i = threadIdx.x; i < P; i += blockDim.x) {
-    unsigned long long v = (i < n) ? gk[i] : 0ull;
-    k[i] = v;
-  }
-  __syncthreads();
-  bitonic_desc(k, P);
-
-  int* sc = db.scratch_i + (size_t)b * db.scratch_stride;
-  int* state = sc;                          // [cand_cap] 0 undecided, 1 accepted, 2 rejected
-  int* cellof = sc + dc.cand_cap;           // [cand_cap]
-  int* items = sc + 2 * dc.cand_cap;        // [cand_cap] candidate ranks grouped by cell
-  int* cstart = sc + 3 * dc.cand_cap;       // [ncells + 1]
   int* corner = db.corner_idx + (size_t)b * dc.max_before_anms;
-  __shared__ int s_total, s_flag;
-
+  __shared__ int s_total, s_chunk, wsum[32];
   const int md = dc.min_distance;
-  if (md < 1) {                             // no min-distance: top maxCorners
+  const int tid = threadIdx.x;
+
+  if (md < 1) {                             // no min-distance: plain top-maxCorners (needs the full sort)
+    int P = 2;
+    while (P < n) P <<= 1;
+    unsigned long long* k = (P <= smem_keys) ? skeys : gk;
+    for (int i = tid; i < P; i += blockDim.x) k[i] = (i < n) ? gk[i] : 0ull;
+    __syncthreads();
+    bitonic_desc(k, P);
     int m = min(n, dc.max_before_anms);
-    for (int i = threadIdx.x; i < m; i += blockDim.x) corner[i] = (int)(k[i] & 0xffffffffu);
-    if (threadIdx.x == 0) db.corner_n[b] = m;
+    for (int i = tid; i < m; i += blockDim.x) corner[i] = (int)(k[i] & 0xffffffffu);
+    if (tid == 0) db.corner_n[b] = m;
     return;
   }
+
+  int* sc = db.scratch_i + (size_t)b * db.scratch_stride;
+  int* cstart = sc;                                   // [ncells + 1]
+  int* head = sc + (dc.cand_cap / 4);                 // [ncells]   (ncells << cand_cap / 4)
+  int* newacc = sc + 2 * (dc.cand_cap / 4);           // [ncells]
+  unsigned char* state = reinterpret_cast<unsigned char*>(sc + 3 * (dc.cand_cap / 4));   // [cand_cap]
+  unsigned long long* tmp = reinterpret_cast<unsigned long long*>(sc + dc.cand_cap);     // [cand_cap] keys by cell
   const int cell = md;                      // cvRound(minDistance), minDistance is an int parameter
   const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
   const int ncells = gw * gh;
-  for (int i = threadIdx.x; i <= ncells; i += blockDim.x) cstart[i] = 0;
+  unsigned long long* sk = (n <= smem_keys) ? skeys : gk;
+  // ---- 1. bucket by cell (counting sort) into tmp
+  for (int i = tid; i <= ncells; i += blockDim.x) cstart[i] = 0;
   __syncthreads();
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int idx = (int)(k[i] & 0xffffffffu);
+  for (int i = tid; i < n; i += blockDim.x) {
+    int idx = (int)(gk[i] & 0xffffffffu);
+    int y = idx / W, x = idx - y * W;
+    atomicAdd(&cstart[(y / cell) * gw + (x / cell) + 1], 1);
+  }
+  __syncthreads();
+  if (tid < 32) {                           // exclusive scan of the cell counts by one warp
+    int carry = 0;
+    for (int base = 0; base <= ncells; base += 32) {
+      int i = base + tid;
+      int v = (i <= ncells) ? cstart[i] : 0, incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        int t = __shfl_up_sync(KVFE_FULL_MASK, incl, o);
+        if (tid >= o) incl += t;
+      }
+      if (i <= ncells) cstart[i] = carry + incl - v;
+      carry += __shfl_sync(KVFE_FULL_MASK, incl, 31);
+    }
+  }
+  __syncthreads();
+  for (int i = tid; i < n; i += blockDim.x) {        // cstart[c+1] = cursor of cell c
+    unsigned long long key = gk[i];
+    int idx = (int)(key & 0xffffffffu);
+    int y = idx / W, x = idx - y * W;
+    int pos = atomicAdd(&cstart[(y / cell) * gw + (x / cell) + 1], 1);
+    tmp[pos] = key;
+  }
+  __syncthreads();
+  // now cell c spans [cstart[c], cstart[c+1]) in tmp
+  // ---- 2. order every cell by key descending (rank by counting inside the cell)
+  for (int i = tid; i < n; i += blockDim.x) {
+    unsigned long long key = tmp[i];
+    int idx = (int)(key & 0xffffffffu);
     int y = idx / W, x = idx - y * W;
     int c = (y / cell) * gw + (x / cell);
-    cellof[i] = c;
+    int a0 = cstart[c], a1 = cstart[c + 1], rank = 0;
+    for (int q = a0; q < a1; ++q) rank += tmp[q] > key;
+    sk[a0 + rank] = key;
     state[i] = 0;
-    atomicAdd(&cstart[c + 1], 1);
   }
+  for (int c = tid; c < ncells; c += blockDim.x) { head[c] = cstart[c]; newacc[c] = -1; }
   __syncthreads();
-  if (threadIdx.x == 0) {                   // exclusive scan over <= a few thousand cells
-    int acc = 0;
-    for (int c = 0; c <= ncells; ++c) { int v = cstart[c]; cstart[c] = acc; acc += v; }
-    // cstart[c] now = start of cell c-1 ... shift: cstart[c+1] held count(c); after the scan
-    // cstart[c+1] = sum_{j<=c-1}... see fill below (uses cstart[c+1] as the running cursor of cell c)
-  }
-  __syncthreads();
-  // after the scan: cstart[c+1] == number of items in cells < c  == start offset of cell c
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int pos = atomicAdd(&cstart[cellof[i] + 1], 1);
-    items[pos] = i;
-  }
-  __syncthreads();
-  // now cstart[c+1] == end of cell c, and start of cell c == (c == 0 ? 0 : cstart[c]) == cstart[c]
-  // because cstart[0] == 0 and cstart[c] (c >= 1) was advanced to the end of cell c-1.
+  // ---- 3. rounds: only the best undecided candidate of each cell ("head") is examined
   const int md2 = md * md;
-  volatile int* vstate = state;
-  for (int round = 0; round < 4096; ++round) {
-    int pending_any = 0;
-    for (int i = threadIdx.x; i < n; i += blockDim.x) {
-      if (vstate[i] != 0) continue;
-      int idx = (int)(k[i] & 0xffffffffu);
-      int y = idx / W, x = idx - y * W;
-      int cxl = x / cell, cyl = y / cell;
-      int x1 = max(cxl - 1, 0), x2 = min(cxl + 1, gw - 1), y1 = max(cyl - 1, 0), y2 = min(cyl + 1, gh - 1);
-      int verdict = 1;                       // accept unless a better conflicting one is accepted / pending
-      for (int yy = y1; yy <= y2 && verdict != 2; ++yy)
-        for (int xx = x1; xx <= x2 && verdict != 2; ++xx) {
-          int c = yy * gw + xx;
-          for (int q = cstart[c]; q < cstart[c + 1]; ++q) {
-            int j = items[q];
-            if (j >= i) continue;
-            int sj = vstate[j];
-            if (sj == 2) continue;
-            int jdx = (int)(k[j] & 0xffffffffu);
-            int jy = jdx / W, jx = jdx - jy * W;
-            int ddx = x - jx, ddy = y - jy;
-            if (ddx * ddx + ddy * ddy < md2) {
-              if (sj == 1) { verdict = 2; break; }
-              verdict = 0;                   // undecided better neighbour: wait
-            }
+  volatile unsigned char* vst = state;
+  volatile int* vhead = head;
+  for (int round = 0; round < 100000; ++round) {
+    int active = 0;
+    // phase A: one thread per cell
+    for (int c = tid; c < ncells; c += blockDim.x) {
+      int h = vhead[c];
+      const int e = cstart[c + 1];
+      while (h < e && vst[h] != 0) ++h;              // skip decided entries
+      vhead[c] = h;
+      newacc[c] = -1;
+      if (h >= e) continue;
+      active = 1;
+      const unsigned long long kh = sk[h];
+      const int idx = (int)(kh & 0xffffffffu);
+      const int y = idx / W, x = idx - y * W;
+      const int cxl = c % gw, cyl = c / gw;
+      const int x1 = max(cxl - 1, 0), x2 = min(cxl + 1, gw - 1), y1 = max(cyl - 1, 0), y2 = min(cyl + 1, gh - 1);
+      int verdict = 1;                                // 1 accept, 0 wait, 2 reject
+      for (int yy = y1; yy <= y2 && verdict == 1; ++yy)
+        for (int xx = x1; xx <= x2 && verdict == 1; ++xx) {
+          const int d = yy * gw + xx;
+          if (d == c) continue;
+          const int de = cstart[d + 1];
+          for (int q = cstart[d]; q < de; ++q) {      // better candidates form a prefix of the cell
+            const unsigned long long kq = sk[q];
+            if (kq < kh) break;
+            const int sq = vst[q];
+            if (sq == 2) continue;
+            const int jdx = (int)(kq & 0xffffffffu);
+            const int jy = jdx / W, jx = jdx - jy * W;
+            const int ddx = x - jx, ddy = y - jy;
+            if (ddx * ddx + ddy * ddy < md2) { verdict = (sq == 1) ? 2 : 0; break; }
           }
         }
-      if (verdict == 0) pending_any = 1;
-      else vstate[i] = verdict;
+      if (verdict == 1) { vst[h] = 1; newacc[c] = h; }
+      else if (verdict == 2) vst[h] = 2;
     }
-    int any = __syncthreads_or(pending_any);
-    if (!any) break;
+    if (!__syncthreads_or(active)) break;
+    // phase B: every newly accepted corner rejects the undecided candidates within minDistance
+    for (int c = tid; c < ncells; c += blockDim.x) {
+      const int h = newacc[c];
+      if (h < 0) continue;
+      const int idx = (int)(sk[h] & 0xffffffffu);
+      const int y = idx / W, x = idx - y * W;
+      const int cxl = c % gw, cyl = c / gw;
+      const int x1 = max(cxl - 1, 0), x2 = min(cxl + 1, gw - 1), y1 = max(cyl - 1, 0), y2 = min(cyl + 1, gh - 1);
+      for (int yy = y1; yy <= y2; ++yy) {
+        const int qa = vhead[yy * gw + x1], qb = cstart[yy * gw + x2 + 1];
+        for (int q = qa; q < qb; ++q) {
+          if (vst[q] != 0) continue;
+          const int jdx = (int)(sk[q] & 0xffffffffu);
+          const int jy = jdx / W, jx = jdx - jy * W;
+          const int ddx = x - jx, ddy = y - jy;
+          if (ddx * ddx + ddy * ddy < md2) vst[q] = 2;
+        }
+      }
+    }
+    __syncthreads();
   }
   __syncthreads();
-  // compact accepted candidates in rank order, stop at maxCorners
-  if (threadIdx.x == 0) s_total = 0;
+  // ---- 4. gather accepted keys, sort them descending, emit the first maxCorners
+  unsigned long long* acc = skeys + smem_keys;
+  if (tid == 0) s_total = 0;
   __syncthreads();
   for (int base = 0; base < n; base += blockDim.x) {
-    int i = base + threadIdx.x;
-    int acc = (i < n && state[i] == 1) ? 1 : 0;
-    // block-wide exclusive scan via warp ballots
-    unsigned bal = __ballot_sync(KVFE_FULL_MASK, acc);
-    __shared__ int wsum[32];
-    int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    int i = base + tid;
+    int a = (i < n && state[i] == 1) ? 1 : 0;
+    unsigned bal = __ballot_sync(KVFE_FULL_MASK, a);
+    int lane = tid & 31, warp = tid >> 5;
     if (lane == 0) wsum[warp] = __popc(bal);
     __syncthreads();
     if (warp == 0) {
-      int v = (lane < (blockDim.x >> 5)) ? wsum[lane] : 0;
-      int incl = v;
+      int v = wsum[lane], incl = v;
 #pragma unroll
       for (int o = 1; o < 32; o <<= 1) {
         int t = __shfl_up_sync(KVFE_FULL_MASK, incl, o);
         if (lane >= o) incl += t;
       }
       wsum[lane] = incl - v;
-      if (lane == 31) s_flag = incl;
+      if (lane == 31) s_chunk = incl;
     }
     __syncthreads();
     int pos = s_total + wsum[warp] + __popc(bal & ((1u << lane) - 1));
-    if (acc && pos < dc.max_before_anms) corner[pos] = (int)(k[i] & 0xffffffffu);
+    if (a && pos < GREEDY_ACC_MAX) acc[pos] = sk[i];
     __syncthreads();
-    if (threadIdx.x == 0) s_total += s_flag;
+    if (tid == 0) s_total += s_chunk;
     __syncthreads();
   }
-  if (threadIdx.x == 0) db.corner_n[b] = min(s_total, dc.max_before_anms);
+  const int na = min(s_total, GREEDY_ACC_MAX);
+  int P = 2;
+  while (P < na) P <<= 1;
+  for (int i = na + tid; i < P; i += blockDim.x) acc[i] = 0ull;
+  __syncthreads();
+  bitonic_desc(acc, P);
+  const int m = min(na, dc.max_before_anms);
+  for (int i = tid; i < m; i += blockDim.x) corner[i] = (int)(acc[i] & 0xffffffffu);
+  if (tid == 0) db.corner_n[b] = m;
   (void)H;
 }
 
@@ -343,16 +452,17 @@ int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, si
   int n = 0;
   gftt_init_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, mode_mask); ++n;
   mask_fill_kernel<<<dim3(64, dc.B), 256, 0, s>>>(dc, db.mask, db.st, mode_mask); ++n;
-  mask_circles_kernel<<<dc.B, 256, 0, s>>>(dc, db, circle_hw, circle_r, mode_mask); ++n;
+  mask_circles_kernel<<<dim3((dc.cap + 7) / 8, dc.B), 256, 0, s>>>(dc, db, circle_hw, circle_r, mode_mask); ++n;
   int groups = (dc.W + 29) / 30;
   mineig_kernel<<<dim3((groups + 3) / 4, dc.B), 128, 0, s>>>(dc, db, img, img_stride, mode_mask, 1); ++n;
   cand_kernel<<<dim3((dc.W + 31) / 32, (dc.H + 7) / 8, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;
   int smem_keys = 16384;
+  const int smem_bytes = (smem_keys + GREEDY_ACC_MAX) * 8;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaFuncSetAttribute(sort_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_keys * 8);
+    cudaFuncSetAttribute(sort_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     attr_set = true;
   }
-  sort_greedy_kernel<<<dc.B, 1024, smem_keys * 8, s>>>(dc, db, mode_mask, smem_keys); ++n;
+  sort_greedy_kernel<<<dc.B, 1024, smem_bytes, s>>>(dc, db, mode_mask, smem_keys); ++n;
   return n;
 }

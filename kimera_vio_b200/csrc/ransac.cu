@@ -14,7 +14,7 @@
 #include "common.cuh"
 #include "matches.cuh"
 
-#define RS_THREADS 256
+#define RS_THREADS 512
 
 // ------------------------------------------------------------------------------------------------
 // relative-pose scoring (opengv triangulation::triangulate2 + reprojection error)
@@ -155,14 +155,16 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
                              double threshold, int max_it, double prob, const int* __restrict__ rnd, int rnd_n,
                              int* wi, double* models, double* best_model, int* inl_flag) {
   __shared__ SacResult res;
-  __shared__ int s_best;
+  __shared__ int s_best, s_done, s_iter, s_nbest, s_j0;
+  __shared__ double s_k;
+  __shared__ int s_counts[RS_THREADS / 32];
   const int ssz = problem == 0 ? 2 : 3;
   const int NS = max_it + 1;
   int* shuffled = wi;
   int* samples = wi + n;
-  int* counts = samples + NS * ssz;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const bool enough = n >= ssz;
+  if (tid == 0) { s_best = -1; s_done = enough ? 0 : 1; s_iter = 0; s_nbest = -2147483647; s_k = 1.0; s_j0 = 0; }
   if (enough) {
     for (int i = tid; i < n; i += blockDim.x) shuffled[i] = i;
     __syncthreads();
@@ -177,15 +179,22 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
         for (int i = 0; i < ssz; ++i) samples[j * ssz + i] = shuffled[i];
       }
     }
-    __syncthreads();
-    for (int j = warp; j < NS; j += nw) {
-      double* m = models + 12 * j;
+  }
+  __syncthreads();
+  // hypotheses are evaluated one chunk (one per warp) at a time and the sequential
+  // "best-so-far / adaptive k" loop is replayed over each chunk; evaluation stops as soon as the
+  // serial loop would have stopped (typically after the first chunk).
+  while (!s_done) {
+    const int j0 = s_j0;
+    const int j = j0 + warp;
+    double* m = models + 12 * (size_t)warp;     // chunk-local model slots
+    int cnt = 0;
+    if (j < NS) {
       if (lane == 0) {
         if (problem == 0) twopt_model(R12, a, b, samples[j * 2], samples[j * 2 + 1], m);
         else arun_model(a, b, samples + j * 3, 3, m);
       }
       __syncwarp();
-      int cnt = 0;
       for (int i = lane; i < n; i += 32) {
         double sc;
         if (problem == 0) {
@@ -196,38 +205,38 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
         cnt += (sc < threshold) ? 1 : 0;
       }
       cnt = warp_sum_i(cnt);
-      if (lane == 0) counts[j] = cnt;
+      if (lane == 0) s_counts[warp] = cnt;
     }
-  }
-  __syncthreads();
-  if (tid == 0) {                        // replay of the sequential loop
-    int iterations = 0, n_best = -2147483647, best = -1;
-    double k = 1.0;
-    if (enough) {
-      int j = 0;
-      while ((double)iterations < k && j < NS) {
-        int c = counts[j];
+    __syncthreads();
+    if (tid == 0) {                        // replay of the sequential loop over this chunk
+      int iterations = s_iter, n_best = s_nbest, best = s_best;
+      double k = s_k;
+      int done = 0;
+      for (int w = 0; w < nw; ++w) {
+        if (!((double)iterations < k) || j0 + w >= NS) { done = 1; break; }
+        int c = s_counts[w];
         if (c > n_best) {
-          n_best = c; best = j;
-          double w = (double)n_best / (double)n;
-          double p_no = 1.0 - pow(w, (double)ssz);
+          n_best = c; best = j0 + w;
+          for (int q = 0; q < 12; ++q) best_model[q] = models[12 * (size_t)w + q];
+          double wr = (double)n_best / (double)n;
+          double p_no = 1.0 - pow(wr, (double)ssz);
           p_no = fmax(2.220446049250313e-16, p_no);
           p_no = fmin(1.0 - 2.220446049250313e-16, p_no);
           k = log(1.0 - prob) / log(p_no);
         }
-        ++iterations; ++j;
-        if (iterations > max_it) break;
+        ++iterations;
+        if (iterations > max_it) { done = 1; break; }
       }
+      if (!done && (!((double)iterations < k) || j0 + nw >= NS)) done = 1;
+      s_iter = iterations; s_nbest = n_best; s_best = best; s_k = k; s_done = done; s_j0 = j0 + nw;
     }
-    s_best = best;
-    res.iterations = iterations;
-    res.success = best >= 0;
+    __syncthreads();
   }
+  if (tid == 0) { res.iterations = s_iter; res.success = s_best >= 0; }
   __syncthreads();
   int cnt_local = 0;
   if (s_best >= 0) {
-    const double* m = models + 12 * s_best;
-    for (int i = tid; i < 12; i += blockDim.x) best_model[i] = m[i];
+    const double* m = best_model;
     for (int i = tid; i < n; i += blockDim.x) {
       double sc;
       if (problem == 0) {
@@ -242,8 +251,6 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
   } else {
     for (int i = tid; i < n; i += blockDim.x) inl_flag[i] = 0;
   }
-  int total = __syncthreads_count(0);    // barrier
-  (void)total;
   __shared__ int s_cnt;
   if (tid == 0) s_cnt = 0;
   __syncthreads();
@@ -265,15 +272,12 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
   return out;
 }
 
-// ------------------------------------------------------------------------------------------------
-// FSM kernels
-// ------------------------------------------------------------------------------------------------
 // layout of the per-stream double workspace rs_d: [a: cap*3][b: cap*3][models: (max_it+1)*12][tmp: cap*16]
 __device__ __forceinline__ double* ws_a(const DevCfg& dc, const DevBuf& db, int b) { return db.rs_d + (size_t)b * db.rs_stride; }
 __device__ __forceinline__ double* ws_b(const DevCfg& dc, const DevBuf& db, int b) { return ws_a(dc, db, b) + 3 * dc.cap; }
 __device__ __forceinline__ double* ws_models(const DevCfg& dc, const DevBuf& db, int b) { return ws_b(dc, db, b) + 3 * dc.cap; }
 __device__ __forceinline__ double* ws_tmp(const DevCfg& dc, const DevBuf& db, int b) {
-  return ws_models(dc, db, b) + 12 * (size_t)(dc.ransac_iters + 1);
+  return ws_models(dc, db, b) + 12 * (size_t)(dc.ransac_iters + 1 > 32 ? dc.ransac_iters + 1 : 32);
 }
 
 // outlierRejectionMono (VisionImuFrontend.cpp:90-113) -> geometricOutlierRejection2d2d(Frame*, Frame*, Pose3)
@@ -374,27 +378,36 @@ __device__ __forceinline__ float maha_f32(const float* vi, const float* Oi, cons
 
 // 1-point voting on n matches.  rel (n*3 f64), cov (n*9 f64) prepared by the caller; relf/covf f32
 // copies; returns status, writes inlier flags, pose [R|t], info.
-__device__ int voting_1pt(const DevCfg& dc, int n, const double* rel, const double* cov, const float* relf,
+__device__ int voting_1pt(const DevCfg& dc, int n, const double* rel, double* cov, const float* relf,
                           const float* covf, const double* R, int* sizes, int* inl, double* pose, double* info,
                           int* n_inl_out) {
   __shared__ int s_maxid, s_maxsize, s_ninl;
   __shared__ double acc[12];
   const float thr = (float)dc.thr_stereo;
-  for (int i = threadIdx.x; i < n; i += blockDim.x) {
-    int c = 1;
-    for (int j = 0; j < n; ++j) {
-      if (j == i) continue;
-      int lo = i < j ? i : j, hi = i < j ? j : i;
-      float m = maha_f32(relf + 3 * lo, covf + 9 * lo, relf + 3 * hi, covf + 9 * hi);
-      c += (m < thr) ? 1 : 0;
-    }
-    sizes[i] = c;
+  for (int i = threadIdx.x; i < n; i += blockDim.x) sizes[i] = 1;    // coherent with itself
+  __syncthreads();
+  // every unordered pair once (the reference evaluates (i, j), i < j, and credits both sets)
+  const long long npairs = (long long)n * (n - 1) / 2;
+  for (long long q = threadIdx.x; q < npairs; q += blockDim.x) {
+    // q -> (i, j), i < j, row-major over the strict upper triangle
+    int i = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * (double)q)) * 0.5);
+    long long base = (long long)i * (2 * n - i - 1) / 2;
+    while (base > q) { --i; base = (long long)i * (2 * n - i - 1) / 2; }
+    while (base + (n - i - 1) <= q) { base += (n - i - 1); ++i; }
+    int j = i + 1 + (int)(q - base);
+    float m = maha_f32(relf + 3 * i, covf + 9 * i, relf + 3 * j, covf + 9 * j);
+    if (m < thr) { atomicAdd(&sizes[i], 1); atomicAdd(&sizes[j], 1); }
   }
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x < 32) {                       // first maximum (strict >), warp arg-max
     int ms = 0, mi = 0;
-    for (int i = 0; i < n; ++i) if (sizes[i] > ms) { ms = sizes[i]; mi = i; }
-    s_maxid = mi; s_maxsize = ms; s_ninl = 0;
+    for (int i = threadIdx.x; i < n; i += 32) if (sizes[i] > ms) { ms = sizes[i]; mi = i; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+      int os = __shfl_xor_sync(KVFE_FULL_MASK, ms, o), oi = __shfl_xor_sync(KVFE_FULL_MASK, mi, o);
+      if (os > ms || (os == ms && oi < mi)) { ms = os; mi = oi; }
+    }
+    if (threadIdx.x == 0) { s_maxid = mi; s_maxsize = ms; s_ninl = 0; }
   }
   __syncthreads();
   if (s_maxsize < 2) {
@@ -413,6 +426,11 @@ __device__ int voting_1pt(const DevCfg& dc, int n, const double* rel, const doub
       f = maha_f32(relf + 3 * lo, covf + 9 * lo, relf + 3 * hi, covf + 9 * hi) < thr ? 1 : 0;
     }
     inl[i] = f;
+    if (f) {                                    // information matrix in place of the covariance
+      double im[9];
+      inv3_eigen(cov + 9 * i, im);
+      for (int q = 0; q < 9; ++q) cov[9 * i + q] = im[q];
+    }
   }
   __syncthreads();
   // translation = (sum info)^-1 sum info * rel over inliers in ascending order; 12 lanes, one
@@ -423,8 +441,7 @@ __device__ int voting_1pt(const DevCfg& dc, int n, const double* rel, const doub
     for (int i = 0; i < n; ++i) {
       if (!inl[i]) continue;
       ++cnt;
-      double im[9];
-      inv3_eigen(cov + 9 * i, im);
+      const double* im = cov + 9 * i;
       double term;
       if (threadIdx.x < 3) term = dot3(im + 3 * threadIdx.x, rel + 3 * i);
       else term = im[threadIdx.x - 3];

@@ -73,34 +73,53 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf 
   if (scx < 0) scx = 0;
   // cv::Rect of the template / stripe must lie inside the image (OpenCV would assert otherwise)
   tcx = clampi(tcx, 0, max(W - tc, 0));
+  // shared memory: template rows padded to a multiple of 4 bytes (zero pad), stripe rows padded so
+  // that every shifted 4-byte window can be assembled from two aligned words, then the scores.
+  const int tstride = (tc + 3) & ~3;
+  const int sstride = ((sc + 3) & ~3) + 8;
   unsigned char* templ = smraw;
-  unsigned char* stripe = smraw + ((tc * tr + 15) & ~15);
-  int* score = reinterpret_cast<int*>(stripe + ((sc * sr + 15) & ~15));
+  unsigned char* stripe = smraw + ((tstride * tr + 15) & ~15);
+  int* score = reinterpret_cast<int*>(stripe + ((sstride * sr + 15) & ~15));
   const unsigned char* L = db.rectL + (size_t)b * dc.img_stride;
   const unsigned char* R = db.rectR + (size_t)b * dc.img_stride;
-  for (int t = threadIdx.x; t < tc * tr; t += blockDim.x) {
-    int r = t / tc, c = t - r * tc;
-    templ[t] = L[(size_t)(tcy + r) * dc.pitch + tcx + c];
+  for (int t = threadIdx.x; t < tstride * tr; t += blockDim.x) {
+    int r = t / tstride, c = t - r * tstride;
+    templ[t] = (c < tc) ? L[(size_t)(tcy + r) * dc.pitch + tcx + c] : 0;
   }
-  for (int t = threadIdx.x; t < sc * sr; t += blockDim.x) {
-    int r = t / sc, c = t - r * sc;
-    stripe[t] = R[(size_t)(scy + r) * dc.pitch + scx + c];
+  for (int t = threadIdx.x; t < sstride * sr; t += blockDim.x) {
+    int r = t / sstride, c = t - r * sstride;
+    stripe[t] = (c < sc) ? R[(size_t)(scy + r) * dc.pitch + scx + c] : 0;
   }
   __syncthreads();
   const int npos_x = sc - tc + 1, npos_y = sr - tr + 1;
   const int npos = npos_x * npos_y;
+  const int nwords = tstride >> 2;
+  // byte mask of the last template word (columns >= tc must not contribute to sum S^2)
+  const unsigned int lastmask = (tc & 3) ? (0xffffffffu >> (8 * (4 - (tc & 3)))) : 0xffffffffu;
+  // exact integer TM_SQDIFF = sum S^2 - 2 sum S*T + sum T^2, four pixels per dp4a
+  unsigned int tt = 0;
+  for (int r = 0; r < tr; ++r) {
+    const unsigned int* tw = reinterpret_cast<const unsigned int*>(templ + r * tstride);
+    for (int w = 0; w < nwords; ++w) tt = __dp4a(tw[w], tw[w], tt);
+  }
   for (int p = threadIdx.x; p < npos; p += blockDim.x) {
-    int py = p / npos_x, px = p - py * npos_x;
-    int acc = 0;
+    const int py = p / npos_x, px = p - py * npos_x;
+    const int sh = 8 * (px & 3);
+    unsigned int st = 0, ss = 0;
     for (int r = 0; r < tr; ++r) {
-      const unsigned char* sp = stripe + (py + r) * sc + px;
-      const unsigned char* tp = templ + r * tc;
-      for (int c = 0; c < tc; ++c) {
-        int d = (int)sp[c] - (int)tp[c];
-        acc += d * d;
+      const unsigned int* sw = reinterpret_cast<const unsigned int*>(stripe + (py + r) * sstride) + (px >> 2);
+      const unsigned int* tw = reinterpret_cast<const unsigned int*>(templ + r * tstride);
+      unsigned int lo = sw[0];
+      for (int w = 0; w < nwords; ++w) {
+        const unsigned int hi = sw[w + 1];
+        unsigned int v = __funnelshift_r(lo, hi, sh);
+        lo = hi;
+        st = __dp4a(v, tw[w], st);
+        if (w == nwords - 1) v &= lastmask;
+        ss = __dp4a(v, v, ss);
       }
     }
-    score[p] = acc;
+    score[p] = (int)(ss + tt - 2u * st);
   }
   __syncthreads();
   // first minimum in row-major order (cv::minMaxLoc)
@@ -198,7 +217,8 @@ int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_c
                          cudaStream_t s) {
   int n = 0;
   left_rect_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); ++n;
-  size_t sm = ((dc.templ_cols * dc.templ_rows + 15) & ~15) + ((dc.stripe_cols * dc.stripe_rows + 15) & ~15) +
+  const int tstride = (dc.templ_cols + 3) & ~3, sstride = ((dc.stripe_cols + 3) & ~3) + 8;
+  size_t sm = ((tstride * dc.templ_rows + 15) & ~15) + ((sstride * dc.stripe_rows + 15) & ~15) +
               sizeof(int) * (size_t)(dc.stripe_cols - dc.templ_cols + 1) * (dc.stripe_rows - dc.templ_rows + 1);
   if (sm < (size_t)SUBPIX_PATCH * 4) sm = (size_t)SUBPIX_PATCH * 4;
   static size_t attr = 0;
