@@ -214,7 +214,188 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
   }
 }
 
+// ------------------------------------------------------------------------------------------------
+// Register-resident specialisation for windows that are a multiple of 8 (Euroc: 24): lane x owns
+// column x of the window.  Patch columns are loaded one row at a time (a coalesced 27-byte row per
+// instruction), right-hand neighbours come from warp shuffles, the fixed-point window I / Ix / Iy
+// lives in registers, and nothing goes through shared memory.  Arithmetic identical to lk_kernel.
+// ------------------------------------------------------------------------------------------------
+template <int WIN>
+__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf db, int prev_slot, int cur_slot) {
+  constexpr int PW = WIN + 3, TW = WIN + 1;
+  const int b = blockIdx.y;
+  const StreamState& st = db.st[b];
+  if (st.mode == 0) return;
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int pt = blockIdx.x * LK_WARPS + warp;
+  if (pt >= st.n_ref) return;
+  const size_t gi = (size_t)b * dc.cap + pt;
+  const unsigned char* prevPyr = db.pyr[prev_slot] + (size_t)b * dc.pyr_stride;
+  const unsigned char* nextPyr = db.pyr[cur_slot] + (size_t)b * dc.pyr_stride;
+  const float halfWin = (WIN - 1) * 0.5f;
+  const float px0 = db.lk_px[gi], py0 = db.lk_py[gi];
+  float nx = db.lk_qx[gi], ny = db.lk_qy[gi];
+  bool status = true;
+  const int maxLevel = dc.n_levels - 1;
+  const float FLT_SCALE = 1.f / (1 << 20);
+
+  for (int level = maxLevel; level >= 0; --level) {
+    const int cols = dc.lvl_w[level], rows = dc.lvl_h[level], pitch = dc.lvl_pitch[level];
+    const unsigned char* I = prevPyr + dc.lvl_off[level];
+    const unsigned char* Jimg = nextPyr + dc.lvl_off[level];
+    const float scl = (float)(1. / (1 << level));
+    float ppx = px0 * scl, ppy = py0 * scl;
+    if (level == maxLevel) { nx = nx * scl; ny = ny * scl; }
+    else { nx = nx * 2.f; ny = ny * 2.f; }
+    ppx -= halfWin; ppy -= halfWin;
+    const int ipx = cv_floor(ppx), ipy = cv_floor(ppy);
+    if (ipx < -WIN || ipx >= cols || ipy < -WIN || ipy >= rows) {
+      if (level == 0) status = false;
+      continue;
+    }
+    float a = ppx - ipx, bb = ppy - ipy;
+    int iw00 = cv_round((1.f - a) * (1.f - bb) * (1 << 14));
+    int iw01 = cv_round(a * (1.f - bb) * (1 << 14));
+    int iw10 = cv_round((1.f - a) * bb * (1 << 14));
+    int iw11 = (1 << 14) - iw00 - iw01 - iw10;
+
+    // ---- window of I, Ix, Iy (registers) streamed over the (WIN+3) patch rows
+    int wI[WIN], wIx[WIN], wIy[WIN];
+    {
+      const int colx = reflect101(ipx - 1 + min(lane, PW - 1), cols);
+      const bool xin = (ipx + lane) >= 0 && (ipx + lane) < cols;     // derivative tap column inside the image
+      int L0 = 0, C0 = 0, R0 = 0, L1 = 0, C1 = 0, R1 = 0;             // patch rows r-2, r-1
+      int dxp = 0, dyp = 0, dxpn = 0, dypn = 0;                      // derivative row d-1 (own, right neighbour)
+#pragma unroll
+      for (int r = 0; r < PW; ++r) {
+        const int yy = reflect101(ipy - 1 + r, rows);
+        const int L2 = I[(size_t)yy * pitch + colx];
+        const int C2 = __shfl_down_sync(KVFE_FULL_MASK, L2, 1);
+        const int R2 = __shfl_down_sync(KVFE_FULL_MASK, L2, 2);
+        if (r >= 2) {
+          const int d = r - 2;                                        // derivative row (tap row ipy + d)
+          int dx = 3 * (R0 - L0) + 10 * (R1 - L1) + 3 * (R2 - L2);
+          int dy = 3 * (L2 - L0) + 10 * (C2 - C0) + 3 * (R2 - R0);
+          const bool yin = (ipy + d) >= 0 && (ipy + d) < rows;
+          if (!(xin && yin)) { dx = 0; dy = 0; }
+          const int dxn = __shfl_down_sync(KVFE_FULL_MASK, dx, 1);
+          const int dyn = __shfl_down_sync(KVFE_FULL_MASK, dy, 1);
+          if (d >= 1) {
+            const int y = d - 1;                                      // window row
+            // I taps: patch rows y+1 = d (C0, R0) and y+2 = d+1 (C1, R1)
+            wI[y] = descale(C0 * iw00 + R0 * iw01 + C1 * iw10 + R1 * iw11, 14 - 5);
+            wIx[y] = descale(dxp * iw00 + dxpn * iw01 + dx * iw10 + dxn * iw11, 14);
+            wIy[y] = descale(dyp * iw00 + dypn * iw01 + dy * iw10 + dyn * iw11, 14);
+          }
+          dxp = dx; dyp = dy; dxpn = dxn; dypn = dyn;
+        }
+        L0 = L1; C0 = C1; R0 = R1; L1 = L2; C1 = C2; R1 = R2;
+      }
+    }
+    // ---- structure tensor: OpenCV lane c = x % 4, row-major sequential float accumulation
+    float A11, A12, A22;
+    {
+      float a11 = 0.f, a12 = 0.f, a22 = 0.f;      // chains live on lanes 0..3
+      const int src0 = lane & 3;
+#pragma unroll
+      for (int y = 0; y < WIN; ++y) {
+        const float pxx = (float)(wIx[y] * wIx[y]), pxy = (float)(wIx[y] * wIy[y]), pyy = (float)(wIy[y] * wIy[y]);
+#pragma unroll
+        for (int t = 0; t < WIN / 4; ++t) {
+          a11 = a11 + __shfl_sync(KVFE_FULL_MASK, pxx, src0 + 4 * t);
+          a12 = a12 + __shfl_sync(KVFE_FULL_MASK, pxy, src0 + 4 * t);
+          a22 = a22 + __shfl_sync(KVFE_FULL_MASK, pyy, src0 + 4 * t);
+        }
+      }
+      // (L0 + L2) + (L1 + L3)
+      float t11 = (__shfl_sync(KVFE_FULL_MASK, a11, 0) + __shfl_sync(KVFE_FULL_MASK, a11, 2)) +
+                  (__shfl_sync(KVFE_FULL_MASK, a11, 1) + __shfl_sync(KVFE_FULL_MASK, a11, 3));
+      float t12 = (__shfl_sync(KVFE_FULL_MASK, a12, 0) + __shfl_sync(KVFE_FULL_MASK, a12, 2)) +
+                  (__shfl_sync(KVFE_FULL_MASK, a12, 1) + __shfl_sync(KVFE_FULL_MASK, a12, 3));
+      float t22 = (__shfl_sync(KVFE_FULL_MASK, a22, 0) + __shfl_sync(KVFE_FULL_MASK, a22, 2)) +
+                  (__shfl_sync(KVFE_FULL_MASK, a22, 1) + __shfl_sync(KVFE_FULL_MASK, a22, 3));
+      A11 = t11 * FLT_SCALE; A12 = t12 * FLT_SCALE; A22 = t22 * FLT_SCALE;
+    }
+    float D = A11 * A22 - A12 * A12;
+    float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
+    if (minEig < dc.min_eig_thr || D < 1.1920929e-07f) {
+      if (level == 0) status = false;
+      continue;
+    }
+    D = 1.f / D;
+    float qx = nx - halfWin, qy = ny - halfWin;
+    float pdx = 0.f, pdy = 0.f;
+    for (int j = 0; j < dc.max_iter; ++j) {
+      const int iqx = cv_floor(qx), iqy = cv_floor(qy);
+      if (iqx < -WIN || iqx >= cols || iqy < -WIN || iqy >= rows) {
+        if (level == 0) status = false;
+        break;
+      }
+      a = qx - iqx; bb = qy - iqy;
+      iw00 = cv_round((1.f - a) * (1.f - bb) * (1 << 14));
+      iw01 = cv_round(a * (1.f - bb) * (1 << 14));
+      iw10 = cv_round((1.f - a) * bb * (1 << 14));
+      iw11 = (1 << 14) - iw00 - iw01 - iw10;
+      // J patch column of this lane: all TW row loads are issued first
+      const int colx = reflect101(iqx + min(lane, TW - 1), cols);
+      int Jc[TW];
+      if (iqy >= 0 && iqy + TW <= rows) {
+        const unsigned char* jp = Jimg + (size_t)iqy * pitch + colx;
+#pragma unroll
+        for (int r = 0; r < TW; ++r) Jc[r] = jp[(size_t)r * pitch];
+      } else {
+#pragma unroll
+        for (int r = 0; r < TW; ++r) Jc[r] = Jimg[(size_t)reflect101(iqy + r, rows) * pitch + colx];
+      }
+      // mismatch vector with OpenCV's SIMD128 order: chain m (lanes 0..3) over groups of 8 pixels
+      float b1 = 0.f, b2 = 0.f;
+      int jr0 = __shfl_down_sync(KVFE_FULL_MASK, Jc[0], 1);
+#pragma unroll
+      for (int y = 0; y < WIN; ++y) {
+        const int jr1 = __shfl_down_sync(KVFE_FULL_MASK, Jc[y + 1], 1);
+        const int diff = descale(Jc[y] * iw00 + jr0 * iw01 + Jc[y + 1] * iw10 + jr1 * iw11, 14 - 5) - wI[y];
+        jr0 = jr1;
+        int t1 = diff * wIx[y], t2 = diff * wIy[y];
+        t1 += __shfl_down_sync(KVFE_FULL_MASK, t1, 4);        // pixels (x, x + 4), valid where (x & 4) == 0
+        t2 += __shfl_down_sync(KVFE_FULL_MASK, t2, 4);
+        const float f1 = (float)t1, f2 = (float)t2;
+        const int m = lane & 3;
+#pragma unroll
+        for (int q = 0; q < WIN / 8; ++q) {
+          b1 = b1 + __shfl_sync(KVFE_FULL_MASK, f1, m + 8 * q);
+          b2 = b2 + __shfl_sync(KVFE_FULL_MASK, f2, m + 8 * q);
+        }
+      }
+      {
+        float t1 = (__shfl_sync(KVFE_FULL_MASK, b1, 0) + __shfl_sync(KVFE_FULL_MASK, b1, 2)) +
+                   (__shfl_sync(KVFE_FULL_MASK, b1, 1) + __shfl_sync(KVFE_FULL_MASK, b1, 3));
+        float t2 = (__shfl_sync(KVFE_FULL_MASK, b2, 0) + __shfl_sync(KVFE_FULL_MASK, b2, 2)) +
+                   (__shfl_sync(KVFE_FULL_MASK, b2, 1) + __shfl_sync(KVFE_FULL_MASK, b2, 3));
+        b1 = t1 * FLT_SCALE; b2 = t2 * FLT_SCALE;
+      }
+      float dxv = (float)((A12 * b2 - A22 * b1) * D);
+      float dyv = (float)((A12 * b1 - A11 * b2) * D);
+      qx += dxv; qy += dyv;
+      nx = qx + halfWin; ny = qy + halfWin;
+      if ((double)dxv * (double)dxv + (double)dyv * (double)dyv <= (double)dc.eps2) break;
+      if (j > 0 && fabsf(dxv + pdx) < 0.01 && fabsf(dyv + pdy) < 0.01) {
+        nx -= dxv * 0.5f; ny -= dyv * 0.5f;
+        break;
+      }
+      pdx = dxv; pdy = dyv;
+    }
+  }
+  if (lane == 0) {
+    db.lk_qx[gi] = nx; db.lk_qy[gi] = ny;
+    db.lk_status[gi] = status ? 1 : 0;
+  }
+}
+
 int launch_lk(const DevCfg& dc, const DevBuf& db, int prev_slot, int cur_slot, cudaStream_t s) {
+  dim3 grid((dc.cap + LK_WARPS - 1) / LK_WARPS, dc.B);
+  if (dc.win == 24) { lk_kernel_reg<24><<<grid, LK_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
+  if (dc.win == 16) { lk_kernel_reg<16><<<grid, LK_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
+  if (dc.win == 8) { lk_kernel_reg<8><<<grid, LK_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
   size_t sm = LK_WARPS * lk_warp_bytes(dc.win);
   static size_t attr = 0;
   if (sm > 48 * 1024 && sm > attr) {
