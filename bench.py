@@ -189,37 +189,47 @@ def run_gpu(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, K, Wm = args.batch, args.steps, args.warmup
+    B, K, Wm, NC = args.batch, args.steps, args.warmup, args.contexts
+    assert B % NC == 0
+    Bc = B // NC                                   # streams per context (sub-batch in flight on its own CUDA stream)
     n_frames = Wm + K
     rig = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
     left, right, rot = frame_pool(n_frames, rig)
     p = FrontendParams.euroc()
-    cfg = kl.make_config(p, W, H, batch=B)
-    ctx = kl.Context(cfg, rig.to_c())
-    stream = torch.cuda.ExternalStream(kl.load().kvfe_cuda_stream(ctx.h))
+    ctxs = [kl.Context(kl.make_config(p, W, H, batch=Bc), rig.to_c()) for _ in range(NC)]
+    streams = [torch.cuda.ExternalStream(kl.load().kvfe_cuda_stream(c.h)) for c in ctxs]
+    pkb = ctxs[0].packet_bytes
+
+    def slot(c, i):                                # global batch slot of context c, local stream i
+        return c * Bc + i
 
     # IMU rotations need the last-keyframe index per slot, which depends on the device-side keyframe
     # decisions: run the sequence once (untimed, host path) to learn the keyframe schedule.
-    def host_ptrs(k):
-        lp = (C.c_void_p * B)(*[left[b % POOL_STREAMS, k].ctypes.data for b in range(B)])
-        rp = (C.c_void_p * B)(*[right[b % POOL_STREAMS, k].ctypes.data for b in range(B)])
-        return lp, rp
     ts_all = np.array([[slot_timestamp(rank * B + b, k) for b in range(B)] for k in range(n_frames)], np.int64)
     lkf = np.zeros(B, np.int64)
     R_all = np.zeros((n_frames, B, 9))
     kf_sched = np.zeros((n_frames, B), bool)
-    pk_buf = np.empty(B * ctx.packet_bytes, np.uint8)
+    pk_buf = np.empty(Bc * pkb, np.uint8)
+    n_kp = []
     for k in range(n_frames):
         for b in range(B):
             R_all[k, b] = rot[b % POOL_STREAMS, lkf[b], k].reshape(9)
-        lp, rp = host_ptrs(k)
-        rc = ctx.step_raw(lp, rp, W, ts_all[k], R_all[k], pk_buf)
-        assert rc == 0, kl.load().kvfe_last_error(ctx.h)
-        for b, pk in enumerate(ctx.parse_packets(pk_buf)):
-            if pk["is_keyframe"]:
-                lkf[b] = k
-                kf_sched[k, b] = True
-    n_kp_mean = float(np.mean([pk["n"] for pk in ctx.parse_packets(pk_buf)]))
+        for c, ctx in enumerate(ctxs):
+            lp = (C.c_void_p * Bc)(*[left[slot(c, i) % POOL_STREAMS, k].ctypes.data for i in range(Bc)])
+            rp = (C.c_void_p * Bc)(*[right[slot(c, i) % POOL_STREAMS, k].ctypes.data for i in range(Bc)])
+            tsk = np.ascontiguousarray(ts_all[k, c * Bc:(c + 1) * Bc])
+            Rk = np.ascontiguousarray(R_all[k, c * Bc:(c + 1) * Bc])
+            rc = ctx.step_raw(lp, rp, W, tsk, Rk, pk_buf)
+            assert rc == 0, kl.load().kvfe_last_error(ctx.h)
+            for i, pk in enumerate(ctx.parse_packets(pk_buf)):
+                if pk["is_keyframe"]:
+                    lkf[slot(c, i)] = k
+                    kf_sched[k, slot(c, i)] = True
+                if k == n_frames - 1:
+                    n_kp.append(pk["n"])
+    n_kp_mean = float(np.mean(n_kp))
+    ts_c = [[np.ascontiguousarray(ts_all[k, c * Bc:(c + 1) * Bc]) for k in range(n_frames)] for c in range(NC)]
+    R_c = [[np.ascontiguousarray(R_all[k, c * Bc:(c + 1) * Bc]) for k in range(n_frames)] for c in range(NC)]
 
     def barrier():
         if world > 1:
@@ -227,53 +237,74 @@ def run_gpu(args):
         torch.cuda.synchronize()
 
     # ---------------- device-resident measurement (value) ----------------
-    dL = torch.empty((n_frames, B, H, W), dtype=torch.uint8, device="cuda")
+    dL = torch.empty((NC, n_frames, Bc, H, W), dtype=torch.uint8, device="cuda")
     dR = torch.empty_like(dL)
-    for k in range(n_frames):
-        for b in range(B):
-            dL[k, b].copy_(torch.from_numpy(left[b % POOL_STREAMS, k]))
-            dR[k, b].copy_(torch.from_numpy(right[b % POOL_STREAMS, k]))
+    for c in range(NC):
+        for k in range(n_frames):
+            for i in range(Bc):
+                dL[c, k, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
+                dR[c, k, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
     torch.cuda.synchronize()
 
     def run_dev(k0, k1):
         for k in range(k0, k1):
-            rc = ctx.step_dev(dL[k].data_ptr(), dR[k].data_ptr(), W, ts_all[k], R_all[k])
-            assert rc == 0
+            for c, ctx in enumerate(ctxs):
+                rc = ctx.step_dev(dL[c, k].data_ptr(), dR[c, k].data_ptr(), W, ts_c[c][k], R_c[c][k])
+                assert rc == 0
 
     sampler = ClockSampler(local)
-    ctx.reset()
+    for ctx in ctxs:
+        ctx.reset()
     run_dev(0, Wm)
     barrier()
-    launches0 = ctx.launches
-    ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    launches0 = sum(c.launches for c in ctxs)
+    ev0 = torch.cuda.Event(enable_timing=True)
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
     with sampler:
-        ev0.record(stream)
+        ev0.record(streams[0])
+        for st in streams[1:]:
+            st.wait_event(ev0)
         run_dev(Wm, n_frames)
-        ev1.record(stream)
+        for e, st in zip(ev1, streams):
+            e.record(st)
         barrier()
-    dev_ms = ev0.elapsed_time(ev1)
-    launches = ctx.launches - launches0
+    dev_ms = max(ev0.elapsed_time(e) for e in ev1)
+    launches = sum(c.launches for c in ctxs) - launches0
     clocks = sampler.summary()
 
     # ---------------- end-to-end measurement through host buffers (e2e) ----------------
-    import ctypes
-    pinL = torch.empty((n_frames, B, H, W), dtype=torch.uint8).pin_memory()
+    pinL = torch.empty((NC, n_frames, Bc, H, W), dtype=torch.uint8).pin_memory()
     pinR = torch.empty_like(pinL).pin_memory()
-    for k in range(n_frames):
-        for b in range(B):
-            pinL[k, b].copy_(torch.from_numpy(left[b % POOL_STREAMS, k]))
-            pinR[k, b].copy_(torch.from_numpy(right[b % POOL_STREAMS, k]))
-    pk_pin = torch.empty(B * ctx.packet_bytes, dtype=torch.uint8).pin_memory()
-    pk_np = pk_pin.numpy()
-    ptrs = [((C.c_void_p * B)(*[pinL[k, b].data_ptr() for b in range(B)]),
-             (C.c_void_p * B)(*[pinR[k, b].data_ptr() for b in range(B)])) for k in range(n_frames)]
+    for c in range(NC):
+        for k in range(n_frames):
+            for i in range(Bc):
+                pinL[c, k, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
+                pinR[c, k, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
+    pk_pin = [torch.empty(Bc * pkb, dtype=torch.uint8).pin_memory() for _ in range(NC)]
+    pk_np = [t.numpy() for t in pk_pin]
+    ptrs = [[((C.c_void_p * Bc)(*[pinL[c, k, i].data_ptr() for i in range(Bc)]),
+              (C.c_void_p * Bc)(*[pinR[c, k, i].data_ptr() for i in range(Bc)])) for k in range(n_frames)]
+            for c in range(NC)]
 
-    def run_host(k0, k1):
+    def run_host_ctx(c, k0, k1):
+        ctx = ctxs[c]
         for k in range(k0, k1):
-            rc = ctx.step_raw(ptrs[k][0], ptrs[k][1], W, ts_all[k], R_all[k], pk_np)
+            rc = ctx.step_raw(ptrs[c][k][0], ptrs[c][k][1], W, ts_c[c][k], R_c[c][k], pk_np[c])
             assert rc == 0
 
-    ctx.reset()
+    def run_host(k0, k1):
+        if NC == 1:
+            run_host_ctx(0, k0, k1)
+            return
+        # one host thread per context: the blocking C-ABI call releases the GIL (ctypes)
+        th = [threading.Thread(target=run_host_ctx, args=(c, k0, k1)) for c in range(NC)]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
+
+    for ctx in ctxs:
+        ctx.reset()
     run_host(0, Wm)
     barrier()
     t0 = time.perf_counter()
@@ -301,13 +332,14 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": "Euroc stereo 752x480, %d feats, 1xB200 batch=%d frame-pairs per step "
                                    "(BASELINE.json configs[1]); %d independent streams per GPU" % (N_FEATS, B, B),
-                       "batch_per_gpu": B, "keyframe_ratio": rho, "mean_keypoints": n_kp_mean,
-                       "timing": "CUDA events on the library stream, max over ranks; every step reads fresh "
+                       "batch_per_gpu": B, "sub_batches_in_flight": NC, "keyframe_ratio": rho,
+                       "mean_keypoints": n_kp_mean,
+                       "timing": "CUDA events on the library streams, max over ranks; every step reads fresh "
                                  "device-resident inputs (%d MB per rank > L2), no L2 flush" %
                                  (2 * n_frames * B * H * W // 2 ** 20)},
             "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": e2e_ms / K,
                     "h2d_bytes_per_step": int(2 * B * W * H + B * 80),
-                    "d2h_bytes_per_step": int(B * ctx.packet_bytes)},
+                    "d2h_bytes_per_step": int(B * pkb)},
             "gpu_launches": int(launches),
             "clocks": clocks,
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
@@ -318,7 +350,8 @@ def run_gpu(args):
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline_single(4, 24)
         print(json.dumps(line))
-    ctx.close()
+    for ctx in ctxs:
+        ctx.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -329,6 +362,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--contexts", type=int, default=1, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--impl", default="kvfe", choices=["kvfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -297,7 +297,7 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
     CU(dmalloc(&f.n, B * 3)); CU(dmalloc(&f.timestamp, B * 3)); CU(dmalloc(&f.frame_id, B * 3));
     CU(dmalloc(&f.kx, n)); CU(dmalloc(&f.ky, n)); CU(dmalloc(&f.lmk, n)); CU(dmalloc(&f.age, n));
     CU(dmalloc(&f.versor, 3 * n)); CU(dmalloc(&f.lstat, n)); CU(dmalloc(&f.lrx, n)); CU(dmalloc(&f.lry, n));
-    CU(dmalloc(&f.rstat, n)); CU(dmalloc(&f.rrx, n)); CU(dmalloc(&f.rry, n)); CU(dmalloc(&f.depth, n));
+    CU(dmalloc(&f.rstat, n)); CU(dmalloc(&f.mstat, n)); CU(dmalloc(&f.rrx, n)); CU(dmalloc(&f.rry, n)); CU(dmalloc(&f.depth, n));
     CU(dmalloc(&f.p3d, 3 * n)); CU(dmalloc(&f.rkx, n)); CU(dmalloc(&f.rky, n));
   }
   CU(dmalloc(&db.st, B));
@@ -325,7 +325,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
                   db.m_cur, db.m_n, db.inl, db.inl_n, db.rs_d, db.fr.n, db.fr.timestamp, db.fr.frame_id, db.fr.kx,
-                  db.fr.ky, db.fr.lmk, db.fr.age, db.fr.versor, db.fr.lstat, db.fr.lrx, db.fr.lry, db.fr.rstat,
+                  db.fr.ky, db.fr.lmk, db.fr.age, db.fr.versor, db.fr.lstat, db.fr.lrx, db.fr.lry, db.fr.rstat, db.fr.mstat,
                   db.fr.rrx, db.fr.rry, db.fr.depth, db.fr.p3d, db.fr.rkx, db.fr.rky, db.st, db.packets, ctx->d_ts,
                   ctx->d_Rin};
   for (void* p : ptrs) if (p) cudaFree(p);
@@ -376,9 +376,17 @@ static int park_other_streams(kvfe_ctx* ctx) {
   return KVFE_OK;
 }
 
-static int upload_image(kvfe_ctx* ctx, unsigned char* dst, int dst_pitch, const uint8_t* src, size_t pitch) {
-  CU(cudaMemcpy2DAsync(dst, dst_pitch, src, pitch, ctx->dc.W, ctx->dc.H, cudaMemcpyHostToDevice, ctx->stream));
+// image copies: a single contiguous transfer when both sides are densely packed (the common case:
+// pitch == width), else a strided 2-D copy
+static int copy_image(kvfe_ctx* ctx, void* dst, size_t dst_pitch, const void* src, size_t src_pitch,
+                      cudaMemcpyKind kind) {
+  const size_t W = ctx->dc.W, H = ctx->dc.H;
+  if (dst_pitch == W && src_pitch == W) CU(cudaMemcpyAsync(dst, src, W * H, kind, ctx->stream));
+  else CU(cudaMemcpy2DAsync(dst, dst_pitch, src, src_pitch, W, H, kind, ctx->stream));
   return KVFE_OK;
+}
+static int upload_image(kvfe_ctx* ctx, unsigned char* dst, int dst_pitch, const uint8_t* src, size_t pitch) {
+  return copy_image(ctx, dst, dst_pitch, src, pitch, cudaMemcpyHostToDevice);
 }
 static int download_image(kvfe_ctx* ctx, uint8_t* dst, size_t pitch, const unsigned char* src, int src_pitch) {
   CU(cudaMemcpy2DAsync(dst, pitch, src, src_pitch, ctx->dc.W, ctx->dc.H, cudaMemcpyDeviceToHost, ctx->stream));
@@ -615,7 +623,7 @@ extern "C" int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint
   RET(upload_image(ctx, db.right_raw, dc.pitch, right, pitch));
   ctx->launches += launch_rectify(dc, ctx->d_cam, 0, L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
   ctx->launches += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
-  ctx->launches += launch_sparse_stereo(dc, db, ctx->d_cam, 1 << 2, ctx->stream);
+  ctx->launches += launch_sparse_stereo(dc, db, ctx->d_cam, 1 << 2, 0, ctx->stream);
   CHECK_LAUNCH();
   CU(cudaStreamSynchronize(ctx->stream));
   const FrameSoA& f = db.fr;
@@ -757,7 +765,7 @@ static int enqueue_step(kvfe_ctx* ctx) {
   n += launch_ransac_mono(dc, db, M_KF, s);
   n += launch_rectify(dc, ctx->d_cam, 0, Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
   n += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
-  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_KF, s);
+  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_KF, 0, s);
   n += launch_ransac_stereo(dc, db, M_KF, s);
   // detection (bootstrap, keyframe, all-tracks-lost)
   n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, s);
@@ -765,7 +773,7 @@ static int enqueue_step(kvfe_ctx* ctx) {
   n += launch_select(dc, db, Lcur, dc.pyr_stride, ctx->d_cam, M_BOOT | M_KF | M_LOST, 1, s);
   // sparse stereo over all keypoints incl. the new ones (the second remap of the reference is
   // idempotent -- same raw images, same maps -- and is therefore not repeated)
-  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, s);
+  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, 1, s);
   n += launch_finalize(dc, db, s);
   ctx->launches += n;
   CU(cudaGetLastError());
@@ -799,10 +807,10 @@ extern "C" int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, co
   RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
   // device-to-device placement into the pyramid slot / right buffer (strided destination)
   for (size_t b = 0; b < B; ++b) {
-    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
-                         left_dev + b * pitch * dc.H, pitch, dc.W, dc.H, cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpy2DAsync(db.right_raw + b * dc.img_stride, dc.pitch, right_dev + b * pitch * dc.H, pitch, dc.W, dc.H,
-                         cudaMemcpyDeviceToDevice, s));
+    RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
+                   left_dev + b * pitch * dc.H, pitch, cudaMemcpyDeviceToDevice));
+    RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right_dev + b * pitch * dc.H, pitch,
+                   cudaMemcpyDeviceToDevice));
   }
   return enqueue_step(ctx);
 }
@@ -815,10 +823,9 @@ extern "C" int kvfe_frontend_step(kvfe_ctx* ctx, const uint8_t* const* left, con
   const size_t B = dc.B;
   RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
   for (size_t b = 0; b < B; ++b) {
-    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch, left[b], pitch, dc.W,
-                         dc.H, cudaMemcpyHostToDevice, s));
-    CU(cudaMemcpy2DAsync(db.right_raw + b * dc.img_stride, dc.pitch, right[b], pitch, dc.W, dc.H,
-                         cudaMemcpyHostToDevice, s));
+    RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch, left[b], pitch,
+                   cudaMemcpyHostToDevice));
+    RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right[b], pitch, cudaMemcpyHostToDevice));
   }
   RET(enqueue_step(ctx));
   CU(cudaMemcpyAsync(ctx->h_packets, db.packets, B * db.packet_bytes, cudaMemcpyDeviceToHost, s));

@@ -204,24 +204,27 @@ __global__ void __launch_bounds__(256) cand_kernel(DevCfg dc, DevBuf db, int mod
   const int b = blockIdx.z;
   if (!mode_on(db.st[b].mode, mode_mask)) return;
   const int W = dc.W, H = dc.H;
-  const int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x < 1 || y < 1 || x > W - 2 || y > H - 2) return;
+  const int x = blockIdx.x * 32 + (threadIdx.x & 31);
   const float* e = db.eig + (size_t)b * W * H;
   float maxv = ord2f(db.eig_max[b]);
   if (!(maxv > -INFINITY)) maxv = 0.f;              // empty mask: minMaxLoc leaves maxVal = 0
   const float thr = (float)((double)maxv * (double)dc.quality);
-  const float v = e[(size_t)y * W + x];
-  if (!(v > thr)) return;
-  if (!db.mask[(size_t)b * dc.img_stride + (size_t)y * dc.pitch + x]) return;
-  const float* r0 = e + (size_t)(y - 1) * W + x;
-  const float* r1 = r0 + W;
-  const float* r2 = r1 + W;
-  float nb = fmaxf(fmaxf(fmaxf(r0[-1], r0[0]), fmaxf(r0[1], r1[-1])), fmaxf(fmaxf(r1[1], r2[-1]), fmaxf(r2[0], r2[1])));
-  if (v < nb) return;
-  int slot = atomicAdd(&db.cand_n[b], 1);
-  if (slot < dc.cand_cap)
-    db.cand[(size_t)b * dc.cand_cap + slot] =
-        ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * W + x);
+  for (int k = 0; k < 8; ++k) {
+    const int y = blockIdx.y * 64 + k * 8 + (threadIdx.x >> 5);
+    if (x < 1 || y < 1 || x > W - 2 || y > H - 2) continue;
+    const float v = e[(size_t)y * W + x];
+    if (!(v > thr)) continue;
+    if (!db.mask[(size_t)b * dc.img_stride + (size_t)y * dc.pitch + x]) continue;
+    const float* r0 = e + (size_t)(y - 1) * W + x;
+    const float* r1 = r0 + W;
+    const float* r2 = r1 + W;
+    float nb = fmaxf(fmaxf(fmaxf(r0[-1], r0[0]), fmaxf(r0[1], r1[-1])), fmaxf(fmaxf(r1[1], r2[-1]), fmaxf(r2[0], r2[1])));
+    if (v < nb) continue;
+    int slot = atomicAdd(&db.cand_n[b], 1);
+    if (slot < dc.cand_cap)
+      db.cand[(size_t)b * dc.cand_cap + slot] =
+          ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * W + x);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -248,7 +251,8 @@ __device__ void bitonic_desc(unsigned long long* k, int P) {
   }
 }
 
-#define GREEDY_ACC_MAX 8192
+#define GREEDY_ACC_MAX 2048
+#define GREEDY_SMEM_CELLS 4096
 
 // Layout of the dynamic shared memory: skey[smem_keys] (candidates ordered by (cell, key desc)),
 // then acc[GREEDY_ACC_MAX].  When the candidates do not fit, skey lives in the global candidate
@@ -279,14 +283,18 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   }
 
   int* sc = db.scratch_i + (size_t)b * db.scratch_stride;
-  int* cstart = sc;                                   // [ncells + 1]
-  int* head = sc + (dc.cand_cap / 4);                 // [ncells]   (ncells << cand_cap / 4)
-  int* newacc = sc + 2 * (dc.cand_cap / 4);           // [ncells]
-  unsigned char* state = reinterpret_cast<unsigned char*>(sc + 3 * (dc.cand_cap / 4));   // [cand_cap]
-  unsigned long long* tmp = reinterpret_cast<unsigned long long*>(sc + dc.cand_cap);     // [cand_cap] keys by cell
   const int cell = md;                      // cvRound(minDistance), minDistance is an int parameter
   const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
   const int ncells = gw * gh;
+  // bookkeeping arrays: shared memory when the grid and the candidate list fit, else global scratch
+  unsigned char* sm_tail = reinterpret_cast<unsigned char*>(skeys + smem_keys + GREEDY_ACC_MAX);
+  const bool small = (ncells + 1 <= GREEDY_SMEM_CELLS) && (n <= smem_keys);
+  int* cstart = small ? reinterpret_cast<int*>(sm_tail) : sc;                                   // [ncells + 1]
+  int* head = small ? cstart + GREEDY_SMEM_CELLS : sc + (dc.cand_cap / 4);                      // [ncells]
+  int* newacc = small ? head + GREEDY_SMEM_CELLS : sc + 2 * (dc.cand_cap / 4);                  // [ncells]
+  unsigned char* state = small ? reinterpret_cast<unsigned char*>(newacc + GREEDY_SMEM_CELLS)
+                               : reinterpret_cast<unsigned char*>(sc + 3 * (dc.cand_cap / 4)); // [n]
+  unsigned long long* tmp = reinterpret_cast<unsigned long long*>(sc + dc.cand_cap);            // [cand_cap] keys by cell
   unsigned long long* sk = (n <= smem_keys) ? skeys : gk;
   // ---- 1. bucket by cell (counting sort) into tmp
   for (int i = tid; i <= ncells; i += blockDim.x) cstart[i] = 0;
@@ -455,9 +463,9 @@ int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, si
   mask_circles_kernel<<<dim3((dc.cap + 7) / 8, dc.B), 256, 0, s>>>(dc, db, circle_hw, circle_r, mode_mask); ++n;
   int groups = (dc.W + 29) / 30;
   mineig_kernel<<<dim3((groups + 3) / 4, dc.B), 128, 0, s>>>(dc, db, img, img_stride, mode_mask, 1); ++n;
-  cand_kernel<<<dim3((dc.W + 31) / 32, (dc.H + 7) / 8, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;
+  cand_kernel<<<dim3((dc.W + 31) / 32, (dc.H + 63) / 64, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;
   int smem_keys = 16384;
-  const int smem_bytes = (smem_keys + GREEDY_ACC_MAX) * 8;
+  const int smem_bytes = (smem_keys + GREEDY_ACC_MAX) * 8 + 3 * GREEDY_SMEM_CELLS * 4 + smem_keys;
   static bool attr_set = false;
   if (!attr_set) {
     cudaFuncSetAttribute(sort_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);

@@ -35,6 +35,7 @@ struct FrameSoA {        // flat arrays, index (stream*3 + slot)*cap + i
   double* versor;        // *3
   int* lstat; float *lrx, *lry;
   int* rstat; float *rrx, *rry;
+  int* mstat;            // status right after template matching (before depth / RANSAC rewrite it)
   double* depth;
   double* p3d;           // *3
   float *rkx, *rky;
@@ -178,7 +179,7 @@ int launch_select(const DevCfg& dc, const DevBuf& db, const unsigned char* img, 
                   const CamModel* d_cam, int mode_mask, int append, cudaStream_t s);
 // stereo.cu
 int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, int mode_mask,
-                         cudaStream_t s);
+                         int reuse_tracked, cudaStream_t s);
 int launch_undistort(const DevCfg& dc, const CamModel* d_cam, int cam, int use_R, int use_P,
                      const float* x, const float* y, int n, float* ox, float* oy, cudaStream_t s);
 int launch_bearing(const DevCfg& dc, const CamModel* d_cam, const float* x, const float* y, int n,

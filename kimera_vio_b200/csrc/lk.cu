@@ -215,20 +215,28 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
 }
 
 // ------------------------------------------------------------------------------------------------
-// Register-resident specialisation for windows that are a multiple of 8 (Euroc: 24): lane x owns
-// column x of the window.  Patch columns are loaded one row at a time (a coalesced 27-byte row per
-// instruction), right-hand neighbours come from warp shuffles, the fixed-point window I / Ix / Iy
-// lives in registers, and nothing goes through shared memory.  Arithmetic identical to lk_kernel.
+// Column-per-lane specialisation for windows that are a multiple of 8 (Euroc: 24): lane x owns
+// column x of the window.  Patch columns are loaded one row at a time (a coalesced <=27-byte row per
+// instruction), right-hand neighbours come from warp shuffles, the fixed-point window I / Ix / Iy is
+// kept in shared memory (conflict-free column access) so that the row loops stay rolled: small code
+// (no instruction-cache thrash), few registers, high occupancy.  Arithmetic identical to lk_kernel.
 // ------------------------------------------------------------------------------------------------
+#define LKC_WARPS 8
+#define LKC_CHUNK 6      // window rows per software-pipelined chunk of J loads
+
 template <int WIN>
-__global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf db, int prev_slot, int cur_slot) {
+__global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBuf db, int prev_slot, int cur_slot) {
   constexpr int PW = WIN + 3, TW = WIN + 1;
+  static_assert(WIN % LKC_CHUNK == 0 || WIN % 8 == 0, "window must be a multiple of 8");
+  __shared__ short sI[LKC_WARPS][WIN * WIN], sIx[LKC_WARPS][WIN * WIN], sIy[LKC_WARPS][WIN * WIN];
   const int b = blockIdx.y;
   const StreamState& st = db.st[b];
   if (st.mode == 0) return;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  const int pt = blockIdx.x * LK_WARPS + warp;
+  const int pt = blockIdx.x * LKC_WARPS + warp;
   if (pt >= st.n_ref) return;
+  short* wI = sI[warp]; short* wIx = sIx[warp]; short* wIy = sIy[warp];
+  const int xl = min(lane, WIN - 1);               // window column of this lane (lanes >= WIN idle copies)
   const size_t gi = (size_t)b * dc.cap + pt;
   const unsigned char* prevPyr = db.pyr[prev_slot] + (size_t)b * dc.pyr_stride;
   const unsigned char* nextPyr = db.pyr[cur_slot] + (size_t)b * dc.pyr_stride;
@@ -238,6 +246,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf
   bool status = true;
   const int maxLevel = dc.n_levels - 1;
   const float FLT_SCALE = 1.f / (1 << 20);
+  const int m4 = lane & 3;
 
   for (int level = maxLevel; level >= 0; --level) {
     const int cols = dc.lvl_w[level], rows = dc.lvl_h[level], pitch = dc.lvl_pitch[level];
@@ -258,22 +267,23 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf
     int iw01 = cv_round(a * (1.f - bb) * (1 << 14));
     int iw10 = cv_round((1.f - a) * bb * (1 << 14));
     int iw11 = (1 << 14) - iw00 - iw01 - iw10;
-
-    // ---- window of I, Ix, Iy (registers) streamed over the (WIN+3) patch rows
-    int wI[WIN], wIx[WIN], wIy[WIN];
+    __syncwarp();
+    // ---- window of I, Ix, Iy streamed over the (WIN+3) patch rows; structure tensor chains on the fly
+    float a11 = 0.f, a12 = 0.f, a22 = 0.f;         // OpenCV lane c = x % 4 chains live on lanes 0..3
     {
       const int colx = reflect101(ipx - 1 + min(lane, PW - 1), cols);
-      const bool xin = (ipx + lane) >= 0 && (ipx + lane) < cols;     // derivative tap column inside the image
-      int L0 = 0, C0 = 0, R0 = 0, L1 = 0, C1 = 0, R1 = 0;             // patch rows r-2, r-1
-      int dxp = 0, dyp = 0, dxpn = 0, dypn = 0;                      // derivative row d-1 (own, right neighbour)
-#pragma unroll
+      const bool xin = (ipx + lane) >= 0 && (ipx + lane) < cols;
+      int L0 = 0, C0 = 0, R0 = 0, L1 = 0, C1 = 0, R1 = 0;
+      int dxp = 0, dyp = 0, dxpn = 0, dypn = 0;
+      int Lnext = I[(size_t)reflect101(ipy - 1, rows) * pitch + colx];
+#pragma unroll 3
       for (int r = 0; r < PW; ++r) {
-        const int yy = reflect101(ipy - 1 + r, rows);
-        const int L2 = I[(size_t)yy * pitch + colx];
+        const int L2 = Lnext;
+        if (r + 1 < PW) Lnext = I[(size_t)reflect101(ipy + r, rows) * pitch + colx];   // prefetch next row
         const int C2 = __shfl_down_sync(KVFE_FULL_MASK, L2, 1);
         const int R2 = __shfl_down_sync(KVFE_FULL_MASK, L2, 2);
         if (r >= 2) {
-          const int d = r - 2;                                        // derivative row (tap row ipy + d)
+          const int d = r - 2;
           int dx = 3 * (R0 - L0) + 10 * (R1 - L1) + 3 * (R2 - L2);
           int dy = 3 * (L2 - L0) + 10 * (C2 - C0) + 3 * (R2 - R0);
           const bool yin = (ipy + d) >= 0 && (ipy + d) < rows;
@@ -281,32 +291,27 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf
           const int dxn = __shfl_down_sync(KVFE_FULL_MASK, dx, 1);
           const int dyn = __shfl_down_sync(KVFE_FULL_MASK, dy, 1);
           if (d >= 1) {
-            const int y = d - 1;                                      // window row
-            // I taps: patch rows y+1 = d (C0, R0) and y+2 = d+1 (C1, R1)
-            wI[y] = descale(C0 * iw00 + R0 * iw01 + C1 * iw10 + R1 * iw11, 14 - 5);
-            wIx[y] = descale(dxp * iw00 + dxpn * iw01 + dx * iw10 + dxn * iw11, 14);
-            wIy[y] = descale(dyp * iw00 + dypn * iw01 + dy * iw10 + dyn * iw11, 14);
+            const int y = d - 1;
+            const int iv = descale(C0 * iw00 + R0 * iw01 + C1 * iw10 + R1 * iw11, 14 - 5);
+            const int ix = descale(dxp * iw00 + dxpn * iw01 + dx * iw10 + dxn * iw11, 14);
+            const int iy = descale(dyp * iw00 + dypn * iw01 + dy * iw10 + dyn * iw11, 14);
+            if (lane < WIN) { wI[y * WIN + lane] = (short)iv; wIx[y * WIN + lane] = (short)ix; wIy[y * WIN + lane] = (short)iy; }
+            const float pxx = (float)(ix * ix), pxy = (float)(ix * iy), pyy = (float)(iy * iy);
+#pragma unroll
+            for (int t = 0; t < WIN / 4; ++t) {
+              a11 = a11 + __shfl_sync(KVFE_FULL_MASK, pxx, m4 + 4 * t);
+              a12 = a12 + __shfl_sync(KVFE_FULL_MASK, pxy, m4 + 4 * t);
+              a22 = a22 + __shfl_sync(KVFE_FULL_MASK, pyy, m4 + 4 * t);
+            }
           }
           dxp = dx; dyp = dy; dxpn = dxn; dypn = dyn;
         }
         L0 = L1; C0 = C1; R0 = R1; L1 = L2; C1 = C2; R1 = R2;
       }
     }
-    // ---- structure tensor: OpenCV lane c = x % 4, row-major sequential float accumulation
+    __syncwarp();
     float A11, A12, A22;
     {
-      float a11 = 0.f, a12 = 0.f, a22 = 0.f;      // chains live on lanes 0..3
-      const int src0 = lane & 3;
-#pragma unroll
-      for (int y = 0; y < WIN; ++y) {
-        const float pxx = (float)(wIx[y] * wIx[y]), pxy = (float)(wIx[y] * wIy[y]), pyy = (float)(wIy[y] * wIy[y]);
-#pragma unroll
-        for (int t = 0; t < WIN / 4; ++t) {
-          a11 = a11 + __shfl_sync(KVFE_FULL_MASK, pxx, src0 + 4 * t);
-          a12 = a12 + __shfl_sync(KVFE_FULL_MASK, pxy, src0 + 4 * t);
-          a22 = a22 + __shfl_sync(KVFE_FULL_MASK, pyy, src0 + 4 * t);
-        }
-      }
       // (L0 + L2) + (L1 + L3)
       float t11 = (__shfl_sync(KVFE_FULL_MASK, a11, 0) + __shfl_sync(KVFE_FULL_MASK, a11, 2)) +
                   (__shfl_sync(KVFE_FULL_MASK, a11, 1) + __shfl_sync(KVFE_FULL_MASK, a11, 3));
@@ -336,34 +341,37 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf
       iw01 = cv_round(a * (1.f - bb) * (1 << 14));
       iw10 = cv_round((1.f - a) * bb * (1 << 14));
       iw11 = (1 << 14) - iw00 - iw01 - iw10;
-      // J patch column of this lane: all TW row loads are issued first
       const int colx = reflect101(iqx + min(lane, TW - 1), cols);
-      int Jc[TW];
-      if (iqy >= 0 && iqy + TW <= rows) {
-        const unsigned char* jp = Jimg + (size_t)iqy * pitch + colx;
-#pragma unroll
-        for (int r = 0; r < TW; ++r) Jc[r] = jp[(size_t)r * pitch];
-      } else {
-#pragma unroll
-        for (int r = 0; r < TW; ++r) Jc[r] = Jimg[(size_t)reflect101(iqy + r, rows) * pitch + colx];
-      }
-      // mismatch vector with OpenCV's SIMD128 order: chain m (lanes 0..3) over groups of 8 pixels
+      const bool inner = iqy >= 0 && iqy + TW <= rows;
+      const unsigned char* jp = Jimg + (size_t)max(iqy, 0) * pitch + colx;
       float b1 = 0.f, b2 = 0.f;
-      int jr0 = __shfl_down_sync(KVFE_FULL_MASK, Jc[0], 1);
+      // chunks of LKC_CHUNK window rows: the chunk's J rows are loaded first, then consumed
+      int jprev = inner ? jp[0] : Jimg[(size_t)reflect101(iqy, rows) * pitch + colx];
+      int jprevR = __shfl_down_sync(KVFE_FULL_MASK, jprev, 1);
+#pragma unroll 1
+      for (int y0 = 0; y0 < WIN; y0 += LKC_CHUNK) {
+        int Jr[LKC_CHUNK];
 #pragma unroll
-      for (int y = 0; y < WIN; ++y) {
-        const int jr1 = __shfl_down_sync(KVFE_FULL_MASK, Jc[y + 1], 1);
-        const int diff = descale(Jc[y] * iw00 + jr0 * iw01 + Jc[y + 1] * iw10 + jr1 * iw11, 14 - 5) - wI[y];
-        jr0 = jr1;
-        int t1 = diff * wIx[y], t2 = diff * wIy[y];
-        t1 += __shfl_down_sync(KVFE_FULL_MASK, t1, 4);        // pixels (x, x + 4), valid where (x & 4) == 0
-        t2 += __shfl_down_sync(KVFE_FULL_MASK, t2, 4);
-        const float f1 = (float)t1, f2 = (float)t2;
-        const int m = lane & 3;
+        for (int u = 0; u < LKC_CHUNK; ++u) {
+          const int r = y0 + u + 1;
+          Jr[u] = inner ? jp[(size_t)r * pitch] : Jimg[(size_t)reflect101(iqy + r, rows) * pitch + colx];
+        }
 #pragma unroll
-        for (int q = 0; q < WIN / 8; ++q) {
-          b1 = b1 + __shfl_sync(KVFE_FULL_MASK, f1, m + 8 * q);
-          b2 = b2 + __shfl_sync(KVFE_FULL_MASK, f2, m + 8 * q);
+        for (int u = 0; u < LKC_CHUNK; ++u) {
+          const int y = y0 + u;
+          const int jn = Jr[u];
+          const int jnR = __shfl_down_sync(KVFE_FULL_MASK, jn, 1);
+          const int diff = descale(jprev * iw00 + jprevR * iw01 + jn * iw10 + jnR * iw11, 14 - 5) - wI[y * WIN + xl];
+          jprev = jn; jprevR = jnR;
+          int t1 = diff * wIx[y * WIN + xl], t2 = diff * wIy[y * WIN + xl];
+          t1 += __shfl_down_sync(KVFE_FULL_MASK, t1, 4);      // pixels (x, x + 4), valid where (x & 4) == 0
+          t2 += __shfl_down_sync(KVFE_FULL_MASK, t2, 4);
+          const float f1 = (float)t1, f2 = (float)t2;
+#pragma unroll
+          for (int q = 0; q < WIN / 8; ++q) {
+            b1 = b1 + __shfl_sync(KVFE_FULL_MASK, f1, m4 + 8 * q);
+            b2 = b2 + __shfl_sync(KVFE_FULL_MASK, f2, m4 + 8 * q);
+          }
         }
       }
       {
@@ -392,10 +400,9 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel_reg(DevCfg dc, DevBuf
 }
 
 int launch_lk(const DevCfg& dc, const DevBuf& db, int prev_slot, int cur_slot, cudaStream_t s) {
+  dim3 gridc((dc.cap + LKC_WARPS - 1) / LKC_WARPS, dc.B);
+  if (dc.win == 24) { lk_kernel_col<24><<<gridc, LKC_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
   dim3 grid((dc.cap + LK_WARPS - 1) / LK_WARPS, dc.B);
-  if (dc.win == 24) { lk_kernel_reg<24><<<grid, LK_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
-  if (dc.win == 16) { lk_kernel_reg<16><<<grid, LK_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
-  if (dc.win == 8) { lk_kernel_reg<8><<<grid, LK_WARPS * 32, 0, s>>>(dc, db, prev_slot, cur_slot); return 1; }
   size_t sm = LK_WARPS * lk_warp_bytes(dc.win);
   static size_t attr = 0;
   if (sm > 48 * 1024 && sm > attr) {

@@ -18,6 +18,12 @@ static __device__ int block_find_matches(const DevCfg& dc, const DevBuf& db, int
   const int nr = db.fr.n[fs_ref], nc = db.fr.n[fs_cur];
   const long long* lr = db.fr.lmk + (size_t)fs_ref * dc.cap;
   const long long* lc = db.fr.lmk + (size_t)fs_cur * dc.cap;
+  __shared__ long long s_lr[1024];                 // reference landmark ids (searched once per current keypoint)
+  if (nr <= 1024) {
+    for (int j = threadIdx.x; j < nr; j += blockDim.x) s_lr[j] = lr[j];
+    __syncthreads();
+    lr = s_lr;
+  }
   for (int base = 0; base < nc; base += blockDim.x) {
     int i = base + threadIdx.x;
     int found = -1;
@@ -76,6 +82,12 @@ static __device__ double block_median_disparity(const DevCfg& dc, const DevBuf& 
   const int m = s_m;
   if (m == 0) return -1.0;
   const int center = m / 2;
+  __shared__ double s_tmp[1024];
+  if (m <= 1024) {
+    for (int i = threadIdx.x; i < m; i += blockDim.x) s_tmp[i] = tmp[i];
+    __syncthreads();
+    tmp = s_tmp;
+  }
   for (int i = threadIdx.x; i < m; i += blockDim.x) {
     double v = tmp[i];
     int less = 0, eq_before = 0;

@@ -160,8 +160,10 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
   __shared__ int s_counts[RS_THREADS / 32];
   const int ssz = problem == 0 ? 2 : 3;
   const int NS = max_it + 1;
-  int* shuffled = wi;
-  int* samples = wi + n;
+  __shared__ int s_shuffled[2048];
+  __shared__ int s_samples[3 * 256];
+  int* shuffled = (n <= 2048) ? s_shuffled : wi;
+  int* samples = (NS <= 256) ? s_samples : wi + n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const bool enough = n >= ssz;
   if (tid == 0) { s_best = -1; s_done = enough ? 0 : 1; s_iter = 0; s_nbest = -2147483647; s_k = 1.0; s_j0 = 0; }

@@ -26,35 +26,37 @@ __device__ __forceinline__ unsigned char remap_px(const unsigned char* __restric
   return (unsigned char)((v + (1 << 14)) >> 15);
 }
 
-// grid: (ceil(W/4/64), H, nimg); 64 threads x 4 px = 256 px per block row segment
+// grid: (ceil(W/4/64), ceil(H/RECT_ROWS), nimg); 64 threads x 4 px per row, RECT_ROWS rows per block
+#define RECT_ROWS 8
 __global__ void __launch_bounds__(64) rectify_kernel(DevCfg dc, const CamModel* __restrict__ cams, int cam,
                                                      const unsigned char* __restrict__ src, size_t src_stride,
                                                      unsigned char* __restrict__ dst, size_t dst_stride,
                                                      const StreamState* __restrict__ st, int mode_mask) {
   const int img = blockIdx.z;
   if (st && !mode_on(st[img].mode, mode_mask)) return;
-  const int v = blockIdx.y;
   const int u0 = (blockIdx.x * 64 + threadIdx.x) * 4;
   if (u0 >= dc.W) return;
-  __shared__ CamModel c;
   // every thread reads the model from global (L1-broadcast); cheap and avoids a barrier
   const CamModel& cm = cams[cam];
   const unsigned char* s = src + (size_t)img * src_stride;
-  unsigned char out[4];
+  for (int rr = 0; rr < RECT_ROWS; ++rr) {
+    const int v = blockIdx.y * RECT_ROWS + rr;
+    if (v >= dc.H) break;
+    unsigned char out[4];
 #pragma unroll
-  for (int k = 0; k < 4; ++k) {
-    int u = u0 + k;
-    float mx, my;
-    rect_map_at(cm, u < dc.W ? u : dc.W - 1, v, &mx, &my);
-    out[k] = remap_px(s, dc.pitch, dc.W, dc.H, mx, my);
+    for (int k = 0; k < 4; ++k) {
+      int u = u0 + k;
+      float mx, my;
+      rect_map_at(cm, u < dc.W ? u : dc.W - 1, v, &mx, &my);
+      out[k] = remap_px(s, dc.pitch, dc.W, dc.H, mx, my);
+    }
+    unsigned char* d = dst + (size_t)img * dst_stride + (size_t)v * dc.pitch + u0;
+    if (u0 + 3 < dc.W) {
+      *reinterpret_cast<uchar4*>(d) = make_uchar4(out[0], out[1], out[2], out[3]);
+    } else {
+      for (int k = 0; k < 4 && u0 + k < dc.W; ++k) d[k] = out[k];
+    }
   }
-  unsigned char* d = dst + (size_t)img * dst_stride + (size_t)v * dc.pitch + u0;
-  if (u0 + 3 < dc.W) {
-    *reinterpret_cast<uchar4*>(d) = make_uchar4(out[0], out[1], out[2], out[3]);
-  } else {
-    for (int k = 0; k < 4 && u0 + k < dc.W; ++k) d[k] = out[k];
-  }
-  (void)c;
 }
 
 __global__ void maps_kernel(DevCfg dc, const CamModel* __restrict__ cams, int cam, float* __restrict__ mx,
@@ -70,7 +72,7 @@ __global__ void maps_kernel(DevCfg dc, const CamModel* __restrict__ cams, int ca
 int launch_rectify(const DevCfg& dc, const CamModel* d_cam, int cam, const unsigned char* src,
                    size_t src_stride, unsigned char* dst, size_t dst_stride, int nimg,
                    const StreamState* st, int mode_mask, cudaStream_t s) {
-  dim3 grid((dc.W / 4 + 63) / 64, dc.H, nimg);
+  dim3 grid((dc.W / 4 + 63) / 64, (dc.H + RECT_ROWS - 1) / RECT_ROWS, nimg);
   rectify_kernel<<<grid, 64, 0, s>>>(dc, d_cam, cam, src, src_stride, dst, dst_stride, st, mode_mask);
   return 1;
 }

@@ -41,7 +41,7 @@ __global__ void __launch_bounds__(128) left_rect_kernel(DevCfg dc, DevBuf db, co
 #define MATCH_THREADS 128
 
 // grid (cap, B); dynamic smem: templ (tc*tr) + stripe (sc*sr) bytes + scores (sc - tc + 1) ints
-__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf db, int mode_mask) {
+__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf db, int mode_mask, int reuse_tracked) {
   extern __shared__ unsigned char smraw[];
   const int b = blockIdx.y;
   const StreamState& s = db.st[b];
@@ -51,17 +51,27 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf 
   if (i >= db.fr.n[fs]) return;
   const size_t k = (size_t)fs * dc.cap + i;
   const int lst = db.fr.lstat[k];
+  // Second reconstruction of a keyframe (StereoVisionImuFrontend.cpp:426): the tracked keypoints
+  // were already matched in the first one (:364) on the same rectified images with the same left
+  // keypoints, so their match is restored instead of recomputed (identical by construction).
+  if (reuse_tracked && s.mode == 2 && dc.use_ransac && i < s.nr_tracked) {
+    if (threadIdx.x == 0) db.fr.rstat[k] = db.fr.mstat[k];
+    return;
+  }
   const int tc = dc.templ_cols, tr = dc.templ_rows, sc = dc.stripe_cols, sr = dc.stripe_rows;
   const int W = dc.W, H = dc.H;
   if (lst != KVFE_KP_VALID) {
-    if (threadIdx.x == 0) { db.fr.rstat[k] = lst; db.fr.rrx[k] = 0.f; db.fr.rry[k] = 0.f; }
+    if (threadIdx.x == 0) { db.fr.rstat[k] = lst; db.fr.mstat[k] = lst; db.fr.rrx[k] = 0.f; db.fr.rry[k] = 0.f; }
     return;
   }
   const int rx = (int)roundf(db.fr.lrx[k]), ry = (int)roundf(db.fr.lry[k]);
   const int tcy = ry - (tr - 1) / 2;
   const int scy = ry - (sr - 1) / 2;
   if (tcy < 0 || tcy + tr > H - 1 || scy < 0 || scy + sr > H - 1) {
-    if (threadIdx.x == 0) { db.fr.rstat[k] = KVFE_KP_NO_RIGHT_RECT; db.fr.rrx[k] = 0.f; db.fr.rry[k] = 0.f; }
+    if (threadIdx.x == 0) {
+      db.fr.rstat[k] = KVFE_KP_NO_RIGHT_RECT; db.fr.mstat[k] = KVFE_KP_NO_RIGHT_RECT;
+      db.fr.rrx[k] = 0.f; db.fr.rry[k] = 0.f;
+    }
     return;
   }
   int offset_temp = 0;
@@ -152,7 +162,8 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf 
     }
     if (threadIdx.x == 0) {
       // after NORM_MINMAX the minimum is ~0, so "min_val < tolerance" holds iff tolerance > 0
-      db.fr.rstat[k] = (dc.tol_templ > 0.f) ? KVFE_KP_VALID : KVFE_KP_NO_RIGHT_RECT;
+      const int ms = (dc.tol_templ > 0.f) ? KVFE_KP_VALID : KVFE_KP_NO_RIGHT_RECT;
+      db.fr.rstat[k] = ms; db.fr.mstat[k] = ms;
       db.fr.rrx[k] = mx; db.fr.rry[k] = my;
     }
   }
@@ -214,7 +225,7 @@ __global__ void bearing_kernel(const CamModel* __restrict__ cams, const float* x
 }
 
 int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, int mode_mask,
-                         cudaStream_t s) {
+                         int reuse_tracked, cudaStream_t s) {
   int n = 0;
   left_rect_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); ++n;
   const int tstride = (dc.templ_cols + 3) & ~3, sstride = ((dc.stripe_cols + 3) & ~3) + 8;
@@ -226,7 +237,7 @@ int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_c
     cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attr = sm;
   }
-  match_kernel<<<dim3(dc.cap, dc.B), MATCH_THREADS, sm, s>>>(dc, db, mode_mask); ++n;
+  match_kernel<<<dim3(dc.cap, dc.B), MATCH_THREADS, sm, s>>>(dc, db, mode_mask, reuse_tracked); ++n;
   depth_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); ++n;
   return n;
 }
