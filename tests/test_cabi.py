@@ -1,0 +1,87 @@
+"""CPU checks of the drop-in boundary: the C-ABI library builds, loads and exports every symbol
+include/kvfe.h declares; struct layouts agree between the header and the ctypes mirror; without a
+CUDA device context creation fails loudly (no CPU fallback)."""
+import ctypes as C
+import os
+import re
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HDR = os.path.join(ROOT, "include", "kvfe.h")
+
+
+@pytest.fixture(scope="module")
+def so_path():
+    from kimera_vio_b200 import build
+    return build.build()
+
+
+def declared_symbols():
+    txt = open(HDR).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(kvfe_[a-z0-9_]+)\s*\(", txt)))
+
+
+def test_header_declares_entry_points():
+    syms = declared_symbols()
+    for s in ("kvfe_create", "kvfe_destroy", "kvfe_rectify_pair", "kvfe_detect", "kvfe_track",
+              "kvfe_sparse_stereo", "kvfe_ransac_mono", "kvfe_ransac_stereo_1pt", "kvfe_ransac_stereo_3pt",
+              "kvfe_frontend_step", "kvfe_frontend_step_dev", "kvfe_last_error"):
+        assert s in syms
+
+
+def test_library_exports_every_declared_symbol(so_path):
+    out = subprocess.check_output(["nm", "-D", "--defined-only", so_path], text=True)
+    exported = set(l.split()[-1] for l in out.splitlines() if " T " in l)
+    missing = [s for s in declared_symbols() if s not in exported]
+    assert not missing, missing
+
+
+def test_header_compiles_as_c(tmp_path):
+    src = tmp_path / "t.c"
+    src.write_text('#include "kvfe.h"\nint main(void){ kvfe_config c; (void)c; return (int)sizeof(kvfe_packet_header) == 0; }\n')
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-c", str(src),
+                           "-o", str(tmp_path / "t.o")])
+
+
+def test_struct_layouts_match_ctypes(tmp_path, so_path):
+    from kimera_vio_b200 import lib as kl
+    src = tmp_path / "sz.c"
+    src.write_text('#include <stdio.h>\n#include <stddef.h>\n#include "kvfe.h"\nint main(void){printf("%zu %zu %zu %zu %zu %zu\\n",'
+                   'sizeof(kvfe_config), sizeof(kvfe_rig), sizeof(kvfe_packet_header), sizeof(kvfe_stereo_out),'
+                   'offsetof(kvfe_config, max_disparity_since_lkf), offsetof(kvfe_packet_header, median_disparity));return 0;}\n')
+    exe = tmp_path / "sz"
+    subprocess.check_call(["gcc", "-I", os.path.join(ROOT, "include"), str(src), "-o", str(exe)])
+    a = [int(v) for v in subprocess.check_output([str(exe)], text=True).split()]
+    assert a[0] == C.sizeof(kl.Config)
+    assert a[1] == C.sizeof(kl.Rig)
+    assert a[2] == C.sizeof(kl.PacketHeader)
+    assert a[3] == C.sizeof(kl.StereoOut)
+    assert a[4] == kl.Config.max_disparity_since_lkf.offset
+    assert a[5] == kl.PacketHeader.median_disparity.offset
+
+
+def test_no_cpu_fallback(so_path):
+    """Without a GPU the product must refuse to run (never route through a CPU path)."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is visible here")
+    from kimera_vio_b200 import lib as kl
+    from kimera_vio_b200.params import CameraParams, FrontendParams
+    from kimera_vio_b200.rig import StereoRigSetup
+    rig = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
+    cfg = kl.make_config(FrontendParams.euroc(), 752, 480)
+    with pytest.raises(kl.KvfeError) as e:
+        kl.Context(cfg, rig.to_c())
+    assert "no CUDA device" in str(e.value) or "CUDA" in str(e.value)
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "kimera_vio_b200")
+    for dp, _, fs in os.walk(pkg):
+        for f in fs:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                txt = open(os.path.join(dp, f)).read()
+                assert "import oracle" not in txt and "from oracle" not in txt, f
