@@ -255,6 +255,20 @@ int kvfe_frontend_step(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t*
  * context's stream; kvfe_sync() waits. */
 int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev,
                            size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur);
+/* Same as kvfe_frontend_step_dev but synchronous, without the CUDA graph, with CUDA events around
+ * the stages; stage_ms receives KVFE_N_STAGES durations in milliseconds (measurement aid for
+ * bench.py's roofline line): 0 prep+pyramid, 1 LK tracking (track_pre, lk, track_post), 2 decide +
+ * mono RANSAC, 3 rectification, 4 sparse stereo #1 + stereo RANSAC, 5 GFTT (mask, response,
+ * selection), 6 NMS + sub-pixel + append, 7 sparse stereo #2 + finalize, 8 the LK kernel alone. */
+#define KVFE_N_STAGES 9
+int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev,
+                                 size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
+                                 float* stage_ms);
+/* Enqueues one kvfe_frontend_step_dev on each of n contexts (sub-batches that run concurrently on
+ * their own CUDA streams) with a single host call; arrays are indexed by context. */
+int kvfe_frontend_step_dev_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* left_dev,
+                                 const uint8_t* const* right_dev, size_t pitch,
+                                 const int64_t* const* timestamps, const double* const* keyframe_R_cur);
 int kvfe_frontend_read_packets(kvfe_ctx* ctx, uint8_t* packets);
 int kvfe_frontend_read_rectified(kvfe_ctx* ctx, int stream, uint8_t* rect_left,
                                  uint8_t* rect_right, size_t rect_pitch);

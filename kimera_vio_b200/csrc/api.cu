@@ -5,6 +5,7 @@
 #include <cmath>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <numeric>
 #include <random>
@@ -312,6 +313,10 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   ctx->launches += launch_reset(dc, db, ctx->stream);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->cur_slot = 0;
+  {
+    const char* e = getenv("KVFE_NO_GRAPH");
+    ctx->use_graph = !(e && e[0] == '1');
+  }
   *out = ctx;
   return KVFE_OK;
 }
@@ -334,6 +339,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
   if (ctx->h_Rin) cudaFreeHost(ctx->h_Rin);
   for (int i = 0; i < KVFE_IN_SLOTS; ++i) if (ctx->in_ev[i]) cudaEventDestroy(ctx->in_ev[i]);
+  for (int i = 0; i < 2; ++i) if (ctx->graph_ready[i]) cudaGraphExecDestroy(ctx->step_graph[i]);
   cudaStreamDestroy(ctx->stream);
   delete ctx;
 }
@@ -749,7 +755,38 @@ extern "C" int kvfe_frontend_reset(kvfe_ctx* ctx) {
 
 // the fixed kernel sequence of one step; images of the current frame already sit in
 // pyr[cur_slot] level 0 (left) and right_raw (right).
+static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch);
+
+// The kernel sequence of a step is identical from step to step (all arguments are by-value structs
+// of device pointers; only the pyramid slot alternates), so it is captured once per slot into a
+// CUDA graph and replayed: one cudaGraphLaunch instead of ~28 kernel launches per step.
 static int enqueue_step(kvfe_ctx* ctx) {
+  const int cur = ctx->cur_slot;
+  long long n = 0;
+  if (ctx->use_graph) {
+    if (!ctx->graph_ready[cur]) {
+      cudaGraph_t g = nullptr;
+      CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
+      int rc = enqueue_step_kernels(ctx, &n);
+      cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
+      if (rc != KVFE_OK) return rc;
+      if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+      CU(cudaGraphInstantiate(&ctx->step_graph[cur], g, 0));
+      cudaGraphDestroy(g);
+      ctx->graph_ready[cur] = 1;
+      ctx->graph_launches = n;
+    }
+    CU(cudaGraphLaunch(ctx->step_graph[cur], ctx->stream));
+    ctx->launches += ctx->graph_launches;
+  } else {
+    RET(enqueue_step_kernels(ctx, &n));
+    ctx->launches += n;
+  }
+  ctx->cur_slot ^= 1;
+  return KVFE_OK;
+}
+
+static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch) {
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const int cur = ctx->cur_slot, prev = cur ^ 1;
   const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
@@ -775,9 +812,8 @@ static int enqueue_step(kvfe_ctx* ctx) {
   // idempotent -- same raw images, same maps -- and is therefore not repeated)
   n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, 1, s);
   n += launch_finalize(dc, db, s);
-  ctx->launches += n;
+  *n_launch = n;
   CU(cudaGetLastError());
-  ctx->cur_slot ^= 1;
   return KVFE_OK;
 }
 
@@ -806,13 +842,96 @@ extern "C" int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, co
   const size_t B = dc.B;
   RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
   // device-to-device placement into the pyramid slot / right buffer (strided destination)
-  for (size_t b = 0; b < B; ++b) {
-    RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
-                   left_dev + b * pitch * dc.H, pitch, cudaMemcpyDeviceToDevice));
-    RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right_dev + b * pitch * dc.H, pitch,
-                   cudaMemcpyDeviceToDevice));
+  if (pitch == (size_t)dc.W && dc.pitch == dc.W) {
+    // densely packed images: one strided copy per camera for the whole batch (row = one image)
+    const size_t img = (size_t)dc.W * dc.H;
+    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, left_dev, img, img, B,
+                         cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpy2DAsync(db.right_raw, dc.img_stride, right_dev, img, img, B, cudaMemcpyDeviceToDevice, s));
+  } else {
+    for (size_t b = 0; b < B; ++b) {
+      RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
+                     left_dev + b * pitch * dc.H, pitch, cudaMemcpyDeviceToDevice));
+      RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right_dev + b * pitch * dc.H, pitch,
+                     cudaMemcpyDeviceToDevice));
+    }
   }
   return enqueue_step(ctx);
+}
+
+extern "C" int kvfe_frontend_step_dev_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* left_dev,
+                                            const uint8_t* const* right_dev, size_t pitch,
+                                            const int64_t* const* timestamps, const double* const* keyframe_R_cur) {
+  if (!ctxs || n <= 0 || !left_dev || !right_dev || !timestamps || !keyframe_R_cur) return KVFE_ERR_INVALID_ARG;
+  for (int i = 0; i < n; ++i) {
+    int rc = kvfe_frontend_step_dev(ctxs[i], left_dev[i], right_dev[i], pitch, timestamps[i], keyframe_R_cur[i]);
+    if (rc != KVFE_OK) return rc;
+  }
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev,
+                                            size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
+                                            float* stage_ms) {
+  if (!ctx || !left_dev || !right_dev || !timestamps || !keyframe_R_cur || !stage_ms) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
+  const size_t B = dc.B;
+  RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
+  if (pitch == (size_t)dc.W && dc.pitch == dc.W) {
+    // densely packed images: one strided copy per camera for the whole batch (row = one image)
+    const size_t img = (size_t)dc.W * dc.H;
+    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, left_dev, img, img, B,
+                         cudaMemcpyDeviceToDevice, s));
+    CU(cudaMemcpy2DAsync(db.right_raw, dc.img_stride, right_dev, img, img, B, cudaMemcpyDeviceToDevice, s));
+  } else {
+    for (size_t b = 0; b < B; ++b) {
+      RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
+                     left_dev + b * pitch * dc.H, pitch, cudaMemcpyDeviceToDevice));
+      RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right_dev + b * pitch * dc.H, pitch,
+                     cudaMemcpyDeviceToDevice));
+    }
+  }
+  const int cur = ctx->cur_slot, prev = cur ^ 1;
+  const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
+  unsigned char* Lcur = db.pyr[cur] + dc.lvl_off[0];
+  cudaEvent_t ev[KVFE_N_STAGES + 3];
+  for (auto& e : ev) CU(cudaEventCreate(&e));
+  long long n = 0;
+  CU(cudaEventRecord(ev[0], s));
+  n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, s);
+  n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
+  CU(cudaEventRecord(ev[1], s));
+  n += launch_track_pre(dc, db, s);
+  CU(cudaEventRecord(ev[9], s));
+  n += launch_lk(dc, db, prev, cur, s);
+  CU(cudaEventRecord(ev[10], s));
+  n += launch_track_post(dc, db, ctx->d_cam, s);
+  CU(cudaEventRecord(ev[2], s));
+  n += launch_decide(dc, db, s);
+  n += launch_ransac_mono(dc, db, M_KF, s);
+  CU(cudaEventRecord(ev[3], s));
+  n += launch_rectify(dc, ctx->d_cam, 0, Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  CU(cudaEventRecord(ev[4], s));
+  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_KF, 0, s);
+  n += launch_ransac_stereo(dc, db, M_KF, s);
+  CU(cudaEventRecord(ev[5], s));
+  n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, s);
+  n += launch_gftt(dc, db, Lcur, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, M_BOOT | M_KF | M_LOST, s);
+  CU(cudaEventRecord(ev[6], s));
+  n += launch_select(dc, db, Lcur, dc.pyr_stride, ctx->d_cam, M_BOOT | M_KF | M_LOST, 1, s);
+  CU(cudaEventRecord(ev[7], s));
+  n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, 1, s);
+  n += launch_finalize(dc, db, s);
+  CU(cudaEventRecord(ev[8], s));
+  CU(cudaGetLastError());
+  CU(cudaStreamSynchronize(s));
+  for (int i = 0; i < 8; ++i) CU(cudaEventElapsedTime(&stage_ms[i], ev[i], ev[i + 1]));
+  CU(cudaEventElapsedTime(&stage_ms[8], ev[9], ev[10]));
+  for (auto& e : ev) cudaEventDestroy(e);
+  ctx->launches += n;
+  ctx->cur_slot ^= 1;
+  return KVFE_OK;
 }
 
 extern "C" int kvfe_frontend_step(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right, size_t pitch,

@@ -346,67 +346,74 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   const int md2 = md * md;
   volatile unsigned char* vst = state;
   volatile int* vhead = head;
+  // Asynchronous relaxation: a cell thread keeps deciding its successive heads without waiting
+  // for a block-wide barrier; an accepted head immediately rejects the undecided candidates around
+  // it.  States only move 0 -> 1/2, readers of a stale 0 merely wait, and two conflicting heads can
+  // never both be accepted (the worse one always sees the better one as undecided or accepted).
   for (int round = 0; round < 100000; ++round) {
     int active = 0;
-    // phase A: one thread per cell
     for (int c = tid; c < ncells; c += blockDim.x) {
-      int h = vhead[c];
       const int e = cstart[c + 1];
-      while (h < e && vst[h] != 0) ++h;              // skip decided entries
-      vhead[c] = h;
-      newacc[c] = -1;
-      if (h >= e) continue;
-      active = 1;
-      const unsigned long long kh = sk[h];
-      const int idx = (int)(kh & 0xffffffffu);
-      const int y = idx / W, x = idx - y * W;
       const int cxl = c % gw, cyl = c / gw;
       const int x1 = max(cxl - 1, 0), x2 = min(cxl + 1, gw - 1), y1 = max(cyl - 1, 0), y2 = min(cyl + 1, gh - 1);
-      int verdict = 1;                                // 1 accept, 0 wait, 2 reject
-      for (int yy = y1; yy <= y2 && verdict == 1; ++yy)
-        for (int xx = x1; xx <= x2 && verdict == 1; ++xx) {
-          const int d = yy * gw + xx;
-          if (d == c) continue;
-          const int de = cstart[d + 1];
-          for (int q = cstart[d]; q < de; ++q) {      // better candidates form a prefix of the cell
-            const unsigned long long kq = sk[q];
-            if (kq < kh) break;
-            const int sq = vst[q];
-            if (sq == 2) continue;
-            const int jdx = (int)(kq & 0xffffffffu);
-            const int jy = jdx / W, jx = jdx - jy * W;
-            const int ddx = x - jx, ddy = y - jy;
-            if (ddx * ddx + ddy * ddy < md2) { verdict = (sq == 1) ? 2 : 0; break; }
+      int h = vhead[c];
+      for (int attempt = 0; attempt < 64; ++attempt) {
+        while (h < e && vst[h] != 0) ++h;              // skip decided entries
+        if (h >= e) break;
+        const unsigned long long kh = sk[h];
+        const int idx = (int)(kh & 0xffffffffu);
+        const int y = idx / W, x = idx - y * W;
+        int verdict = 1;                                // 1 accept, 0 wait, 2 reject
+        for (int yy = y1; yy <= y2 && verdict == 1; ++yy)
+          for (int xx = x1; xx <= x2 && verdict == 1; ++xx) {
+            const int d = yy * gw + xx;
+            if (d == c) continue;
+            const int de = cstart[d + 1];
+            for (int q = cstart[d]; q < de; ++q) {      // better candidates form a prefix of the cell
+              const unsigned long long kq = sk[q];
+              if (kq < kh) break;
+              const int sq = vst[q];
+              if (sq == 2) continue;
+              const int jdx = (int)(kq & 0xffffffffu);
+              const int jy = jdx / W, jx = jdx - jy * W;
+              const int ddx = x - jx, ddy = y - jy;
+              if (ddx * ddx + ddy * ddy < md2) { verdict = (sq == 1) ? 2 : 0; break; }
+            }
+          }
+        if (verdict == 0) { active = 1; break; }        // blocked by an undecided better neighbour
+        vst[h] = (unsigned char)verdict;
+        if (verdict == 1) {
+          __threadfence_block();
+          for (int yy = y1; yy <= y2; ++yy) {           // reject the undecided candidates within minDistance
+            const int qa = cstart[yy * gw + x1], qb = cstart[yy * gw + x2 + 1];
+            for (int q = qa; q < qb; ++q) {
+              if (vst[q] != 0) continue;
+              const int jdx = (int)(sk[q] & 0xffffffffu);
+              const int jy = jdx / W, jx = jdx - jy * W;
+              const int ddx = x - jx, ddy = y - jy;
+              if (ddx * ddx + ddy * ddy < md2) vst[q] = 2;
+            }
           }
         }
-      if (verdict == 1) { vst[h] = 1; newacc[c] = h; }
-      else if (verdict == 2) vst[h] = 2;
+      }
+      while (h < e && vst[h] != 0) ++h;
+      vhead[c] = h;
+      if (h < e) active = 1;
     }
     if (!__syncthreads_or(active)) break;
-    // phase B: every newly accepted corner rejects the undecided candidates within minDistance
-    for (int c = tid; c < ncells; c += blockDim.x) {
-      const int h = newacc[c];
-      if (h < 0) continue;
-      const int idx = (int)(sk[h] & 0xffffffffu);
-      const int y = idx / W, x = idx - y * W;
-      const int cxl = c % gw, cyl = c / gw;
-      const int x1 = max(cxl - 1, 0), x2 = min(cxl + 1, gw - 1), y1 = max(cyl - 1, 0), y2 = min(cyl + 1, gh - 1);
-      for (int yy = y1; yy <= y2; ++yy) {
-        const int qa = vhead[yy * gw + x1], qb = cstart[yy * gw + x2 + 1];
-        for (int q = qa; q < qb; ++q) {
-          if (vst[q] != 0) continue;
-          const int jdx = (int)(sk[q] & 0xffffffffu);
-          const int jy = jdx / W, jx = jdx - jy * W;
-          const int ddx = x - jx, ddy = y - jy;
-          if (ddx * ddx + ddy * ddy < md2) vst[q] = 2;
-        }
-      }
-    }
-    __syncthreads();
   }
   __syncthreads();
   // ---- 4. gather accepted keys, sort them descending, emit the first maxCorners
-  unsigned long long* acc = skeys + smem_keys;
+  // (shared memory when they fit, else the -- now free -- global bucket buffer)
+  int my_acc = 0;
+  for (int i = tid; i < n; i += blockDim.x) my_acc += (state[i] == 1);
+  if (tid == 0) s_total = 0;
+  __syncthreads();
+  if (my_acc) atomicAdd(&s_total, my_acc);
+  __syncthreads();
+  const int acc_cap = (s_total <= GREEDY_ACC_MAX) ? GREEDY_ACC_MAX : dc.cand_cap;
+  unsigned long long* acc = (s_total <= GREEDY_ACC_MAX) ? (skeys + smem_keys) : tmp;
+  __syncthreads();
   if (tid == 0) s_total = 0;
   __syncthreads();
   for (int base = 0; base < n; base += blockDim.x) {
@@ -428,12 +435,12 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
     }
     __syncthreads();
     int pos = s_total + wsum[warp] + __popc(bal & ((1u << lane) - 1));
-    if (a && pos < GREEDY_ACC_MAX) acc[pos] = sk[i];
+    if (a && pos < acc_cap) acc[pos] = sk[i];
     __syncthreads();
     if (tid == 0) s_total += s_chunk;
     __syncthreads();
   }
-  const int na = min(s_total, GREEDY_ACC_MAX);
+  const int na = min(s_total, acc_cap);
   int P = 2;
   while (P < na) P <<= 1;
   for (int i = na + tid; i < P; i += blockDim.x) acc[i] = 0ull;

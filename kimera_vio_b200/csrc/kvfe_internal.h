@@ -155,6 +155,10 @@ struct kvfe_ctx {
   long long* d_ts; double* d_Rin;        // step inputs
   long long* h_ts; double* h_Rin;        // KVFE_IN_SLOTS pinned slots each
   cudaEvent_t in_ev[KVFE_IN_SLOTS]; int in_used[KVFE_IN_SLOTS]; int in_slot;
+  cudaGraphExec_t step_graph[2];   // captured kernel sequence of one step, per pyramid slot
+  int graph_ready[2];
+  int use_graph;
+  long long graph_launches;
   int* circle_hw;              // device: half widths of the filled-circle raster rows (2r+1)
   int circle_r;
 };

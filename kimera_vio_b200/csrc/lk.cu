@@ -221,7 +221,7 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
 // kept in shared memory (conflict-free column access) so that the row loops stay rolled: small code
 // (no instruction-cache thrash), few registers, high occupancy.  Arithmetic identical to lk_kernel.
 // ------------------------------------------------------------------------------------------------
-#define LKC_WARPS 8
+#define LKC_WARPS 4
 #define LKC_CHUNK 6      // window rows per software-pipelined chunk of J loads
 
 template <int WIN>
@@ -229,6 +229,7 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
   constexpr int PW = WIN + 3, TW = WIN + 1;
   static_assert(WIN % LKC_CHUNK == 0 || WIN % 8 == 0, "window must be a multiple of 8");
   __shared__ short sI[LKC_WARPS][WIN * WIN], sIx[LKC_WARPS][WIN * WIN], sIy[LKC_WARPS][WIN * WIN];
+  __shared__ float sP[LKC_WARPS][3][WIN * WIN];     // structure-tensor products (xx, xy, yy)
   const int b = blockIdx.y;
   const StreamState& st = db.st[b];
   if (st.mode == 0) return;
@@ -236,6 +237,7 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
   const int pt = blockIdx.x * LKC_WARPS + warp;
   if (pt >= st.n_ref) return;
   short* wI = sI[warp]; short* wIx = sIx[warp]; short* wIy = sIy[warp];
+  float (*wP)[WIN * WIN] = sP[warp];
   const int xl = min(lane, WIN - 1);               // window column of this lane (lanes >= WIN idle copies)
   const size_t gi = (size_t)b * dc.cap + pt;
   const unsigned char* prevPyr = db.pyr[prev_slot] + (size_t)b * dc.pyr_stride;
@@ -269,7 +271,6 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
     int iw11 = (1 << 14) - iw00 - iw01 - iw10;
     __syncwarp();
     // ---- window of I, Ix, Iy streamed over the (WIN+3) patch rows; structure tensor chains on the fly
-    float a11 = 0.f, a12 = 0.f, a22 = 0.f;         // OpenCV lane c = x % 4 chains live on lanes 0..3
     {
       const int colx = reflect101(ipx - 1 + min(lane, PW - 1), cols);
       const bool xin = (ipx + lane) >= 0 && (ipx + lane) < cols;
@@ -295,13 +296,10 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
             const int iv = descale(C0 * iw00 + R0 * iw01 + C1 * iw10 + R1 * iw11, 14 - 5);
             const int ix = descale(dxp * iw00 + dxpn * iw01 + dx * iw10 + dxn * iw11, 14);
             const int iy = descale(dyp * iw00 + dypn * iw01 + dy * iw10 + dyn * iw11, 14);
-            if (lane < WIN) { wI[y * WIN + lane] = (short)iv; wIx[y * WIN + lane] = (short)ix; wIy[y * WIN + lane] = (short)iy; }
-            const float pxx = (float)(ix * ix), pxy = (float)(ix * iy), pyy = (float)(iy * iy);
-#pragma unroll
-            for (int t = 0; t < WIN / 4; ++t) {
-              a11 = a11 + __shfl_sync(KVFE_FULL_MASK, pxx, m4 + 4 * t);
-              a12 = a12 + __shfl_sync(KVFE_FULL_MASK, pxy, m4 + 4 * t);
-              a22 = a22 + __shfl_sync(KVFE_FULL_MASK, pyy, m4 + 4 * t);
+            if (lane < WIN) {
+              const int o = y * WIN + lane;
+              wI[o] = (short)iv; wIx[o] = (short)ix; wIy[o] = (short)iy;
+              wP[0][o] = (float)(ix * ix); wP[1][o] = (float)(ix * iy); wP[2][o] = (float)(iy * iy);
             }
           }
           dxp = dx; dyp = dy; dxpn = dxn; dypn = dyn;
@@ -312,14 +310,19 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
     __syncwarp();
     float A11, A12, A22;
     {
+      // OpenCV lane c = i % 4, sequential float accumulation; 12 chains (3 sums x 4 lanes) on lanes 0..11
+      float acc = 0.f;
+      if (lane < 12) {
+        const float* P = wP[lane >> 2];
+#pragma unroll 8
+        for (int i = m4; i < WIN * WIN; i += 4) acc = acc + P[i];
+      }
       // (L0 + L2) + (L1 + L3)
-      float t11 = (__shfl_sync(KVFE_FULL_MASK, a11, 0) + __shfl_sync(KVFE_FULL_MASK, a11, 2)) +
-                  (__shfl_sync(KVFE_FULL_MASK, a11, 1) + __shfl_sync(KVFE_FULL_MASK, a11, 3));
-      float t12 = (__shfl_sync(KVFE_FULL_MASK, a12, 0) + __shfl_sync(KVFE_FULL_MASK, a12, 2)) +
-                  (__shfl_sync(KVFE_FULL_MASK, a12, 1) + __shfl_sync(KVFE_FULL_MASK, a12, 3));
-      float t22 = (__shfl_sync(KVFE_FULL_MASK, a22, 0) + __shfl_sync(KVFE_FULL_MASK, a22, 2)) +
-                  (__shfl_sync(KVFE_FULL_MASK, a22, 1) + __shfl_sync(KVFE_FULL_MASK, a22, 3));
-      A11 = t11 * FLT_SCALE; A12 = t12 * FLT_SCALE; A22 = t22 * FLT_SCALE;
+      const float tot = (acc + __shfl_down_sync(KVFE_FULL_MASK, acc, 2)) +
+                        (__shfl_down_sync(KVFE_FULL_MASK, acc, 1) + __shfl_down_sync(KVFE_FULL_MASK, acc, 3));
+      A11 = __shfl_sync(KVFE_FULL_MASK, tot, 0) * FLT_SCALE;
+      A12 = __shfl_sync(KVFE_FULL_MASK, tot, 4) * FLT_SCALE;
+      A22 = __shfl_sync(KVFE_FULL_MASK, tot, 8) * FLT_SCALE;
     }
     float D = A11 * A22 - A12 * A12;
     float minEig = (A22 + A11 - sqrtf((A11 - A22) * (A11 - A22) + 4.f * A12 * A12)) / (float)(2 * WIN * WIN);
@@ -344,7 +347,8 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
       const int colx = reflect101(iqx + min(lane, TW - 1), cols);
       const bool inner = iqy >= 0 && iqy + TW <= rows;
       const unsigned char* jp = Jimg + (size_t)max(iqy, 0) * pitch + colx;
-      float b1 = 0.f, b2 = 0.f;
+      float bacc = 0.f;                            // lanes 0..3: b1 chains, lanes 4..7: b2 chains
+      const int m8 = lane & 7;
       // chunks of LKC_CHUNK window rows: the chunk's J rows are loaded first, then consumed
       int jprev = inner ? jp[0] : Jimg[(size_t)reflect101(iqy, rows) * pitch + colx];
       int jprevR = __shfl_down_sync(KVFE_FULL_MASK, jprev, 1);
@@ -363,23 +367,23 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
           const int jnR = __shfl_down_sync(KVFE_FULL_MASK, jn, 1);
           const int diff = descale(jprev * iw00 + jprevR * iw01 + jn * iw10 + jnR * iw11, 14 - 5) - wI[y * WIN + xl];
           jprev = jn; jprevR = jnR;
-          int t1 = diff * wIx[y * WIN + xl], t2 = diff * wIy[y * WIN + xl];
-          t1 += __shfl_down_sync(KVFE_FULL_MASK, t1, 4);      // pixels (x, x + 4), valid where (x & 4) == 0
-          t2 += __shfl_down_sync(KVFE_FULL_MASK, t2, 4);
-          const float f1 = (float)t1, f2 = (float)t2;
+          const int t1 = diff * wIx[y * WIN + xl], t2 = diff * wIy[y * WIN + xl];
+          // pixel pairs (x, x + 4): the Ix pair sum lands on lanes with (x & 4) == 0, the Iy pair sum
+          // on lanes with (x & 4) != 0, so that ONE gather shuffle per group feeds both chain sets
+          const int s1 = t1 + __shfl_down_sync(KVFE_FULL_MASK, t1, 4);
+          const int s2 = t2 + __shfl_up_sync(KVFE_FULL_MASK, t2, 4);
+          const float g = (float)((lane & 4) ? s2 : s1);
 #pragma unroll
-          for (int q = 0; q < WIN / 8; ++q) {
-            b1 = b1 + __shfl_sync(KVFE_FULL_MASK, f1, m4 + 8 * q);
-            b2 = b2 + __shfl_sync(KVFE_FULL_MASK, f2, m4 + 8 * q);
-          }
+          for (int q = 0; q < WIN / 8; ++q) bacc = bacc + __shfl_sync(KVFE_FULL_MASK, g, m8 + 8 * q);
         }
       }
+      float b1, b2;
       {
-        float t1 = (__shfl_sync(KVFE_FULL_MASK, b1, 0) + __shfl_sync(KVFE_FULL_MASK, b1, 2)) +
-                   (__shfl_sync(KVFE_FULL_MASK, b1, 1) + __shfl_sync(KVFE_FULL_MASK, b1, 3));
-        float t2 = (__shfl_sync(KVFE_FULL_MASK, b2, 0) + __shfl_sync(KVFE_FULL_MASK, b2, 2)) +
-                   (__shfl_sync(KVFE_FULL_MASK, b2, 1) + __shfl_sync(KVFE_FULL_MASK, b2, 3));
-        b1 = t1 * FLT_SCALE; b2 = t2 * FLT_SCALE;
+        // per sum: (c0 + c2) + (c1 + c3)
+        const float tot = (bacc + __shfl_down_sync(KVFE_FULL_MASK, bacc, 2)) +
+                          (__shfl_down_sync(KVFE_FULL_MASK, bacc, 1) + __shfl_down_sync(KVFE_FULL_MASK, bacc, 3));
+        b1 = __shfl_sync(KVFE_FULL_MASK, tot, 0) * FLT_SCALE;
+        b2 = __shfl_sync(KVFE_FULL_MASK, tot, 4) * FLT_SCALE;
       }
       float dxv = (float)((A12 * b2 - A22 * b1) * D);
       float dyv = (float)((A12 * b1 - A11 * b2) * D);

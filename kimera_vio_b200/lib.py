@@ -394,6 +394,12 @@ class Context:
         return self.lib.kvfe_frontend_step_dev(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr),
                                                C.c_size_t(pitch), _p(ts), _p(Rm))
 
+    def step_dev_timed(self, left_dev_ptr: int, right_dev_ptr: int, pitch: int, ts: np.ndarray, Rm: np.ndarray):
+        ms = np.zeros(9, np.float32)
+        self._chk(self.lib.kvfe_frontend_step_dev_timed(self.h, C.c_void_p(left_dev_ptr), C.c_void_p(right_dev_ptr),
+                                                        C.c_size_t(pitch), _p(ts), _p(Rm), _p(ms)))
+        return ms
+
     def sync(self):
         self._chk(self.lib.kvfe_sync(self.h))
 
