@@ -137,7 +137,6 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   if (c.nr_horizontal_bins * c.nr_vertical_bins > 64 || c.nr_horizontal_bins < 1 || c.nr_vertical_bins < 1)
     return set_err(nullptr, KVFE_ERR_INVALID_ARG, "at most 64 bins");
   if (c.ransac_randomize) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "ransac_randomize must be 0");
-  if (!c.ransac_use_2point_mono) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "5-point mono RANSAC not built in this round");
   if (c.enable_subpixel_corner_refinement && (c.subpix_window_size < 1 || c.subpix_window_size > 12 || c.subpix_zero_zone >= 0))
     return set_err(nullptr, KVFE_ERR_INVALID_ARG, "subpix window must be in [1,12], zero zone -1");
   if (c.max_nr_keypoints_before_anms < 1 || c.max_nr_keypoints_before_anms > 4096)
@@ -257,7 +256,7 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   }
   // OpenGV rnd(): uniform_int_distribution<int>(0, INT_MAX)(mt19937(12345)), both libstdc++ algorithms
   {
-    int n = 8 * (dc.ransac_iters + 1) * 12 + 64;
+    int n = 16 * (dc.ransac_iters + 1) + 1024;
     std::vector<int> tab(n);
     std::mt19937 alg; alg.seed(12345u);
     for (int i = 0; i < n;) {
@@ -676,7 +675,7 @@ extern "C" int kvfe_ransac_mono(kvfe_ctx* ctx, const double* f_ref, const double
   CU(cudaMemcpyAsync(d_a, f_ref, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   CU(cudaMemcpyAsync(d_b, f_cur, 3 * (size_t)n * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
   if (R12) CU(cudaMemcpyAsync(d_R, R12, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
-  ctx->launches += launch_ransac_mono_raw(dc, ctx->db, d_a, d_b, n, R12 ? d_R : nullptr, 1, d_inl, d_n, d_pose, d_st, ctx->stream);
+  ctx->launches += launch_ransac_mono_raw(dc, ctx->db, d_a, d_b, n, R12 ? d_R : nullptr, R12 ? 1 : 0, d_inl, d_n, d_pose, d_st, ctx->stream);
   CHECK_LAUNCH();
   std::vector<int> flags(n);
   CU(cudaMemcpyAsync(flags.data(), d_inl, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));

@@ -13,6 +13,7 @@
 //     computeMedianDisparity -- Tracker.cpp:836-1018.
 #include "common.cuh"
 #include "matches.cuh"
+#include "fivept.cuh"
 
 #define RS_THREADS 512
 
@@ -145,28 +146,33 @@ __device__ __forceinline__ double cloud_score(const double* model, const double*
 }
 
 // ------------------------------------------------------------------------------------------------
-// generic sample-consensus CTA routine. problem: 0 = 2-pt (needs R12), 1 = 3-pt Arun.
+// generic sample-consensus CTA routine. problem: 0 = 2-pt (needs R12), 1 = 3-pt Arun, 2 = 5-pt Nister.
 // a, b: n x 3 doubles.  Workspace (ints): shuffled[n] + samples[NS*ssz] + counts[NS];
 // models: NS x 12 doubles.  Returns success; writes best model, inlier flags (0/1) and *n_inl.
 // ------------------------------------------------------------------------------------------------
 struct SacResult { int success; int n_inl; int iterations; };
 
-__device__ SacResult sac_run(int problem, const double* a, const double* b, int n, const double* R12,
+template <int problem>
+__device__ SacResult sac_run(const double* a, const double* b, int n, const double* R12,
                              double threshold, int max_it, double prob, const int* __restrict__ rnd, int rnd_n,
                              int* wi, double* models, double* best_model, int* inl_flag) {
   __shared__ SacResult res;
   __shared__ int s_best, s_done, s_iter, s_nbest, s_j0;
   __shared__ double s_k;
   __shared__ int s_counts[RS_THREADS / 32];
-  const int ssz = problem == 0 ? 2 : 3;
-  const int NS = max_it + 1;
+  __shared__ int s_valid[RS_THREADS / 32];
+  __shared__ int s_skipped;
+  const int ssz = problem == 0 ? 2 : (problem == 1 ? 3 : 8);
+  // the 5-point solver can fail (no real root): such draws are skipped without counting as an
+  // iteration (opengv Ransac::computeModel), so a few more samples than iterations are drawn
+  const int NS = (problem == 2) ? 2 * (max_it + 1) : max_it + 1;
   __shared__ int s_shuffled[2048];
   __shared__ int s_samples[3 * 256];
   int* shuffled = (n <= 2048) ? s_shuffled : wi;
-  int* samples = (NS <= 256) ? s_samples : wi + n;
+  int* samples = (NS * ssz <= 3 * 256) ? s_samples : wi + n;
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5, nw = blockDim.x >> 5;
   const bool enough = n >= ssz;
-  if (tid == 0) { s_best = -1; s_done = enough ? 0 : 1; s_iter = 0; s_nbest = -2147483647; s_k = 1.0; s_j0 = 0; }
+  if (tid == 0) { s_best = -1; s_done = enough ? 0 : 1; s_iter = 0; s_nbest = -2147483647; s_k = 1.0; s_j0 = 0; s_skipped = 0; }
   if (enough) {
     for (int i = tid; i < n; i += blockDim.x) shuffled[i] = i;
     __syncthreads();
@@ -192,14 +198,18 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
     double* m = models + 12 * (size_t)warp;     // chunk-local model slots
     int cnt = 0;
     if (j < NS) {
+      int ok = 1;
       if (lane == 0) {
         if (problem == 0) twopt_model(R12, a, b, samples[j * 2], samples[j * 2 + 1], m);
-        else arun_model(a, b, samples + j * 3, 3, m);
+        else if (problem == 1) arun_model(a, b, samples + j * 3, 3, m);
+        else ok = fivept::solve(a, b, samples + j * 8, m) ? 1 : 0;
+        s_valid[warp] = ok;
       }
       __syncwarp();
-      for (int i = lane; i < n; i += 32) {
+      ok = s_valid[warp];
+      for (int i = lane; ok && i < n; i += 32) {
         double sc;
-        if (problem == 0) {
+        if (problem != 1) {
           double R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]};
           double t[3] = {m[3], m[7], m[11]};
           sc = relpose_score(R, t, a + 3 * i, b + 3 * i);
@@ -214,8 +224,10 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
       int iterations = s_iter, n_best = s_nbest, best = s_best;
       double k = s_k;
       int done = 0;
+      int skipped = s_skipped;
       for (int w = 0; w < nw; ++w) {
-        if (!((double)iterations < k) || j0 + w >= NS) { done = 1; break; }
+        if (!((double)iterations < k) || j0 + w >= NS || skipped >= 10 * max_it) { done = 1; break; }
+        if (!s_valid[w]) { ++skipped; continue; }
         int c = s_counts[w];
         if (c > n_best) {
           n_best = c; best = j0 + w;
@@ -230,6 +242,7 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
         if (iterations > max_it) { done = 1; break; }
       }
       if (!done && (!((double)iterations < k) || j0 + nw >= NS)) done = 1;
+      s_skipped = skipped;
       s_iter = iterations; s_nbest = n_best; s_best = best; s_k = k; s_done = done; s_j0 = j0 + nw;
     }
     __syncthreads();
@@ -241,7 +254,7 @@ __device__ SacResult sac_run(int problem, const double* a, const double* b, int 
     const double* m = best_model;
     for (int i = tid; i < n; i += blockDim.x) {
       double sc;
-      if (problem == 0) {
+      if (problem != 1) {
         double R[9] = {m[0], m[1], m[2], m[4], m[5], m[6], m[8], m[9], m[10]};
         double t[3] = {m[3], m[7], m[11]};
         sc = relpose_score(R, t, a + 3 * i, b + 3 * i);
@@ -283,6 +296,7 @@ __device__ __forceinline__ double* ws_tmp(const DevCfg& dc, const DevBuf& db, in
 }
 
 // outlierRejectionMono (VisionImuFrontend.cpp:90-113) -> geometricOutlierRejection2d2d(Frame*, Frame*, Pose3)
+template <int PROBLEM>
 __global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevBuf db, int mode_mask) {
   const int b = blockIdx.x;
   StreamState& s = db.st[b];
@@ -313,8 +327,8 @@ __global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevB
   }
   __syncthreads();
   int* wi = db.scratch_i + (size_t)b * db.scratch_stride;
-  SacResult r = sac_run(0, a, bb, n, R12, dc.thr_mono, dc.ransac_iters, dc.ransac_prob, db.rnd_table, db.rnd_n,
-                        wi, ws_models(dc, db, b), model, inl);
+  SacResult r = sac_run<PROBLEM>(a, bb, n, R12, dc.thr_mono, dc.ransac_iters, dc.ransac_prob,
+                                 db.rnd_table, db.rnd_n, wi, ws_models(dc, db, b), model, inl);
   int status;
   if (!r.success) status = KVFE_TRK_INVALID;
   else status = (r.n_inl < dc.min_mono_inl) ? KVFE_TRK_FEW_MATCHES : KVFE_TRK_VALID;
@@ -514,8 +528,8 @@ __global__ void __launch_bounds__(RS_THREADS) stereo_ransac_kernel(DevCfg dc, De
       }
     __syncthreads();
     int* wi = db.scratch_i + (size_t)b * db.scratch_stride;
-    SacResult r = sac_run(1, a, bb, n, nullptr, dc.thr_stereo, dc.ransac_iters, dc.ransac_prob, db.rnd_table,
-                          db.rnd_n, wi, ws_models(dc, db, b), pose, inl);
+    SacResult r = sac_run<1>(a, bb, n, nullptr, dc.thr_stereo, dc.ransac_iters, dc.ransac_prob, db.rnd_table,
+                             db.rnd_n, wi, ws_models(dc, db, b), pose, inl);
     if (!r.success) status = KVFE_TRK_INVALID;
     else status = r.n_inl < dc.min_stereo_inl ? KVFE_TRK_FEW_MATCHES : KVFE_TRK_VALID;
     if (threadIdx.x < 9) info[threadIdx.x] = 0.0;
@@ -544,7 +558,8 @@ __global__ void __launch_bounds__(RS_THREADS) stereo_ransac_kernel(DevCfg dc, De
 // ------------------------------------------------------------------------------------------------
 // stage-level ("raw") kernels: one problem, plain arrays
 // ------------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(RS_THREADS) sac_raw_kernel(DevCfg dc, DevBuf db, int problem, const double* a,
+template <int problem>
+__global__ void __launch_bounds__(RS_THREADS) sac_raw_kernel(DevCfg dc, DevBuf db, const double* a,
                                                              const double* b, int n, const double* R12, double thr,
                                                              int min_inl, int* inl, int* n_inl, double* pose,
                                                              int* status) {
@@ -553,8 +568,8 @@ __global__ void __launch_bounds__(RS_THREADS) sac_raw_kernel(DevCfg dc, DevBuf d
   if (threadIdx.x < 9) Rs[threadIdx.x] = R12 ? R12[threadIdx.x] : ((threadIdx.x % 4 == 0) ? 1.0 : 0.0);
   __syncthreads();
   int* wi = db.scratch_i;
-  SacResult r = sac_run(problem, a, b, n, Rs, thr, dc.ransac_iters, dc.ransac_prob, db.rnd_table, db.rnd_n, wi,
-                        ws_models(dc, db, 0), model, inl);
+  SacResult r = sac_run<problem>(a, b, n, Rs, thr, dc.ransac_iters, dc.ransac_prob, db.rnd_table, db.rnd_n, wi,
+                                 ws_models(dc, db, 0), model, inl);
   if (threadIdx.x == 0) {
     *n_inl = r.n_inl;
     *status = !r.success ? KVFE_TRK_INVALID : (r.n_inl < min_inl ? KVFE_TRK_FEW_MATCHES : KVFE_TRK_VALID);
@@ -593,7 +608,8 @@ __global__ void __launch_bounds__(RS_THREADS) vote_raw_kernel(DevCfg dc, DevBuf 
 }
 
 int launch_ransac_mono(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s) {
-  mono_ransac_kernel<<<dc.B, RS_THREADS, 0, s>>>(dc, db, mode_mask);
+  if (dc.use_2pt) mono_ransac_kernel<0><<<dc.B, RS_THREADS, 0, s>>>(dc, db, mode_mask);
+  else mono_ransac_kernel<2><<<dc.B, RS_THREADS, 0, s>>>(dc, db, mode_mask);
   return 1;
 }
 int launch_ransac_stereo(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s) {
@@ -603,15 +619,16 @@ int launch_ransac_stereo(const DevCfg& dc, const DevBuf& db, int mode_mask, cuda
 int launch_ransac_mono_raw(const DevCfg& dc, const DevBuf& db, const double* f_ref, const double* f_cur,
                            int n, const double* R12, int use_2pt, int* inl, int* n_inl, double* pose,
                            int* status, cudaStream_t s) {
-  (void)use_2pt;
-  sac_raw_kernel<<<1, RS_THREADS, 0, s>>>(dc, db, 0, f_ref, f_cur, n, R12, dc.thr_mono, dc.min_mono_inl, inl, n_inl,
-                                          pose, status);
+  if (use_2pt) sac_raw_kernel<0><<<1, RS_THREADS, 0, s>>>(dc, db, f_ref, f_cur, n, R12, dc.thr_mono, dc.min_mono_inl, inl,
+                                                          n_inl, pose, status);
+  else sac_raw_kernel<2><<<1, RS_THREADS, 0, s>>>(dc, db, f_ref, f_cur, n, R12, dc.thr_mono, dc.min_mono_inl, inl,
+                                                   n_inl, pose, status);
   return 1;
 }
 int launch_ransac_3pt_raw(const DevCfg& dc, const DevBuf& db, const double* p_ref, const double* p_cur,
                           int n, int* inl, int* n_inl, double* pose, int* status, cudaStream_t s) {
-  sac_raw_kernel<<<1, RS_THREADS, 0, s>>>(dc, db, 1, p_ref, p_cur, n, nullptr, dc.thr_stereo, dc.min_stereo_inl, inl,
-                                          n_inl, pose, status);
+  sac_raw_kernel<1><<<1, RS_THREADS, 0, s>>>(dc, db, p_ref, p_cur, n, nullptr, dc.thr_stereo, dc.min_stereo_inl, inl,
+                                             n_inl, pose, status);
   return 1;
 }
 int launch_ransac_1pt_raw(const DevCfg& dc, const DevBuf& db, const float* rl, const float* rr,

@@ -122,3 +122,19 @@ def test_sequence_synthetic_batch():
     ok = run_sequence(ctx, oracles, frames, lambda b, k, l: streams[b].kf_rotation(l, k), "synth")
     ctx.close()
     assert ok
+
+
+def test_sequence_d455_like_5pt_3pt():
+    """The rig that switches both IMU-aided RANSAC variants off (params/D455/FrontendParams.yaml:59-60):
+    5-point Nister mono + 3-point Arun stereo, one synthetic stream."""
+    import dataclasses
+    p = dataclasses.replace(FrontendParams.euroc(), ransac_use_2point_mono=False, ransac_use_1point_stereo=False)
+    N = 10
+    p, rig, ctx = H.euroc_setup(batch=1, params=p)
+    orig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    s, fr = H.synth_frames(N, seed=20240)
+    frames = [[(f.left, f.right, f.timestamp) for f in fr]]
+    fe = ofe.StereoFrontend(p, orig)
+    ok = run_sequence(ctx, [fe], frames, lambda b, k, l: s.kf_rotation(l, k), "d455")
+    ctx.close()
+    assert ok

@@ -281,3 +281,34 @@ def test_ransac_1pt(env):
         assert ginl == inl
         assert np.abs(gpose - pose).max() < 1e-6
         assert np.abs(ginfo - info).max() <= 1e-9 * (np.abs(info).max() + 1e-30)
+
+
+def test_ransac_5pt_nister():
+    """5-point mono RANSAC (ransac_use_2point_mono = 0, e.g. params/D455): inlier masks and statuses
+    against the oracle on the reference's synthetic scenes (tests/testTracker.cpp:704-801)."""
+    import dataclasses
+    p = dataclasses.replace(FrontendParams.euroc(), ransac_use_2point_mono=False, ransac_use_1point_stereo=False,
+                            ransac_max_iterations=1000)
+    p2, rig, ctx = H.euroc_setup(batch=1, params=p)
+    cam = CameraParams.euroc_left()
+    R, T = scenes.expmap([0.01, 0.01, 0.01]), np.array([1.0, 0, 0])
+    for planar, n_in, n_out in ((False, 82, 0), (False, 80, 40), (True, 80, 40), (False, 7, 0)):
+        rng = np.random.default_rng(3)
+        f_ref, f_cur = scenes.mono_scene(rng, cam, R, T, n_in, n_out, planar)
+        prob = ors.Problem2d2dNister(f_ref, f_cur, ors.rnd_table(32768)) if n_in + n_out >= 8 else None
+        if prob is not None:
+            ok, pose, inl = ors.run_ransac(prob, 1e-6, 1000, 0.995)
+        else:
+            ok, pose, inl = False, None, []
+        st, gpose, ginl = ctx.ransac_mono(f_ref, f_cur, None)
+        est = ors.INVALID if not ok else (ors.FEW_MATCHES if len(inl) < 10 else ors.VALID)
+        H.diag("ransac_5pt", planar=planar, n_in=n_in, n_out=n_out, status_gpu=st, status_ref=est,
+               inliers_equal=ginl == inl, n_inl_gpu=len(ginl), n_inl_ref=len(inl),
+               pose_err=float(np.abs(gpose - pose).max()) if ok and st != ors.INVALID else -1.0)
+        assert st == est
+        assert ginl == inl
+        if ok:
+            assert np.allclose(gpose[:, :3], R, atol=1e-3)
+            t = gpose[:, 3] / np.linalg.norm(gpose[:, 3])
+            assert np.allclose(t, T, atol=1e-3)
+    ctx.close()
