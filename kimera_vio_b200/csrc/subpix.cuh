@@ -75,8 +75,10 @@ static __device__ void corner_subpix_warp(const unsigned char* __restrict__ img,
     float nx = (float)(cIx + c * scale * bb1 - bsum * scale * bb2);
     float ny = (float)(cIy - bsum * scale * bb1 + a * scale * bb2);
     err = (nx - cIx) * (nx - cIx) + (ny - cIy) * (ny - cIy);
+    // cv2 4.13: a step that leaves the image is discarded (the previous estimate is kept) -- pinned
+    // against cv2.cornerSubPix on a corner 3 px from the right border (tests: min_distance_8 variant)
+    if (nx < 0 || nx >= W || ny < 0 || ny >= H) break;
     cIx = nx; cIy = ny;
-    if (cIx < 0 || cIx >= W || cIy < 0 || cIy >= H) break;
   } while (++iter < max_iters && err > eps2);
   if (fabsf(cIx - cTx) > win || fabsf(cIy - cTy) > win) { cIx = cTx; cIy = cTy; }
   *px = cIx; *py = cIy;

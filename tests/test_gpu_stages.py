@@ -312,3 +312,43 @@ def test_ransac_5pt_nister():
             t = gpose[:, 3] / np.linalg.norm(gpose[:, 3])
             assert np.allclose(t, T, atol=1e-3)
     ctx.close()
+
+
+@pytest.mark.parametrize("variant", ["no_nms", "topn", "binning_mask", "min_distance_8", "quality_1e-10"])
+def test_detector_param_variants(variant):
+    """The detector configurations of the reference's own tests (tests/testFeatureDetector.cpp:26-258:
+    no NMS, TopN, Binning with a bin mask, quality 1e-10) and the uHumans2 min_distance (8, which
+    reaches the 2000-corner cap) -- GPU vs oracle on a real Euroc image and a synthetic one."""
+    import dataclasses
+    from kimera_vio_b200.params import ANMS_TOPN
+    base = FrontendParams.euroc()
+    if variant == "no_nms":
+        p = dataclasses.replace(base, enable_non_max_suppression=False, max_nr_keypoints_before_anms=400,
+                                enable_subpixel_corner_refinement=False)
+    elif variant == "topn":
+        p = dataclasses.replace(base, non_max_suppression_type=ANMS_TOPN)
+    elif variant == "binning_mask":
+        m = np.ones((5, 4)); m[0, :] = 0; m[2, 1] = 0; m[4, 3] = 0
+        p = dataclasses.replace(base, nr_horizontal_bins=4, nr_vertical_bins=5, binning_mask=m,
+                                max_features_per_frame=140, quality_level=1e-10,
+                                enable_subpixel_corner_refinement=False)
+    elif variant == "min_distance_8":
+        p = dataclasses.replace(base, min_distance=8)
+    else:
+        p = dataclasses.replace(base, quality_level=1e-10)
+    p, rig, ctx = H.euroc_setup(batch=1, params=p)
+    g, lefts, _ = H.golden()
+    s, frames = H.synth_frames(1)
+    det = ofe.FeatureDetector(p)
+    cam = CameraParams.euroc_left()
+    for name, img in (("euroc", lefts[2]), ("synth", frames[0].left)):
+        fr = ofe.Frame(0, 0, img, cam)
+        need = p.max_features_per_frame
+        e = det.detect_corners(fr, need)
+        gq = ctx.detect(img, [], [], need)
+        same_n = len(e) == len(gq)
+        err = float(np.abs(gq - e).max()) if same_n and len(e) else -1.0
+        H.diag("detector_variant", variant=variant, image=name, n_gpu=len(gq), n_ref=len(e), max_err=err)
+        assert same_n
+        assert len(e) == 0 or err <= TOL_PX
+    ctx.close()
