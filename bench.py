@@ -290,28 +290,30 @@ def run_gpu(args):
             for i in range(Bc):
                 pinL[c, k, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
                 pinR[c, k, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
-    pk_pin = [torch.empty(Bc * pkb, dtype=torch.uint8).pin_memory() for _ in range(NC)]
-    pk_np = [t.numpy() for t in pk_pin]
-    ptrs = [[((C.c_void_p * Bc)(*[pinL[c, k, i].data_ptr() for i in range(Bc)]),
-              (C.c_void_p * Bc)(*[pinR[c, k, i].data_ptr() for i in range(Bc)])) for k in range(n_frames)]
-            for c in range(NC)]
-
-    def run_host_ctx(c, k0, k1):
-        ctx = ctxs[c]
-        for k in range(k0, k1):
-            rc = ctx.step_raw(ptrs[c][k][0], ptrs[c][k][1], W, ts_c[c][k], R_c[c][k], pk_np[c])
-            assert rc == 0
+    # two pinned packet buffers per context (a step's buffer is owned by the library until wait returns)
+    pk_pin = [[torch.empty(Bc * pkb, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(NC)]
+    sub_args = [[(ctxs[c].h,
+                  (C.c_void_p * Bc)(*[pinL[c, k, i].data_ptr() for i in range(Bc)]),
+                  (C.c_void_p * Bc)(*[pinR[c, k, i].data_ptr() for i in range(Bc)]),
+                  C.c_size_t(W), C.c_void_p(ts_c[c][k].ctypes.data), C.c_void_p(R_c[c][k].ctypes.data),
+                  C.c_void_p(pk_pin[c][k & 1].data_ptr())) for k in range(n_frames)] for c in range(NC)]
+    hs = [c.h for c in ctxs]
 
     def run_host(k0, k1):
-        if NC == 1:
-            run_host_ctx(0, k0, k1)
-            return
-        # one host thread per context: the blocking C-ABI call releases the GIL (ctypes)
-        th = [threading.Thread(target=run_host_ctx, args=(c, k0, k1)) for c in range(NC)]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
+        # one host thread, round-robin over the sub-batches: collect frame k-1 of a context, then submit its
+        # frame k at once (H2D + kernels + packet D2H enqueued on its stream).  A context never has more than
+        # one step in flight -- the IMU rotation of frame k depends on frame k-1's keyframe decision -- but
+        # the other contexts keep the PCIe link and the SMs busy meanwhile (kvfe_frontend_submit/wait).
+        for k in range(k0, k1):
+            for c in range(NC):
+                if k > k0:
+                    rc = lib.kvfe_frontend_wait(hs[c])
+                    assert rc == 0
+                rc = lib.kvfe_frontend_submit(*sub_args[c][k])
+                assert rc == 0, lib.kvfe_last_error(hs[c])
+        for c in range(NC):
+            rc = lib.kvfe_frontend_wait(hs[c])
+            assert rc == 0
 
     for ctx in ctxs:
         ctx.reset()
@@ -402,7 +404,7 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--contexts", type=int, default=16, help="sub-batches in flight on separate CUDA streams")
+    ap.add_argument("--contexts", type=int, default=32, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--impl", default="kvfe", choices=["kvfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()

@@ -264,6 +264,23 @@ int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t
 int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev,
                                  size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
                                  float* stage_ms);
+/* Pipelined host-buffer step (the asynchronous input/output queues of the reference's
+ * PipelineModule around the frontend, pipeline/PipelineModule.h:190-215 spin(), :359-416
+ * SIMOPipelineModule input queue): submit enqueues the H2D
+ * copies, the step and the packet D2H copy and returns; wait blocks until the oldest submitted step
+ * is done and `packets` (given at submit; owned by the library until wait returns) is filled.  At
+ * most two steps may be in flight per context.  A pinned `packets` buffer receives the D2H copy
+ * directly.  With several contexts a single host thread keeps the PCIe link and the GPU busy:
+ * submit(k+1) on every context, then wait(k) on every context. */
+int kvfe_frontend_submit(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right,
+                         size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
+                         uint8_t* packets);
+int kvfe_frontend_wait(kvfe_ctx* ctx);
+/* submit on each of n contexts, then wait on each (one blocking call for n sub-batches). */
+int kvfe_frontend_step_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* const* left,
+                             const uint8_t* const* const* right, size_t pitch,
+                             const int64_t* const* timestamps, const double* const* keyframe_R_cur,
+                             uint8_t* const* packets);
 /* Enqueues one kvfe_frontend_step_dev on each of n contexts (sub-batches that run concurrently on
  * their own CUDA streams) with a single host call; arrays are indexed by context. */
 int kvfe_frontend_step_dev_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* left_dev,

@@ -305,6 +305,10 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CU(dmalloc(&db.packets, B * db.packet_bytes));
   CU(cudaMallocHost((void**)&ctx->h_stage, 2 * B * dc.img_stride));
   CU(cudaMallocHost((void**)&ctx->h_packets, B * db.packet_bytes));
+  for (int i = 0; i < 2; ++i) {
+    CU(cudaMallocHost((void**)&ctx->h_pipe[i], B * db.packet_bytes));
+    CU(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
+  }
   CU(cudaMallocHost((void**)&ctx->h_ts, KVFE_IN_SLOTS * B * sizeof(long long)));
   CU(cudaMallocHost((void**)&ctx->h_Rin, KVFE_IN_SLOTS * B * 9 * sizeof(double)));
   for (int i = 0; i < KVFE_IN_SLOTS; ++i) CU(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
@@ -335,6 +339,10 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->h_pipe[i]) cudaFreeHost(ctx->h_pipe[i]);
+    if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
+  }
   if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
   if (ctx->h_Rin) cudaFreeHost(ctx->h_Rin);
   for (int i = 0; i < KVFE_IN_SLOTS; ++i) if (ctx->in_ev[i]) cudaEventDestroy(ctx->in_ev[i]);
@@ -858,6 +866,68 @@ extern "C" int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, co
   return enqueue_step(ctx);
 }
 
+// H2D of one batch of host images: one 2-D copy per side when the batch is contiguous in host memory
+// (image b at left[0] + b*W*H), else one copy per image.
+static int upload_batch(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right, size_t pitch) {
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  const size_t B = dc.B, img = (size_t)dc.W * dc.H;
+  bool contig = (pitch == (size_t)dc.W && (size_t)dc.pitch == pitch);
+  for (size_t b = 1; b < B && contig; ++b)
+    contig = left[b] == left[0] + b * img && right[b] == right[0] + b * img;
+  unsigned char* dl = db.pyr[ctx->cur_slot] + dc.lvl_off[0];
+  if (contig && B > 1) {
+    CU(cudaMemcpy2DAsync(dl, dc.pyr_stride, left[0], img, img, B, cudaMemcpyHostToDevice, ctx->stream));
+    CU(cudaMemcpy2DAsync(db.right_raw, dc.img_stride, right[0], img, img, B, cudaMemcpyHostToDevice, ctx->stream));
+    return KVFE_OK;
+  }
+  for (size_t b = 0; b < B; ++b) {
+    RET(copy_image(ctx, dl + b * dc.pyr_stride, dc.pitch, left[b], pitch, cudaMemcpyHostToDevice));
+    RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right[b], pitch, cudaMemcpyHostToDevice));
+  }
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_submit(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right, size_t pitch,
+                                    const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets) {
+  if (!ctx || !left || !right || !timestamps || !keyframe_R_cur || !packets) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (ctx->n_submitted - ctx->n_waited >= 2) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit: two steps already in flight, call kvfe_frontend_wait first");
+  const int slot = (int)(ctx->n_submitted & 1);
+  const size_t bytes = (size_t)ctx->dc.B * ctx->db.packet_bytes;
+  RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
+  RET(upload_batch(ctx, left, right, pitch));
+  RET(enqueue_step(ctx));
+  // pinned (cudaHostAlloc / cudaHostRegister) output buffers receive the packets directly
+  cudaPointerAttributes at{};
+  const bool direct = cudaPointerGetAttributes(&at, packets) == cudaSuccess && at.type == cudaMemoryTypeHost;
+  cudaGetLastError();
+  CU(cudaMemcpyAsync(direct ? packets : ctx->h_pipe[slot], ctx->db.packets, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaEventRecord(ctx->pipe_done[slot], ctx->stream));
+  ctx->pipe_user[slot] = packets; ctx->pipe_direct[slot] = direct;
+  ++ctx->n_submitted;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_wait(kvfe_ctx* ctx) {
+  if (!ctx) return KVFE_ERR_INVALID_ARG;
+  if (ctx->n_waited == ctx->n_submitted) return set_err(ctx, KVFE_ERR_INVALID_ARG, "wait: nothing in flight");
+  const int slot = (int)(ctx->n_waited & 1);
+  CU(cudaEventSynchronize(ctx->pipe_done[slot]));
+  if (!ctx->pipe_direct[slot]) memcpy(ctx->pipe_user[slot], ctx->h_pipe[slot], (size_t)ctx->dc.B * ctx->db.packet_bytes);
+  ++ctx->n_waited;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_step_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* const* left,
+                                        const uint8_t* const* const* right, size_t pitch,
+                                        const int64_t* const* timestamps, const double* const* keyframe_R_cur,
+                                        uint8_t* const* packets) {
+  if (!ctxs || n <= 0 || !left || !right || !timestamps || !keyframe_R_cur || !packets) return KVFE_ERR_INVALID_ARG;
+  for (int i = 0; i < n; ++i)
+    RET(kvfe_frontend_submit(ctxs[i], left[i], right[i], pitch, timestamps[i], keyframe_R_cur[i], packets[i]));
+  for (int i = 0; i < n; ++i) RET(kvfe_frontend_wait(ctxs[i]));
+  return KVFE_OK;
+}
+
 extern "C" int kvfe_frontend_step_dev_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* left_dev,
                                             const uint8_t* const* right_dev, size_t pitch,
                                             const int64_t* const* timestamps, const double* const* keyframe_R_cur) {
@@ -939,12 +1009,9 @@ extern "C" int kvfe_frontend_step(kvfe_ctx* ctx, const uint8_t* const* left, con
   if (!ctx || !left || !right || !timestamps || !keyframe_R_cur || !packets) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const size_t B = dc.B;
+  if (ctx->n_submitted != ctx->n_waited) return set_err(ctx, KVFE_ERR_INVALID_ARG, "step: submitted steps still in flight");
   RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
-  for (size_t b = 0; b < B; ++b) {
-    RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch, left[b], pitch,
-                   cudaMemcpyHostToDevice));
-    RET(copy_image(ctx, db.right_raw + b * dc.img_stride, dc.pitch, right[b], pitch, cudaMemcpyHostToDevice));
-  }
+  RET(upload_batch(ctx, left, right, pitch));
   RET(enqueue_step(ctx));
   CU(cudaMemcpyAsync(ctx->h_packets, db.packets, B * db.packet_bytes, cudaMemcpyDeviceToHost, s));
   CU(cudaStreamSynchronize(s));

@@ -152,6 +152,9 @@ struct kvfe_ctx {
   // pinned staging for the host-buffer step
   unsigned char* h_stage;      // 2 * B * img_stride
   unsigned char* h_packets;
+  // submit/wait pipeline (depth KVFE_PIPE_DEPTH): pinned packet staging per in-flight step
+  unsigned char* h_pipe[2]; cudaEvent_t pipe_done[2]; unsigned char* pipe_user[2]; bool pipe_direct[2];
+  unsigned long long n_submitted, n_waited;
   long long* d_ts; double* d_Rin;        // step inputs
   long long* h_ts; double* h_Rin;        // KVFE_IN_SLOTS pinned slots each
   cudaEvent_t in_ev[KVFE_IN_SLOTS]; int in_used[KVFE_IN_SLOTS]; int in_slot;

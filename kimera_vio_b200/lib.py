@@ -400,6 +400,13 @@ class Context:
                                                         C.c_size_t(pitch), _p(ts), _p(Rm), _p(ms)))
         return ms
 
+    def submit_raw(self, lp, rp, pitch: int, ts: np.ndarray, Rm: np.ndarray, packets: np.ndarray):
+        """kvfe_frontend_submit with prebuilt pointer arrays; `packets` must stay alive until wait()."""
+        return self.lib.kvfe_frontend_submit(self.h, lp, rp, C.c_size_t(pitch), _p(ts), _p(Rm), _p(packets))
+
+    def wait(self):
+        return self.lib.kvfe_frontend_wait(self.h)
+
     def sync(self):
         self._chk(self.lib.kvfe_sync(self.h))
 

@@ -138,3 +138,54 @@ def test_sequence_d455_like_5pt_3pt():
     ok = run_sequence(ctx, [fe], frames, lambda b, k, l: s.kf_rotation(l, k), "d455")
     ctx.close()
     assert ok
+
+
+def test_submit_wait_pipeline_matches_step():
+    """kvfe_frontend_submit / kvfe_frontend_wait (two steps in flight, pinned and pageable output
+    buffers) must produce byte-identical packets to the blocking kvfe_frontend_step."""
+    import ctypes as C
+    import torch
+    B, N = 2, 8
+    p, rig, ctxA = H.euroc_setup(batch=B)
+    _, _, ctxB = H.euroc_setup(batch=B)
+    streams, frames = [], []
+    for b in range(B):
+        s, fr = H.synth_frames(N, seed=777 + 31 * b)
+        streams.append(s)
+        frames.append(fr)
+    # contiguous host batches (exercises the single 2-D copy upload) for A, separate arrays for B
+    lkf = [0] * B
+    ref, Rs_all, ts_all = [], [], []
+    pkb = ctxA.packet_bytes
+    for k in range(N):
+        Lc = np.ascontiguousarray(np.stack([frames[b][k].left for b in range(B)]))
+        Rc = np.ascontiguousarray(np.stack([frames[b][k].right for b in range(B)]))
+        ts = np.array([frames[b][k].timestamp for b in range(B)], np.int64)
+        Rm = np.ascontiguousarray(np.array([streams[b].kf_rotation(lkf[b], k) for b in range(B)]).reshape(B, 9))
+        buf = np.empty(B * pkb, np.uint8)
+        lp = (C.c_void_p * B)(*[Lc[b].ctypes.data for b in range(B)])
+        rp = (C.c_void_p * B)(*[Rc[b].ctypes.data for b in range(B)])
+        assert ctxA.step_raw(lp, rp, Lc.shape[2], ts, Rm, buf) == 0
+        for b, pk in enumerate(ctxA.parse_packets(buf)):
+            if pk["is_keyframe"]:
+                lkf[b] = k
+        ref.append(buf)
+        Rs_all.append(Rm)
+        ts_all.append(ts)
+    outs = [torch.empty(B * pkb, dtype=torch.uint8).pin_memory().numpy() if k % 2 == 0 else np.empty(B * pkb, np.uint8)
+            for k in range(N)]
+    keep = []
+    for k in range(N):
+        lp = (C.c_void_p * B)(*[frames[b][k].left.ctypes.data for b in range(B)])
+        rp = (C.c_void_p * B)(*[frames[b][k].right.ctypes.data for b in range(B)])
+        keep.append((lp, rp))
+        assert ctxB.submit_raw(lp, rp, frames[0][k].left.strides[0], ts_all[k], Rs_all[k], outs[k]) == 0
+        if k >= 1:
+            assert ctxB.wait() == 0
+    assert ctxB.wait() == 0
+    assert ctxB.wait() != 0                       # nothing in flight: must fail loudly
+    bad = [k for k in range(N) if not np.array_equal(ref[k], outs[k])]
+    H.diag("submit_wait", mismatching_frames=bad, n_kf=int(sum(l > 0 for l in lkf)))
+    ctxA.close()
+    ctxB.close()
+    assert not bad
