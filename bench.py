@@ -274,7 +274,9 @@ def run_gpu(args):
         ev0.record(streams[0])
         for st in streams[1:]:
             st.wait_event(ev0)
+        t_enq = time.perf_counter()
         run_dev(Wm, n_frames)
+        t_enq = time.perf_counter() - t_enq
         for e, st in zip(ev1, streams):
             e.record(st)
         barrier()
@@ -378,6 +380,7 @@ def run_gpu(args):
                     "h2d_bytes_per_step": int(2 * B * W * H + B * 80),
                     "d2h_bytes_per_step": int(B * pkb)},
             "gpu_launches": int(launches),
+            "host_enqueue_ms_per_step": 1e3 * t_enq / K,
             "clocks": clocks,
             "roofline": {"bound": "hbm", "kernel": "lk_kernel_col<24> (pyramidal LK, dominant: ~30% of the step)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",

@@ -223,6 +223,14 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CU(cudaMemcpy(ctx->d_cam, ctx->cam, sizeof(CamModel) * 2, cudaMemcpyHostToDevice));
   for (int k = 0; k < 2; ++k) CU(dmalloc(&db.pyr[k], B * dc.pyr_stride));
   CU(dmalloc(&db.right_raw, B * dc.img_stride));
+  // fixed-point remap tables (cv::convertMaps-style: integer source pixel + 5+5 fractional bits),
+  // computed once per rig from the in-register f64 map model
+  for (int k = 0; k < 2; ++k) {
+    CU(dmalloc(&db.rmap[k], (size_t)dc.W * dc.H));
+    launch_rmap_table(dc, ctx->d_cam, k, db.rmap[k], ctx->stream);
+  }
+  CU(cudaStreamSynchronize(ctx->stream));
+  CU(cudaGetLastError());
   CU(dmalloc(&db.rectL, B * dc.img_stride));
   CU(dmalloc(&db.rectR, B * dc.img_stride));
   CU(dmalloc(&db.mask, B * dc.img_stride));
@@ -319,7 +327,12 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   {
     const char* e = getenv("KVFE_NO_GRAPH");
     ctx->use_graph = !(e && e[0] == '1');
+    // opt-in: measured 4.5x SLOWER with 32 concurrent step graphs on B200 / CUDA 12.9 (graphs holding
+    // conditional nodes do not overlap across streams the way flat kernel graphs do), see DESIGN.md
+    const char* c = getenv("KVFE_GRAPH_COND");
+    ctx->use_cond = (c && c[0] == '1');
   }
+  CU(dmalloc(&ctx->d_kf_steps, 1));
   *out = ctx;
   return KVFE_OK;
 }
@@ -328,7 +341,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
   DevBuf& db = ctx->db;
-  void* ptrs[] = {ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
+  void* ptrs[] = {ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
                   db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
@@ -353,7 +366,17 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
 
 extern "C" const char* kvfe_last_error(const kvfe_ctx* ctx) { return ctx ? ctx->err : g_create_err; }
 extern "C" int kvfe_max_keypoints(const kvfe_ctx* ctx) { return ctx ? ctx->dc.cap : 0; }
-extern "C" int kvfe_kernel_launches(const kvfe_ctx* ctx) { return ctx ? (int)ctx->launches : 0; }
+// kernels launched so far: host-side count of everything outside the conditional keyframe part
+// plus (executions of that part, counted on the device) x (its kernels)
+extern "C" int kvfe_kernel_launches(const kvfe_ctx* ctx) {
+  if (!ctx) return 0;
+  int kf = 0;
+  if (ctx->d_kf_steps) {
+    cudaStreamSynchronize(ctx->stream);
+    cudaMemcpy(&kf, ctx->d_kf_steps, sizeof(int), cudaMemcpyDeviceToHost);
+  }
+  return (int)(ctx->launches + (long long)kf * ctx->graph_launches_kf);
+}
 extern "C" size_t kvfe_packet_bytes(const kvfe_ctx* ctx) { return ctx ? ctx->db.packet_bytes : 0; }
 extern "C" int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries) {
   if (!ctx || !offsets) return KVFE_ERR_INVALID_ARG;
@@ -415,8 +438,8 @@ extern "C" int kvfe_rectify_pair(kvfe_ctx* ctx, const uint8_t* left, const uint8
   unsigned char* L = db.pyr[0] + dc.lvl_off[0];
   RET(upload_image(ctx, L, dc.pitch, left, pitch));
   RET(upload_image(ctx, db.right_raw, dc.pitch, right, pitch));
-  ctx->launches += launch_rectify(dc, ctx->d_cam, 0, L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
-  ctx->launches += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_rectify(dc, db.rmap[0], L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_rectify(dc, db.rmap[1], db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
   CHECK_LAUNCH();
   RET(download_image(ctx, left_rect, out_pitch, db.rectL, dc.pitch));
   RET(download_image(ctx, right_rect, out_pitch, db.rectR, dc.pitch));
@@ -634,8 +657,8 @@ extern "C" int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint
   unsigned char* L = db.pyr[0] + dc.lvl_off[0];
   RET(upload_image(ctx, L, dc.pitch, left, pitch));
   RET(upload_image(ctx, db.right_raw, dc.pitch, right, pitch));
-  ctx->launches += launch_rectify(dc, ctx->d_cam, 0, L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
-  ctx->launches += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_rectify(dc, db.rmap[0], L, dc.pyr_stride, db.rectL, dc.img_stride, 1, nullptr, 0, ctx->stream);
+  ctx->launches += launch_rectify(dc, db.rmap[1], db.right_raw, dc.img_stride, db.rectR, dc.img_stride, 1, nullptr, 0, ctx->stream);
   ctx->launches += launch_sparse_stereo(dc, db, ctx->d_cam, 1 << 2, 0, ctx->stream);
   CHECK_LAUNCH();
   CU(cudaStreamSynchronize(ctx->stream));
@@ -760,67 +783,157 @@ extern "C" int kvfe_frontend_reset(kvfe_ctx* ctx) {
   return KVFE_OK;
 }
 
-// the fixed kernel sequence of one step; images of the current frame already sit in
-// pyr[cur_slot] level 0 (left) and right_raw (right).
-static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch);
-
-// The kernel sequence of a step is identical from step to step (all arguments are by-value structs
-// of device pointers; only the pyramid slot alternates), so it is captured once per slot into a
-// CUDA graph and replayed: one cudaGraphLaunch instead of ~28 kernel launches per step.
-static int enqueue_step(kvfe_ctx* ctx) {
-  const int cur = ctx->cur_slot;
-  long long n = 0;
-  if (ctx->use_graph) {
-    if (!ctx->graph_ready[cur]) {
-      cudaGraph_t g = nullptr;
-      CU(cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal));
-      int rc = enqueue_step_kernels(ctx, &n);
-      cudaError_t e = cudaStreamEndCapture(ctx->stream, &g);
-      if (rc != KVFE_OK) return rc;
-      if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
-      CU(cudaGraphInstantiate(&ctx->step_graph[cur], g, 0));
-      cudaGraphDestroy(g);
-      ctx->graph_ready[cur] = 1;
-      ctx->graph_launches = n;
-    }
-    CU(cudaGraphLaunch(ctx->step_graph[cur], ctx->stream));
-    ctx->launches += ctx->graph_launches;
-  } else {
-    RET(enqueue_step_kernels(ctx, &n));
-    ctx->launches += n;
-  }
-  ctx->cur_slot ^= 1;
-  return KVFE_OK;
-}
-
-static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch) {
+// The fixed kernel sequence of one step; images of the current frame already sit in
+// pyr[cur_slot] level 0 (left) and right_raw (right).  Three parts: (1) tracking up to the keyframe
+// decision, (2) the keyframe / detection part (every kernel of it exits at entry for a stream in
+// plain tracking mode), (3) packet assembly.
+static int enqueue_part_track(kvfe_ctx* ctx, unsigned long long cond, long long* n_launch) {
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const int cur = ctx->cur_slot, prev = cur ^ 1;
-  const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
-  unsigned char* Lcur = db.pyr[cur] + dc.lvl_off[0];
   long long n = 0;
   n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, s);
   n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
   n += launch_track_pre(dc, db, s);
   n += launch_lk(dc, db, prev, cur, s);
   n += launch_track_post(dc, db, ctx->d_cam, s);
-  n += launch_decide(dc, db, s);
+  n += launch_decide(dc, db, cond, s);
+  *n_launch += n;
+  CU(cudaGetLastError());
+  return KVFE_OK;
+}
+
+static int enqueue_part_keyframe(kvfe_ctx* ctx, int* kf_counter, long long* n_launch) {
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
+  const int cur = ctx->cur_slot;
+  const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
+  unsigned char* Lcur = db.pyr[cur] + dc.lvl_off[0];
+  long long n = 0;
   // keyframe: mono RANSAC -> sparse stereo -> stereo RANSAC
   n += launch_ransac_mono(dc, db, M_KF, s);
-  n += launch_rectify(dc, ctx->d_cam, 0, Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
-  n += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_rectify(dc, db.rmap[0], Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_rectify(dc, db.rmap[1], db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
   n += launch_sparse_stereo(dc, db, ctx->d_cam, M_KF, 0, s);
   n += launch_ransac_stereo(dc, db, M_KF, s);
   // detection (bootstrap, keyframe, all-tracks-lost)
-  n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, s);
+  n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, kf_counter, s);
   n += launch_gftt(dc, db, Lcur, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, M_BOOT | M_KF | M_LOST, s);
   n += launch_select(dc, db, Lcur, dc.pyr_stride, ctx->d_cam, M_BOOT | M_KF | M_LOST, 1, s);
   // sparse stereo over all keypoints incl. the new ones (the second remap of the reference is
   // idempotent -- same raw images, same maps -- and is therefore not repeated)
   n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, 1, s);
-  n += launch_finalize(dc, db, s);
-  *n_launch = n;
+  *n_launch += n;
   CU(cudaGetLastError());
+  return KVFE_OK;
+}
+
+__global__ void kvfe_empty_kernel() {}
+
+static int enqueue_part_finalize(kvfe_ctx* ctx, long long* n_launch) {
+  *n_launch += launch_finalize(ctx->dc, ctx->db, ctx->stream);
+  if (const char* e = getenv("KVFE_EXTRA_LAUNCHES"))      // diagnostic: dispatch-rate sensitivity
+    for (int i = 0; i < atoi(e); ++i) kvfe_empty_kernel<<<1, 32, 0, ctx->stream>>>();
+  CU(cudaGetLastError());
+  return KVFE_OK;
+}
+
+static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch) {
+  *n_launch = 0;
+  RET(enqueue_part_track(ctx, 0ull, n_launch));
+  RET(enqueue_part_keyframe(ctx, nullptr, n_launch));
+  return enqueue_part_finalize(ctx, n_launch);
+}
+
+// The kernel sequence of a step is identical from step to step (all arguments are by-value structs
+// of device pointers; only the pyramid slot alternates), so it is built once per slot as a CUDA
+// graph and replayed: one cudaGraphLaunch per step.  The keyframe part is the body of an IF node
+// whose condition the decision kernel sets on the device (cudaGraphSetConditional): a step in which
+// no stream of the batch is at a keyframe dispatches 10 kernels instead of 32, still without any
+// host round trip.  That variant is opt-in (KVFE_GRAPH_COND=1): with many step graphs in flight on
+// separate streams it measured far slower than the flat captured graph, which is the default;
+// KVFE_NO_GRAPH=1 falls back to plain stream launches.
+static int build_step_graph(kvfe_ctx* ctx, cudaGraphExec_t* exec, long long* n_track, long long* n_kf) {
+  cudaStream_t s = ctx->stream;
+  const cudaStreamCaptureMode mode = cudaStreamCaptureModeThreadLocal;
+  cudaGraph_t g = nullptr, gout = nullptr;
+  long long na = 0, nb = 0, nc = 0;
+  if (!ctx->use_cond) {
+    CU(cudaStreamBeginCapture(s, mode));
+    int rc = enqueue_step_kernels(ctx, &na);
+    cudaError_t e = cudaStreamEndCapture(s, &g);
+    if (rc != KVFE_OK) return rc;
+    if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "graph capture failed: %s", cudaGetErrorString(e));
+    CU(cudaGraphInstantiate(exec, g, 0));
+    cudaGraphDestroy(g);
+    *n_track = na; *n_kf = 0;
+    return KVFE_OK;
+  }
+  CU(cudaGraphCreate(&g, 0));
+  cudaGraphConditionalHandle cond;
+  CU(cudaGraphConditionalHandleCreate(&cond, g, 0, cudaGraphCondAssignDefault));
+  // (1) tracking part
+  CU(cudaStreamBeginCaptureToGraph(s, g, nullptr, nullptr, 0, mode));
+  int rc = enqueue_part_track(ctx, (unsigned long long)cond, &na);
+  cudaError_t e = cudaStreamEndCapture(s, &gout);
+  if (rc != KVFE_OK) return rc;
+  if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "graph capture (tracking part) failed: %s", cudaGetErrorString(e));
+  // its last node: the only node without an outgoing edge (the part is a linear chain)
+  size_t nn = 0, ne = 0;
+  CU(cudaGraphGetNodes(g, nullptr, &nn));
+  std::vector<cudaGraphNode_t> nodes(nn);
+  CU(cudaGraphGetNodes(g, nodes.data(), &nn));
+  CU(cudaGraphGetEdges(g, nullptr, nullptr, &ne));
+  std::vector<cudaGraphNode_t> from(ne), to(ne);
+  if (ne) CU(cudaGraphGetEdges(g, from.data(), to.data(), &ne));
+  cudaGraphNode_t tail = nullptr;
+  int n_tail = 0;
+  for (cudaGraphNode_t nd : nodes) {
+    bool has_out = false;
+    for (size_t i = 0; i < ne; ++i) has_out |= from[i] == nd;
+    if (!has_out) { tail = nd; ++n_tail; }
+  }
+  if (n_tail != 1) return set_err(ctx, KVFE_ERR_CUDA, "step graph: expected one tail node, found %d", n_tail);
+  // (2) IF node + keyframe part as its body
+  cudaGraphNodeParams cp = {};
+  cp.type = cudaGraphNodeTypeConditional;
+  cp.conditional.handle = cond;
+  cp.conditional.type = cudaGraphCondTypeIf;
+  cp.conditional.size = 1;
+  cudaGraphNode_t cnode = nullptr;
+  CU(cudaGraphAddNode(&cnode, g, &tail, 1, &cp));
+  cudaGraph_t body = cp.conditional.phGraph_out[0];
+  CU(cudaStreamBeginCaptureToGraph(s, body, nullptr, nullptr, 0, mode));
+  rc = enqueue_part_keyframe(ctx, ctx->d_kf_steps, &nb);
+  e = cudaStreamEndCapture(s, &gout);
+  if (rc != KVFE_OK) return rc;
+  if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "graph capture (keyframe part) failed: %s", cudaGetErrorString(e));
+  // (3) packet assembly after the IF node
+  CU(cudaStreamBeginCaptureToGraph(s, g, &cnode, nullptr, 1, mode));
+  rc = enqueue_part_finalize(ctx, &nc);
+  e = cudaStreamEndCapture(s, &gout);
+  if (rc != KVFE_OK) return rc;
+  if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "graph capture (finalize part) failed: %s", cudaGetErrorString(e));
+  CU(cudaGraphInstantiate(exec, g, 0));
+  cudaGraphDestroy(g);
+  *n_track = na + nc; *n_kf = nb;
+  return KVFE_OK;
+}
+
+static int enqueue_step(kvfe_ctx* ctx) {
+  const int cur = ctx->cur_slot;
+  if (ctx->use_graph) {
+    if (!ctx->graph_ready[cur]) {
+      RET(build_step_graph(ctx, &ctx->step_graph[cur], &ctx->graph_launches, &ctx->graph_launches_kf));
+      ctx->graph_ready[cur] = 1;
+    }
+    CU(cudaGraphLaunch(ctx->step_graph[cur], ctx->stream));
+    // launches of the IF body are counted by the device (StreamState::kf_steps, read at kvfe_kernel_launches)
+    ctx->launches += ctx->graph_launches;
+  } else {
+    long long n = 0;
+    RET(enqueue_step_kernels(ctx, &n));
+    ctx->launches += n;
+  }
+  ctx->cur_slot ^= 1;
   return KVFE_OK;
 }
 
@@ -976,16 +1089,16 @@ extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_d
   CU(cudaEventRecord(ev[10], s));
   n += launch_track_post(dc, db, ctx->d_cam, s);
   CU(cudaEventRecord(ev[2], s));
-  n += launch_decide(dc, db, s);
+  n += launch_decide(dc, db, 0ull, s);
   n += launch_ransac_mono(dc, db, M_KF, s);
   CU(cudaEventRecord(ev[3], s));
-  n += launch_rectify(dc, ctx->d_cam, 0, Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
-  n += launch_rectify(dc, ctx->d_cam, 1, db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_rectify(dc, db.rmap[0], Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
+  n += launch_rectify(dc, db.rmap[1], db.right_raw, dc.img_stride, db.rectR, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
   CU(cudaEventRecord(ev[4], s));
   n += launch_sparse_stereo(dc, db, ctx->d_cam, M_KF, 0, s);
   n += launch_ransac_stereo(dc, db, M_KF, s);
   CU(cudaEventRecord(ev[5], s));
-  n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, s);
+  n += launch_detect_pre(dc, db, M_BOOT | M_KF | M_LOST, nullptr, s);
   n += launch_gftt(dc, db, Lcur, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, M_BOOT | M_KF | M_LOST, s);
   CU(cudaEventRecord(ev[6], s));
   n += launch_select(dc, db, Lcur, dc.pyr_stride, ctx->d_cam, M_BOOT | M_KF | M_LOST, 1, s);

@@ -204,14 +204,20 @@ __global__ void __launch_bounds__(256) track_post_kernel(DevCfg dc, DevBuf db, c
   if (threadIdx.x == 0) { db.fr.n[fk] = s_total; s.nr_tracked = s_total; }
 }
 
-__global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db) {
+// `cond` (0 = none): conditional handle of the step graph; set to 1 as soon as any stream of the
+// batch needs the keyframe / detection part (bootstrap, keyframe, all tracks lost), which otherwise
+// is skipped as a whole (a CUDA-graph IF node around ~20 kernels that would all exit at entry).
+__global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db, cudaGraphConditionalHandle cond) {
   const int b = blockIdx.x;
   StreamState& s = db.st[b];
-  if (s.mode == 0) return;
+  if (s.mode == 0) {
+    if (threadIdx.x == 0 && cond) cudaGraphSetConditional(cond, 1);
+    return;
+  }
   const int fk = b * 3 + s.slot_k, fl = b * 3 + s.slot_lkf;
   const int nk = db.fr.n[fk];
   if (nk == 0) {                       // StereoVisionImuFrontend.cpp:312-323
-    if (threadIdx.x == 0) s.mode = 3;
+    if (threadIdx.x == 0) { s.mode = 3; if (cond) cudaGraphSetConditional(cond, 1); }
     return;
   }
   int* m_ref = db.m_ref + (size_t)b * dc.cap;
@@ -244,12 +250,15 @@ __global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db) {
       // StereoVisionImuFrontend.cpp:345-346, :402-404
       s.mono_status = dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED;
       s.stereo_status = dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED;
+      if (cond) cudaGraphSetConditional(cond, 1);
     }
   }
 }
 
-__global__ void __launch_bounds__(256) detect_pre_kernel(DevCfg dc, DevBuf db, int mode_mask) {
+// kf_counter (may be null): counts executions of the conditional keyframe part (launch accounting)
+__global__ void __launch_bounds__(256) detect_pre_kernel(DevCfg dc, DevBuf db, int mode_mask, int* kf_counter) {
   const int b = blockIdx.x;
+  if (kf_counter && b == 0 && threadIdx.x == 0) atomicAdd(kf_counter, 1);
   StreamState& s = db.st[b];
   if (!mode_on(s.mode, mode_mask)) return;
   const int fk = b * 3 + s.slot_k;
@@ -376,12 +385,12 @@ int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam,
   track_post_kernel<<<dc.B, 256, 0, s>>>(dc, db, d_cam);
   return 1;
 }
-int launch_decide(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
-  decide_kernel<<<dc.B, 256, 0, s>>>(dc, db);
+int launch_decide(const DevCfg& dc, const DevBuf& db, unsigned long long cond, cudaStream_t s) {
+  decide_kernel<<<dc.B, 256, 0, s>>>(dc, db, (cudaGraphConditionalHandle)cond);
   return 1;
 }
-int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s) {
-  detect_pre_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask);
+int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, int* kf_counter, cudaStream_t s) {
+  detect_pre_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask, kf_counter);
   return 1;
 }
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {

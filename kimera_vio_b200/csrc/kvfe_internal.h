@@ -100,6 +100,7 @@ struct DevCfg {          // passed by value to kernels
 struct DevBuf {
   unsigned char* pyr[2];       // B * pyr_stride each
   unsigned char* right_raw;    // B * img_stride
+  uint2* rmap[2];              // per camera W*H: {ix | iy << 16 (int16 each), fx | fy << 5}
   unsigned char* rectL;        // B * img_stride
   unsigned char* rectR;
   unsigned char* mask;         // B * img_stride (u8 0/255)
@@ -160,17 +161,19 @@ struct kvfe_ctx {
   cudaEvent_t in_ev[KVFE_IN_SLOTS]; int in_used[KVFE_IN_SLOTS]; int in_slot;
   cudaGraphExec_t step_graph[2];   // captured kernel sequence of one step, per pyramid slot
   int graph_ready[2];
-  int use_graph;
-  long long graph_launches;
+  int use_graph, use_cond;
+  long long graph_launches, graph_launches_kf;   // per step: always / inside the IF body
+  int* d_kf_steps;             // device counter: executions of the IF body
   int* circle_hw;              // device: half widths of the filled-circle raster rows (2r+1)
   int circle_r;
 };
 
 // ---- launchers (each returns the number of kernels it launched) ------------------------------
 // rectify.cu
-int launch_rectify(const DevCfg& dc, const CamModel* d_cam, int cam, const unsigned char* src,
-                   size_t src_stride, unsigned char* dst, size_t dst_stride, int nimg,
-                   const StreamState* st, int mode_mask, cudaStream_t s);
+int launch_rectify(const DevCfg& dc, const uint2* rmap, const unsigned char* src, size_t src_stride,
+                   unsigned char* dst, size_t dst_stride, int nimg, const StreamState* st, int mode_mask,
+                   cudaStream_t s);
+int launch_rmap_table(const DevCfg& dc, const CamModel* d_cam, int cam, uint2* rmap, cudaStream_t s);
 int launch_maps(const DevCfg& dc, const CamModel* d_cam, int cam, float* mx, float* my, cudaStream_t s);
 // pyramid.cu
 int launch_pyramid(const DevCfg& dc, unsigned char* pyr, int nimg, cudaStream_t s);
@@ -208,7 +211,7 @@ int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const
                 const double* Rin, cudaStream_t s);
 int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, cudaStream_t s);
-int launch_decide(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
-int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s);
+int launch_decide(const DevCfg& dc, const DevBuf& db, unsigned long long cond, cudaStream_t s);
+int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, int* kf_counter, cudaStream_t s);
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s);

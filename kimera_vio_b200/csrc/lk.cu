@@ -270,23 +270,23 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
     int iw10 = cv_round((1.f - a) * bb * (1 << 14));
     int iw11 = (1 << 14) - iw00 - iw01 - iw10;
     __syncwarp();
-    // ---- window of I, Ix, Iy streamed over the (WIN+3) patch rows; structure tensor chains on the fly
+    // ---- window of I, Ix, Iy streamed over the (WIN+3) patch rows; structure tensor products on the fly
     {
       const int colx = reflect101(ipx - 1 + min(lane, PW - 1), cols);
       const bool xin = (ipx + lane) >= 0 && (ipx + lane) < cols;
-      int L0 = 0, C0 = 0, R0 = 0, L1 = 0, C1 = 0, R1 = 0;
+      int C0 = 0, R0 = 0, C1 = 0, R1 = 0;
+      int h0 = 0, h1 = 0, s0 = 0, s1 = 0;          // per row: horizontal difference R - L and smoothing 3L + 10C + 3R
       int dxp = 0, dyp = 0, dxpn = 0, dypn = 0;
-      int Lnext = I[(size_t)reflect101(ipy - 1, rows) * pitch + colx];
-#pragma unroll 3
-      for (int r = 0; r < PW; ++r) {
-        const int L2 = Lnext;
-        if (r + 1 < PW) Lnext = I[(size_t)reflect101(ipy + r, rows) * pitch + colx];   // prefetch next row
+      // one patch row: L2 = pixel of image row (ipy - 1 + r) at this lane's column
+      auto patch_row = [&](const int r, const int L2) {
         const int C2 = __shfl_down_sync(KVFE_FULL_MASK, L2, 1);
         const int R2 = __shfl_down_sync(KVFE_FULL_MASK, L2, 2);
+        const int h2 = R2 - L2, s2 = 3 * (L2 + R2) + 10 * C2;
         if (r >= 2) {
           const int d = r - 2;
-          int dx = 3 * (R0 - L0) + 10 * (R1 - L1) + 3 * (R2 - L2);
-          int dy = 3 * (L2 - L0) + 10 * (C2 - C0) + 3 * (R2 - R0);
+          // Scharr: dx = [3 10 3]^T (rows) x [-1 0 1] (cols), dy = [-1 0 1]^T x [3 10 3]
+          int dx = 3 * (h0 + h2) + 10 * h1;
+          int dy = s2 - s0;
           const bool yin = (ipy + d) >= 0 && (ipy + d) < rows;
           if (!(xin && yin)) { dx = 0; dy = 0; }
           const int dxn = __shfl_down_sync(KVFE_FULL_MASK, dx, 1);
@@ -304,7 +304,28 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
           }
           dxp = dx; dyp = dy; dxpn = dxn; dypn = dyn;
         }
-        L0 = L1; C0 = C1; R0 = R1; L1 = L2; C1 = C2; R1 = R2;
+        h0 = h1; h1 = h2; s0 = s1; s1 = s2;
+        C0 = C1; R0 = R1; C1 = C2; R1 = R2;
+      };
+      if (ipy - 1 >= 0 && ipy - 1 + PW <= rows) {
+        // all patch rows inside the image: running 32-bit offset, no reflection
+        unsigned int o = (unsigned int)(ipy - 1) * (unsigned int)pitch + (unsigned int)colx;
+        int Lnext = I[o];
+#pragma unroll 3
+        for (int r = 0; r < PW; ++r) {
+          const int L2 = Lnext;
+          o += (unsigned int)pitch;
+          if (r + 1 < PW) Lnext = I[o];                                                 // prefetch next row
+          patch_row(r, L2);
+        }
+      } else {
+        int Lnext = I[(size_t)reflect101(ipy - 1, rows) * pitch + colx];
+#pragma unroll 3
+        for (int r = 0; r < PW; ++r) {
+          const int L2 = Lnext;
+          if (r + 1 < PW) Lnext = I[(size_t)reflect101(ipy + r, rows) * pitch + colx];   // prefetch next row
+          patch_row(r, L2);
+        }
       }
     }
     __syncwarp();
@@ -346,20 +367,11 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
       iw11 = (1 << 14) - iw00 - iw01 - iw10;
       const int colx = reflect101(iqx + min(lane, TW - 1), cols);
       const bool inner = iqy >= 0 && iqy + TW <= rows;
-      const unsigned char* jp = Jimg + (size_t)max(iqy, 0) * pitch + colx;
       float bacc = 0.f;                            // lanes 0..3: b1 chains, lanes 4..7: b2 chains
       const int m8 = lane & 7;
-      // chunks of LKC_CHUNK window rows: the chunk's J rows are loaded first, then consumed
-      int jprev = inner ? jp[0] : Jimg[(size_t)reflect101(iqy, rows) * pitch + colx];
-      int jprevR = __shfl_down_sync(KVFE_FULL_MASK, jprev, 1);
-#pragma unroll 1
-      for (int y0 = 0; y0 < WIN; y0 += LKC_CHUNK) {
-        int Jr[LKC_CHUNK];
-#pragma unroll
-        for (int u = 0; u < LKC_CHUNK; ++u) {
-          const int r = y0 + u + 1;
-          Jr[u] = inner ? jp[(size_t)r * pitch] : Jimg[(size_t)reflect101(iqy + r, rows) * pitch + colx];
-        }
+      int jprev, jprevR;
+      // LKC_CHUNK window rows whose J pixels (rows y0+1 .. y0+LKC_CHUNK of the patch) were loaded together
+      auto consume = [&](const int (&Jr)[LKC_CHUNK], const int y0) {
 #pragma unroll
         for (int u = 0; u < LKC_CHUNK; ++u) {
           const int y = y0 + u;
@@ -375,6 +387,30 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
           const float g = (float)((lane & 4) ? s2 : s1);
 #pragma unroll
           for (int q = 0; q < WIN / 8; ++q) bacc = bacc + __shfl_sync(KVFE_FULL_MASK, g, m8 + 8 * q);
+        }
+      };
+      if (inner) {
+        // patch rows inside the image: running 32-bit offset from the (warp-uniform) level base
+        unsigned int o = (unsigned int)iqy * (unsigned int)pitch + (unsigned int)colx;
+        jprev = Jimg[o];
+        jprevR = __shfl_down_sync(KVFE_FULL_MASK, jprev, 1);
+#pragma unroll 1
+        for (int y0 = 0; y0 < WIN; y0 += LKC_CHUNK) {
+          int Jr[LKC_CHUNK];
+#pragma unroll
+          for (int u = 0; u < LKC_CHUNK; ++u) { o += (unsigned int)pitch; Jr[u] = Jimg[o]; }
+          consume(Jr, y0);
+        }
+      } else {
+        jprev = Jimg[(size_t)reflect101(iqy, rows) * pitch + colx];
+        jprevR = __shfl_down_sync(KVFE_FULL_MASK, jprev, 1);
+#pragma unroll 1
+        for (int y0 = 0; y0 < WIN; y0 += LKC_CHUNK) {
+          int Jr[LKC_CHUNK];
+#pragma unroll
+          for (int u = 0; u < LKC_CHUNK; ++u)
+            Jr[u] = Jimg[(size_t)reflect101(iqy + y0 + u + 1, rows) * pitch + colx];
+          consume(Jr, y0);
         }
       }
       float b1, b2;

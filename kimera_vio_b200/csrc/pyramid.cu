@@ -2,64 +2,45 @@
 // -> cv::buildOpticalFlowPyramid): level l+1 = cv::pyrDown(level l): separable [1 4 6 4 1] at even
 // pixels, BORDER_REFLECT_101, (sum + 128) >> 8, size ((w+1)/2, (h+1)/2).  Exact integer arithmetic.
 //
-// Two launches per batch: (1) level 0 -> 1, tiled over the whole batch (the only level with real
-// HBM traffic: reads W*H, writes W*H/4); (2) levels 1 -> 2 -> ... -> L inside ONE CTA per image
-// (<= 90 KB of pixels, L2/L1 resident, __syncthreads between levels).
+// One launch per level, tiled over the whole batch: thread (x, 8 output rows) marches down the
+// source rows keeping the last five horizontal [1 4 6 4 1] row sums in registers (each source row is
+// filtered once per output column: 2 x 5 loads + 5 multiply-adds per output instead of 25 + 25).
+// Level 0 -> 1 is the only level with real HBM traffic (reads W*H, writes W*H/4).
 #include "common.cuh"
 
-__device__ __forceinline__ int pyr_px(const unsigned char* __restrict__ src, int sp, int sw, int sh, int x,
-                                      int y) {
-  // vertical then horizontal is arithmetically identical to OpenCV's horizontal-then-vertical
-  // (all integer, no intermediate rounding).
-  int acc = 0;
-  const int wgt[5] = {1, 4, 6, 4, 1};
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    int yy = reflect101(2 * y + j - 2, sh);
-    const unsigned char* r = src + (size_t)yy * sp;
-    int rowacc = 0;
-#pragma unroll
-    for (int i = 0; i < 5; ++i) rowacc += wgt[i] * r[reflect101(2 * x + i - 2, sw)];
-    acc += wgt[j] * rowacc;
-  }
-  return (acc + 128) >> 8;
-}
-
-__global__ void __launch_bounds__(256) pyr_level1_kernel(DevCfg dc, unsigned char* __restrict__ pyr) {
+#define PYR_ROWS 8
+// grid (ceil(w/128), ceil(h/PYR_ROWS), nimg), block 128
+__global__ void __launch_bounds__(128) pyr_level_kernel(DevCfg dc, unsigned char* __restrict__ pyr, int level) {
   unsigned char* base = pyr + (size_t)blockIdx.z * dc.pyr_stride;
-  const unsigned char* src = base + dc.lvl_off[0];
-  unsigned char* dst = base + dc.lvl_off[1];
-  int x = blockIdx.x * 32 + (threadIdx.x & 31), y = blockIdx.y * 8 + (threadIdx.x >> 5);
-  if (x >= dc.lvl_w[1] || y >= dc.lvl_h[1]) return;
-  dst[(size_t)y * dc.lvl_pitch[1] + x] =
-      (unsigned char)pyr_px(src, dc.lvl_pitch[0], dc.lvl_w[0], dc.lvl_h[0], x, y);
-}
-
-__global__ void __launch_bounds__(1024) pyr_upper_kernel(DevCfg dc, unsigned char* __restrict__ pyr) {
-  unsigned char* base = pyr + (size_t)blockIdx.x * dc.pyr_stride;
-  for (int l = 2; l < dc.n_levels; ++l) {
-    const unsigned char* src = base + dc.lvl_off[l - 1];
-    unsigned char* dst = base + dc.lvl_off[l];
-    int w = dc.lvl_w[l], h = dc.lvl_h[l];
-    for (int i = threadIdx.x; i < w * h; i += blockDim.x) {
-      int y = i / w, x = i - y * w;
-      dst[(size_t)y * dc.lvl_pitch[l] + x] =
-          (unsigned char)pyr_px(src, dc.lvl_pitch[l - 1], dc.lvl_w[l - 1], dc.lvl_h[l - 1], x, y);
-    }
-    __threadfence_block();
-    __syncthreads();
+  const unsigned char* __restrict__ src = base + dc.lvl_off[level - 1];
+  unsigned char* __restrict__ dst = base + dc.lvl_off[level];
+  const int sw = dc.lvl_w[level - 1], sh = dc.lvl_h[level - 1], sp = dc.lvl_pitch[level - 1];
+  const int w = dc.lvl_w[level], h = dc.lvl_h[level], dp = dc.lvl_pitch[level];
+  const int x = blockIdx.x * 128 + threadIdx.x, y0 = blockIdx.y * PYR_ROWS;
+  if (x >= w) return;
+  const int c0 = reflect101(2 * x - 2, sw), c1 = reflect101(2 * x - 1, sw), c2 = 2 * x,
+            c3 = reflect101(2 * x + 1, sw), c4 = reflect101(2 * x + 2, sw);
+  auto hsum = [&](int r) {
+    const unsigned char* p = src + (size_t)reflect101(r, sh) * sp;
+    return (int)p[c0] + 4 * (int)p[c1] + 6 * (int)p[c2] + 4 * (int)p[c3] + (int)p[c4];
+  };
+  // vertical then horizontal order is irrelevant: all integer, no intermediate rounding
+  int a = hsum(2 * y0 - 2), b = hsum(2 * y0 - 1), c = hsum(2 * y0);
+#pragma unroll
+  for (int u = 0; u < PYR_ROWS; ++u) {
+    const int y = y0 + u;
+    if (y >= h) break;
+    const int d = hsum(2 * y + 1), e = hsum(2 * y + 2);
+    dst[(size_t)y * dp + x] = (unsigned char)((a + 4 * b + 6 * c + 4 * d + e + 128) >> 8);
+    a = c; b = d; c = e;
   }
 }
 
 int launch_pyramid(const DevCfg& dc, unsigned char* pyr, int nimg, cudaStream_t s) {
   int n = 0;
-  if (dc.n_levels > 1) {
-    dim3 grid((dc.lvl_w[1] + 31) / 32, (dc.lvl_h[1] + 7) / 8, nimg);
-    pyr_level1_kernel<<<grid, 256, 0, s>>>(dc, pyr);
-    ++n;
-  }
-  if (dc.n_levels > 2) {
-    pyr_upper_kernel<<<nimg, 1024, 0, s>>>(dc, pyr);
+  for (int l = 1; l < dc.n_levels; ++l) {
+    dim3 grid((dc.lvl_w[l] + 127) / 128, (dc.lvl_h[l] + PYR_ROWS - 1) / PYR_ROWS, nimg);
+    pyr_level_kernel<<<grid, 128, 0, s>>>(dc, pyr, l);
     ++n;
   }
   return n;

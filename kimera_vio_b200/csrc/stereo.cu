@@ -39,10 +39,42 @@ __global__ void __launch_bounds__(128) left_rect_kernel(DevCfg dc, DevBuf db, co
 }
 
 #define MATCH_THREADS 128
+#define MATCH_TP 8          // zero bytes in front of every template row (shifted reads start at -7)
 
-// grid (cap, B); dynamic smem: templ (tc*tr) + stripe (sc*sr) bytes + scores (sc - tc + 1) ints
+// s32 += u8 x u8, 16x8x32 (legacy warp-level tensor-core path; exact integer arithmetic)
+__device__ __forceinline__ void mma_u8(int (&d)[4], unsigned a0, unsigned a1, unsigned a2, unsigned a3, unsigned b0,
+                                       unsigned b1) {
+  asm volatile("mma.sync.aligned.m16n8k32.row.col.s32.u8.u8.s32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};\n"
+               : "+r"(d[0]), "+r"(d[1]), "+r"(d[2]), "+r"(d[3])
+               : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
+}
+
+// geometry of the shared-memory tiles, shared by the kernel and the launcher
+struct MatchGeom { int nq, mt, tstride, sstride, npos_x, npos_y; size_t off_stripe, off_score, off_pref, bytes; };
+__host__ __device__ inline MatchGeom match_geom(int tc, int tr, int sc, int sr) {
+  MatchGeom g;
+  g.npos_x = sc - tc + 1; g.npos_y = sr - tr + 1;
+  g.nq = (tc + 7 + 31) / 32;                        // 32-byte K chunks per template row (c' = j + c < tc + 7)
+  g.mt = ((g.npos_x + 7) / 8 + 15) / 16;            // 16-row M tiles; row i covers shifts 8i .. 8i+7
+  g.tstride = MATCH_TP + 32 * g.nq + 4;
+  g.sstride = 128 * g.mt + 32 * g.nq;
+  g.off_stripe = ((size_t)g.tstride * tr + 15) & ~(size_t)15;
+  g.off_score = g.off_stripe + (((size_t)g.sstride * sr + 15) & ~(size_t)15);
+  g.off_pref = g.off_score + sizeof(int) * (size_t)g.npos_x * g.npos_y;
+  g.bytes = g.off_pref + sizeof(int) * (size_t)(sc + 1);
+  return g;
+}
+
+// grid (cap, B).  TM_SQDIFF(p) = sum S^2 - 2 sum S*T + sum T^2 in exact integers:
+//  * sum S*T for all shifts of one stripe row band is a GEMM: with p = 8 i + j,
+//      corr[8i + j] = sum_r sum_c' S[r][8i + c'] * T[r][c' - j]        (c' = j + c)
+//    A[i][(r, c')] = stripe bytes (16 x 32 fragments are plain aligned words of the staged stripe),
+//    B[(r, c')][j] = the template shifted right by j (funnel-shifted words of the zero-padded
+//    template), D = 16 x 8 int32 -> mma.sync m16n8k32 u8.  Warp w takes template rows r = w mod 4
+//    for all M tiles; the partial sums meet in shared memory (integer adds, order-free).
+//  * sum S^2 per shift = difference of a prefix sum over squared column sums.
 __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf db, int mode_mask, int reuse_tracked) {
-  extern __shared__ unsigned char smraw[];
+  extern __shared__ __align__(16) unsigned char smraw[];
   const int b = blockIdx.y;
   const StreamState& s = db.st[b];
   if (!mode_on(s.mode, mode_mask)) return;
@@ -83,53 +115,120 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf 
   if (scx < 0) scx = 0;
   // cv::Rect of the template / stripe must lie inside the image (OpenCV would assert otherwise)
   tcx = clampi(tcx, 0, max(W - tc, 0));
-  // shared memory: template rows padded to a multiple of 4 bytes (zero pad), stripe rows padded so
-  // that every shifted 4-byte window can be assembled from two aligned words, then the scores.
-  const int tstride = (tc + 3) & ~3;
-  const int sstride = ((sc + 3) & ~3) + 8;
+  const MatchGeom g = match_geom(tc, tr, sc, sr);
+  const int tstride = g.tstride, sstride = g.sstride;
   unsigned char* templ = smraw;
-  unsigned char* stripe = smraw + ((tstride * tr + 15) & ~15);
-  int* score = reinterpret_cast<int*>(stripe + ((sstride * sr + 15) & ~15));
+  unsigned char* stripe = smraw + g.off_stripe;
+  int* score = reinterpret_cast<int*>(smraw + g.off_score);          // sum S*T, then the SQDIFF
+  unsigned int* pref = reinterpret_cast<unsigned int*>(smraw + g.off_pref);
+  __shared__ unsigned int red[MATCH_THREADS / 32];
   const unsigned char* L = db.rectL + (size_t)b * dc.img_stride;
   const unsigned char* R = db.rectR + (size_t)b * dc.img_stride;
-  for (int t = threadIdx.x; t < tstride * tr; t += blockDim.x) {
-    int r = t / tstride, c = t - r * tstride;
-    templ[t] = (c < tc) ? L[(size_t)(tcy + r) * dc.pitch + tcx + c] : 0;
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  // ---- stage the template (zero padded on both sides) and the stripe (aligned words, zero tail)
+  for (int t = tid; t < tstride * tr; t += MATCH_THREADS) {
+    const int r = t / tstride, c = t - r * tstride - MATCH_TP;
+    templ[t] = (c >= 0 && c < tc) ? L[(size_t)(tcy + r) * dc.pitch + tcx + c] : 0;
   }
-  for (int t = threadIdx.x; t < sstride * sr; t += blockDim.x) {
-    int r = t / sstride, c = t - r * sstride;
-    stripe[t] = (c < sc) ? R[(size_t)(scy + r) * dc.pitch + scx + c] : 0;
+  {
+    const int wpr = sstride >> 2;
+    const float inv_wpr = 1.0f / (float)wpr;
+    for (int t = tid; t < wpr * sr; t += MATCH_THREADS) {
+      const int r = (int)(((float)t + 0.5f) * inv_wpr), w = t - r * wpr;
+      unsigned int v = 0;
+      const int c0 = 4 * w;
+      if (c0 < sc) {
+        const unsigned char* src = R + (size_t)(scy + r) * dc.pitch + scx + c0;
+        const size_t a = reinterpret_cast<size_t>(src);
+        const unsigned int* wp = reinterpret_cast<const unsigned int*>(a & ~(size_t)3);
+        const int sh = 8 * (int)(a & 3);
+        const unsigned int lo = wp[0], hi = sh ? wp[1] : 0u;
+        v = __funnelshift_r(lo, hi, sh);
+        if (c0 + 4 > sc) v &= 0xffffffffu >> (8 * (c0 + 4 - sc));
+      }
+      reinterpret_cast<unsigned int*>(stripe)[(size_t)r * wpr + w] = v;
+    }
   }
-  __syncthreads();
-  const int npos_x = sc - tc + 1, npos_y = sr - tr + 1;
+  const int npos_x = g.npos_x, npos_y = g.npos_y;
   const int npos = npos_x * npos_y;
-  const int nwords = tstride >> 2;
-  // byte mask of the last template word (columns >= tc must not contribute to sum S^2)
-  const unsigned int lastmask = (tc & 3) ? (0xffffffffu >> (8 * (4 - (tc & 3)))) : 0xffffffffu;
-  // exact integer TM_SQDIFF = sum S^2 - 2 sum S*T + sum T^2, four pixels per dp4a
+  for (int p = tid; p < npos; p += MATCH_THREADS) score[p] = 0;
+  __syncthreads();
+  // ---- sum T^2
   unsigned int tt = 0;
-  for (int r = 0; r < tr; ++r) {
-    const unsigned int* tw = reinterpret_cast<const unsigned int*>(templ + r * tstride);
-    for (int w = 0; w < nwords; ++w) tt = __dp4a(tw[w], tw[w], tt);
+  for (int t = tid; t < (tstride >> 2) * tr; t += MATCH_THREADS) {
+    const unsigned int v = reinterpret_cast<const unsigned int*>(templ)[t];
+    tt = __dp4a(v, v, tt);
   }
-  for (int p = threadIdx.x; p < npos; p += blockDim.x) {
-    const int py = p / npos_x, px = p - py * npos_x;
-    const int sh = 8 * (px & 3);
-    unsigned int st = 0, ss = 0;
-    for (int r = 0; r < tr; ++r) {
-      const unsigned int* sw = reinterpret_cast<const unsigned int*>(stripe + (py + r) * sstride) + (px >> 2);
-      const unsigned int* tw = reinterpret_cast<const unsigned int*>(templ + r * tstride);
-      unsigned int lo = sw[0];
-      for (int w = 0; w < nwords; ++w) {
-        const unsigned int hi = sw[w + 1];
-        unsigned int v = __funnelshift_r(lo, hi, sh);
-        lo = hi;
-        st = __dp4a(v, tw[w], st);
-        if (w == nwords - 1) v &= lastmask;
-        ss = __dp4a(v, v, ss);
+  for (int o = 16; o > 0; o >>= 1) tt += __shfl_xor_sync(KVFE_FULL_MASK, tt, o);
+  if (lane == 0) red[warp] = tt;
+  // ---- sum S*T on the tensor cores
+  const int gq = lane >> 2, tig = lane & 3;
+  for (int py = 0; py < npos_y; ++py) {
+    for (int mt0 = 0; mt0 < g.mt; mt0 += 4) {
+      int acc[4][4];
+#pragma unroll
+      for (int m = 0; m < 4; ++m) { acc[m][0] = acc[m][1] = acc[m][2] = acc[m][3] = 0; }
+      for (int r = warp; r < tr; r += MATCH_THREADS / 32) {
+        const unsigned int* trow = reinterpret_cast<const unsigned int*>(templ + r * tstride);
+        const unsigned char* srow = stripe + (size_t)(py + r) * sstride;
+        for (int q = 0; q < g.nq; ++q) {
+          // B fragment: template bytes x .. x+3 with x = 32 q + 4 tig - gq (+16), row-padded by MATCH_TP
+          const int o0 = MATCH_TP + 32 * q + 4 * tig - gq;
+          const int sh = 8 * (o0 & 3);
+          const unsigned int b0 = __funnelshift_r(trow[o0 >> 2], trow[(o0 >> 2) + 1], sh);
+          const unsigned int b1 = __funnelshift_r(trow[(o0 >> 2) + 4], trow[(o0 >> 2) + 5], sh);
+#pragma unroll
+          for (int m = 0; m < 4; ++m) {
+            if (mt0 + m < g.mt) {
+              const unsigned int* ap = reinterpret_cast<const unsigned int*>(srow + 128 * (mt0 + m) + 8 * gq + 32 * q) + tig;
+              mma_u8(acc[m], ap[0], ap[16], ap[4], ap[20], b0, b1);
+            }
+          }
+        }
+      }
+#pragma unroll
+      for (int m = 0; m < 4; ++m) {
+        if (mt0 + m < g.mt) {
+          const int p0 = 8 * (16 * (mt0 + m) + gq) + 2 * tig;
+          int* sp = score + py * npos_x;
+          if (p0 < npos_x) atomicAdd(sp + p0, acc[m][0]);
+          if (p0 + 1 < npos_x) atomicAdd(sp + p0 + 1, acc[m][1]);
+          if (p0 + 64 < npos_x) atomicAdd(sp + p0 + 64, acc[m][2]);
+          if (p0 + 65 < npos_x) atomicAdd(sp + p0 + 65, acc[m][3]);
+        }
       }
     }
-    score[p] = (int)(ss + tt - 2u * st);
+  }
+  __syncthreads();
+  tt = 0;
+  for (int w = 0; w < MATCH_THREADS / 32; ++w) tt += red[w];
+  // ---- sum S^2 per shift: prefix over the squared column sums of the row band, then the SQDIFF
+  for (int py = 0; py < npos_y; ++py) {
+    const int ch = (sc + MATCH_THREADS - 1) / MATCH_THREADS;      // consecutive columns per thread
+    const int c0 = tid * ch;
+    unsigned int loc = 0;
+    for (int c = c0; c < min(c0 + ch, sc); ++c) {
+      unsigned int cs = 0;
+      for (int r = 0; r < tr; ++r) { const unsigned int v = stripe[(size_t)(py + r) * sstride + c]; cs += v * v; }
+      pref[c] = cs;                                               // own columns only: no barrier needed
+      loc += cs;
+    }
+    // exclusive block scan of the per-thread sums
+    unsigned int inc = loc;
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int y = __shfl_up_sync(KVFE_FULL_MASK, inc, o); if (lane >= o) inc += y; }
+    __syncthreads();                                              // red free to be rewritten
+    if (lane == 31) red[warp] = inc;
+    __syncthreads();
+    unsigned int base = inc - loc;
+    for (int w = 0; w < warp; ++w) base += red[w];
+    for (int c = c0; c < min(c0 + ch, sc); ++c) { const unsigned int cs = pref[c]; pref[c] = base; base += cs; }
+    if (c0 < sc && c0 + ch >= sc) pref[sc] = base;
+    __syncthreads();
+    for (int px = tid; px < npos_x; px += MATCH_THREADS) {
+      const unsigned int ss = pref[px + tc] - pref[px];
+      const unsigned int st = (unsigned int)score[py * npos_x + px];
+      score[py * npos_x + px] = (int)(ss + tt - 2u * st);
+    }
   }
   __syncthreads();
   // first minimum in row-major order (cv::minMaxLoc)
@@ -228,9 +327,7 @@ int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_c
                          int reuse_tracked, cudaStream_t s) {
   int n = 0;
   left_rect_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); ++n;
-  const int tstride = (dc.templ_cols + 3) & ~3, sstride = ((dc.stripe_cols + 3) & ~3) + 8;
-  size_t sm = ((tstride * dc.templ_rows + 15) & ~15) + ((sstride * dc.stripe_rows + 15) & ~15) +
-              sizeof(int) * (size_t)(dc.stripe_cols - dc.templ_cols + 1) * (dc.stripe_rows - dc.templ_rows + 1);
+  size_t sm = match_geom(dc.templ_cols, dc.templ_rows, dc.stripe_cols, dc.stripe_rows).bytes;
   if (sm < (size_t)SUBPIX_PATCH * 4) sm = (size_t)SUBPIX_PATCH * 4;
   static size_t attr = 0;
   if (sm > 48 * 1024 && sm > attr) {
