@@ -285,46 +285,143 @@ def run_gpu(args):
     clocks = sampler.summary()
 
     # ---------------- end-to-end measurement through host buffers (e2e) ----------------
-    pinL = torch.empty((NC, n_frames, Bc, H, W), dtype=torch.uint8).pin_memory()
+    # host frames: for every frame k the images of all sub-batches are contiguous (group uploads)
+    pinL = torch.empty((n_frames, NC, Bc, H, W), dtype=torch.uint8).pin_memory()
     pinR = torch.empty_like(pinL).pin_memory()
     for c in range(NC):
         for k in range(n_frames):
             for i in range(Bc):
-                pinL[c, k, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
-                pinR[c, k, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
+                pinL[k, c, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
+                pinR[k, c, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
     # two pinned packet buffers per context (a step's buffer is owned by the library until wait returns)
     pk_pin = [[torch.empty(Bc * pkb, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(NC)]
     sub_args = [[(ctxs[c].h,
-                  (C.c_void_p * Bc)(*[pinL[c, k, i].data_ptr() for i in range(Bc)]),
-                  (C.c_void_p * Bc)(*[pinR[c, k, i].data_ptr() for i in range(Bc)]),
+                  (C.c_void_p * Bc)(*[pinL[k, c, i].data_ptr() for i in range(Bc)]),
+                  (C.c_void_p * Bc)(*[pinR[k, c, i].data_ptr() for i in range(Bc)]),
                   C.c_size_t(W), C.c_void_p(ts_c[c][k].ctypes.data), C.c_void_p(R_c[c][k].ctypes.data),
-                  C.c_void_p(pk_pin[c][k & 1].data_ptr())) for k in range(n_frames)] for c in range(NC)]
+                  None) for k in range(n_frames)] for c in range(NC)]     # packets: read in place (packets_view)
     hs = [c.h for c in ctxs]
 
+    # staged uploads: the frames of G consecutive sub-batches travel in one H2D copy per camera, issued one
+    # step ahead (kvfe_upload_frames); G = 1 falls back to per-context image copies (kvfe_frontend_submit)
+    G = max(1, min(args.upload_group, NC))
+    ugroups = [list(range(g, min(g + G, NC))) for g in range(0, NC, G)]
+    HT = max(1, min(args.host_threads, len(ugroups)))
+    uploads, up_args, subu_args = [], [], {}
+    if G > 1:
+        for cs in ugroups:
+            up = C.c_void_p()
+            rc = lib.kvfe_upload_create((C.c_void_p * len(cs))(*[ctxs[c].h.value for c in cs]), C.c_int(len(cs)), C.byref(up))
+            assert rc == 0, lib.kvfe_last_error(hs[cs[0]])
+            uploads.append(up)
+            up_args.append([(up, C.c_void_p(pinL[k, cs[0]].data_ptr()), C.c_void_p(pinR[k, cs[0]].data_ptr()), C.c_size_t(W))
+                            for k in range(n_frames)])
+            for m, c in enumerate(cs):
+                subu_args[c] = [(hs[c], up, C.c_int(m), C.c_void_p(ts_c[c][k].ctypes.data),
+                                 C.c_void_p(R_c[c][k].ctypes.data), None) for k in range(n_frames)]
+
+    host_prof = [0.0, 0.0, 0.0, 0]          # [unused, unused, seconds inside submit, number of polls] (diagnostic)
+
+    def run_host_thread(gis, k0, k1):
+        # one dispatcher thread serving its contexts in COMPLETION order: poll (kvfe_frontend_ready), collect the
+        # finished step (kvfe_frontend_wait, packets read in place), submit the context's next frame at once.  A
+        # context never has more than one step in flight -- the IMU rotation of frame k depends on frame k-1's
+        # keyframe decision -- but contexts advance independently (a keyframe step takes ~3x a tracking step), and
+        # with staged uploads (G > 1) the frames of a group travel one step ahead in one H2D copy per camera.
+        cs_all = [c for gi in gis for c in ugroups[gi]]
+        nxt = {c: k0 for c in cs_all}
+        busy = {c: 0 for c in cs_all}
+        depth = 1
+        up_next = {gi: k0 for gi in gis}
+        remaining = len(cs_all) * (k1 - k0)
+        ready, wait, submit, submit_u, upload = (lib.kvfe_frontend_ready, lib.kvfe_frontend_wait, lib.kvfe_frontend_submit,
+                                                 lib.kvfe_frontend_submit_uploaded, lib.kvfe_upload_frames)
+        prof = host_prof
+        while remaining:
+            for gi in gis:
+                cs = ugroups[gi]
+                if G > 1:
+                    # keep the upload ring one step ahead of the slowest member of the group
+                    lo = min(nxt[c] for c in cs)
+                    while up_next[gi] < k1 and up_next[gi] <= lo + 1:
+                        rc = upload(*up_args[gi][up_next[gi]])
+                        assert rc == 0, lib.kvfe_last_error(hs[cs[0]])
+                        up_next[gi] += 1
+                for c in cs:
+                    if busy[c]:
+                        prof[3] += 1
+                        if ready(hs[c]) == 1:
+                            rc = wait(hs[c])
+                            assert rc == 0
+                            busy[c] -= 1
+                            remaining -= 1
+                    k = nxt[c]
+                    if busy[c] < depth and k < k1 and (G == 1 or k < up_next[gi]):
+                        t_a = time.perf_counter()
+                        rc = submit_u(*subu_args[c][k]) if G > 1 else submit(*sub_args[c][k])
+                        prof[2] += time.perf_counter() - t_a
+                        assert rc == 0, lib.kvfe_last_error(hs[c])
+                        nxt[c] = k + 1
+                        busy[c] += 1
+
     def run_host(k0, k1):
-        # one host thread, round-robin over the sub-batches: collect frame k-1 of a context, then submit its
-        # frame k at once (H2D + kernels + packet D2H enqueued on its stream).  A context never has more than
-        # one step in flight -- the IMU rotation of frame k depends on frame k-1's keyframe decision -- but
-        # the other contexts keep the PCIe link and the SMs busy meanwhile (kvfe_frontend_submit/wait).
-        for k in range(k0, k1):
-            for c in range(NC):
-                if k > k0:
-                    rc = lib.kvfe_frontend_wait(hs[c])
-                    assert rc == 0
-                rc = lib.kvfe_frontend_submit(*sub_args[c][k])
-                assert rc == 0, lib.kvfe_last_error(hs[c])
-        for c in range(NC):
-            rc = lib.kvfe_frontend_wait(hs[c])
-            assert rc == 0
+        parts = [list(range(len(ugroups)))[t::HT] for t in range(HT)]
+        if HT == 1:
+            return run_host_thread(parts[0], k0, k1)
+        th = [threading.Thread(target=run_host_thread, args=(g, k0, k1)) for g in parts]
+        for t in th:
+            t.start()
+        for t in th:
+            t.join()
 
     for ctx in ctxs:
         ctx.reset()
     run_host(0, Wm)
     barrier()
+    host_prof[:] = [0.0, 0.0, 0.0, 0]
     t0 = time.perf_counter()
     run_host(Wm, n_frames)
     barrier()
     e2e_s = time.perf_counter() - t0
+    print("[e2e host profile] total %.3f s, %d polls, %.3f s inside submit calls" % (e2e_s, host_prof[3], host_prof[2]), file=sys.stderr)
+    for up in uploads:
+        lib.kvfe_upload_destroy(up)
+
+    # ---------------- host link rate (what bounds e2e) and single-stream latency ----------------
+    link, latency = None, None
+    if rank == 0:
+        # pinned -> device copy of one step's input volume on one stream, CUDA events
+        nb = 2 * B * W * H                                   # one step's H2D volume, contiguous
+        hbuf, dbuf = pinL.reshape(-1)[:nb], dL.reshape(-1)[:nb]
+        c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dbuf.copy_(hbuf, non_blocking=True)
+        torch.cuda.synchronize()
+        c0.record()
+        for _ in range(8):
+            dbuf.copy_(hbuf, non_blocking=True)
+        c1.record()
+        torch.cuda.synchronize()
+        link = {"h2d_gbs_measured": 8 * hbuf.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9,
+                "copy_bytes": int(hbuf.numel())}
+        # one stream alone on the GPU (batch 1, one context): per-frame latency of the host-buffer call
+        one = kl.Context(kl.make_config(p, W, H, batch=1), rig.to_c())
+        pk1 = np.empty(pkb, np.uint8)
+        lat, lat_kf = [], []
+        for k in range(n_frames):
+            lp = (C.c_void_p * 1)(pinL[k, 0, 0].data_ptr())
+            rp = (C.c_void_p * 1)(pinR[k, 0, 0].data_ptr())
+            t1 = time.perf_counter()
+            rc = one.step_raw(lp, rp, W, ts_c[0][k][:1], R_c[0][k][:1], pk1)
+            dt = (time.perf_counter() - t1) * 1e3
+            assert rc == 0
+            if k >= Wm:
+                (lat_kf if one.parse_packets(pk1)[0]["is_keyframe"] else lat).append(dt)
+        one.close()
+        allv = np.array(lat + lat_kf)
+        latency = {"what": "kvfe_frontend_step, host buffers, batch 1, stream alone on the GPU [ms]",
+                   "p50": float(np.percentile(allv, 50)), "p99": float(np.percentile(allv, 99)),
+                   "non_keyframe_p50": float(np.median(lat)) if lat else None,
+                   "keyframe_p50": float(np.median(lat_kf)) if lat_kf else None, "frames": int(allv.size)}
 
     # ---------------- dominant kernel (LK) launch duration, live CUDA events ----------------
     # one context holding the whole batch; the step is run stage by stage with events on the
@@ -371,7 +468,7 @@ def run_gpu(args):
             "data": "synthetic",
             "config": {"workload": "Euroc stereo 752x480, %d feats, 1xB200 batch=%d frame-pairs per step "
                                    "(BASELINE.json configs[1]); %d independent streams per GPU" % (N_FEATS, B, B),
-                       "batch_per_gpu": B, "sub_batches_in_flight": NC, "keyframe_ratio": rho,
+                       "batch_per_gpu": B, "sub_batches_in_flight": NC, "e2e_dispatcher_threads": HT, "e2e_upload_group": G, "keyframe_ratio": rho,
                        "mean_keypoints": n_kp_mean,
                        "timing": "CUDA events on the library streams, max over ranks; every step reads fresh "
                                  "device-resident inputs (%d MB per rank > L2), no L2 flush" %
@@ -381,12 +478,13 @@ def run_gpu(args):
                     "d2h_bytes_per_step": int(B * pkb)},
             "gpu_launches": int(launches),
             "host_enqueue_ms_per_step": 1e3 * t_enq / K,
+            "host_link": link, "latency_ms": latency,
             "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "lk_kernel_col<24> (pyramidal LK, dominant: ~30% of the step)",
+            "roofline": {"bound": "hbm", "kernel": "lk_kernel_col<24> (pyramidal LK, dominant: 70% of the step's warp instructions, 27% of its serialised kernel time)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": 30961408, "peak_source": which + " (burst copy)",
+                         "frac": achieved / peaks["hbm_gbs"], "traffic": 30850048, "peak_source": which + " (burst copy)",
                          "algorithmic_bytes_per_launch": lk_alg_bytes, "launch_ms": lk_ms,
-                         "traffic_source": "profiles/r01_ncu_lk.txt: dram__bytes_read.sum + write, one launch, batch 32",
+                         "traffic_source": "profiles/r01_ncu_final.txt: dram__bytes_read.sum + dram__bytes_write.sum, one launch, batch 32",
                          "whole_step": {"algorithmic_bytes_per_frame_pair": b_alg, "achieved": step_achieved,
                                         "frac": step_achieved / peaks["hbm_gbs"]},
                          "stage_ms": [float(v) for v in stage_ms],
@@ -407,6 +505,8 @@ def main():
     ap.add_argument("--steps", type=int, default=16)
     ap.add_argument("--warmup", type=int, default=4)
     ap.add_argument("--batch", type=int, default=32)
+    ap.add_argument("--upload-group", type=int, default=8, help="sub-batches that share one H2D copy per camera (e2e loop)")
+    ap.add_argument("--host-threads", type=int, default=1, help="dispatcher threads of the end-to-end (host buffer) loop")
     ap.add_argument("--contexts", type=int, default=32, help="sub-batches in flight on separate CUDA streams")
     ap.add_argument("--impl", default="kvfe", choices=["kvfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -269,13 +269,38 @@ int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_dev, const u
  * SIMOPipelineModule input queue): submit enqueues the H2D
  * copies, the step and the packet D2H copy and returns; wait blocks until the oldest submitted step
  * is done and `packets` (given at submit; owned by the library until wait returns) is filled.  At
- * most two steps may be in flight per context.  A pinned `packets` buffer receives the D2H copy
- * directly.  With several contexts a single host thread keeps the PCIe link and the GPU busy:
- * submit(k+1) on every context, then wait(k) on every context. */
+ * most two steps may be in flight per context.  The step inputs, the kernel sequence and the
+ * packet D2H copy are one CUDA graph over a pinned I/O block owned by the context, so a step costs
+ * the host the image copies, one graph launch and one event record.  `packets` may be NULL: the
+ * packets of the last waited step are then read in place through kvfe_frontend_packets_view()
+ * (valid until the second next submit on this context).  With several contexts one or a few
+ * dispatcher threads keep the host link and the GPU busy: wait(k-1) then submit(k), round-robin. */
 int kvfe_frontend_submit(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right,
                          size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
                          uint8_t* packets);
 int kvfe_frontend_wait(kvfe_ctx* ctx);
+/* 1 when the oldest submitted step is complete (kvfe_frontend_wait will not block), 0 when it is still
+ * running or nothing is in flight, < 0 on error.  Streams are independent and a keyframe step takes
+ * about three times as long as a tracking step, so a dispatcher that serves contexts in COMPLETION order
+ * (poll, collect, resubmit) keeps all of them busy; serving them in a fixed order makes every context
+ * advance at the pace of the slowest one of each round. */
+int kvfe_frontend_ready(kvfe_ctx* ctx);
+const uint8_t* kvfe_frontend_packets_view(const kvfe_ctx* ctx);
+/* Staged uploads.  Copies of a few hundred KB reach well under half of the host link rate, copies of
+ * several MB reach it; and the frames of step k+1 do not depend on the results of step k (only the
+ * IMU rotation does).  A kvfe_upload couples n contexts (same image size and batch) to a two-slot
+ * device staging ring: kvfe_upload_frames enqueues ONE H2D copy per camera for the n * batch
+ * densely packed images of the next step of every member (member 0's batch first) and returns at
+ * once -- it may run one step ahead of the members -- and kvfe_frontend_submit_uploaded is
+ * kvfe_frontend_submit with the images taken from the member's slice of the oldest upload it has
+ * not consumed yet (device-side copy).  Uploads are issued by one thread; every member must
+ * consume upload s before upload s+2 is issued. */
+typedef struct kvfe_upload kvfe_upload;
+int kvfe_upload_create(kvfe_ctx* const* ctxs, int n, kvfe_upload** out);
+void kvfe_upload_destroy(kvfe_upload* u);      /* before the member contexts */
+int kvfe_upload_frames(kvfe_upload* u, const uint8_t* left, const uint8_t* right, size_t pitch);
+int kvfe_frontend_submit_uploaded(kvfe_ctx* ctx, kvfe_upload* u, int member, const int64_t* timestamps,
+                                  const double* keyframe_R_cur, uint8_t* packets);
 /* submit on each of n contexts, then wait on each (one blocking call for n sub-batches). */
 int kvfe_frontend_step_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* const* left,
                              const uint8_t* const* const* right, size_t pitch,

@@ -313,14 +313,18 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CU(dmalloc(&db.packets, B * db.packet_bytes));
   CU(cudaMallocHost((void**)&ctx->h_stage, 2 * B * dc.img_stride));
   CU(cudaMallocHost((void**)&ctx->h_packets, B * db.packet_bytes));
+  ctx->io_pk_off = (B * (sizeof(long long) + 9 * sizeof(double)) + 255) & ~(size_t)255;
   for (int i = 0; i < 2; ++i) {
-    CU(cudaMallocHost((void**)&ctx->h_pipe[i], B * db.packet_bytes));
+    CU(cudaMallocHost((void**)&ctx->h_io[i], ctx->io_pk_off + B * db.packet_bytes));
     CU(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
   }
   CU(cudaMallocHost((void**)&ctx->h_ts, KVFE_IN_SLOTS * B * sizeof(long long)));
   CU(cudaMallocHost((void**)&ctx->h_Rin, KVFE_IN_SLOTS * B * 9 * sizeof(double)));
   for (int i = 0; i < KVFE_IN_SLOTS; ++i) CU(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
-  CU(dmalloc(&ctx->d_ts, B)); CU(dmalloc(&ctx->d_Rin, B * 9));
+  ctx->in_bytes = B * (sizeof(long long) + 9 * sizeof(double));
+  CU(dmalloc(&ctx->d_in, ctx->in_bytes));
+  ctx->d_ts = reinterpret_cast<long long*>(ctx->d_in);
+  ctx->d_Rin = reinterpret_cast<double*>(ctx->d_in + B * sizeof(long long));
   ctx->launches += launch_reset(dc, db, ctx->stream);
   CU(cudaStreamSynchronize(ctx->stream));
   ctx->cur_slot = 0;
@@ -347,15 +351,16 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
                   db.m_cur, db.m_n, db.inl, db.inl_n, db.rs_d, db.fr.n, db.fr.timestamp, db.fr.frame_id, db.fr.kx,
                   db.fr.ky, db.fr.lmk, db.fr.age, db.fr.versor, db.fr.lstat, db.fr.lrx, db.fr.lry, db.fr.rstat, db.fr.mstat,
-                  db.fr.rrx, db.fr.rry, db.fr.depth, db.fr.p3d, db.fr.rkx, db.fr.rky, db.st, db.packets, ctx->d_ts,
-                  ctx->d_Rin};
+                  db.fr.rrx, db.fr.rry, db.fr.depth, db.fr.p3d, db.fr.rkx, db.fr.rky, db.st, db.packets, ctx->d_in};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
   for (int i = 0; i < 2; ++i) {
-    if (ctx->h_pipe[i]) cudaFreeHost(ctx->h_pipe[i]);
+    if (ctx->h_io[i]) cudaFreeHost(ctx->h_io[i]);
+    if (ctx->host_graph_ready[i]) cudaGraphExecDestroy(ctx->host_graph[i]);
     if (ctx->pipe_done[i]) cudaEventDestroy(ctx->pipe_done[i]);
   }
+
   if (ctx->h_ts) cudaFreeHost(ctx->h_ts);
   if (ctx->h_Rin) cudaFreeHost(ctx->h_Rin);
   for (int i = 0; i < KVFE_IN_SLOTS; ++i) if (ctx->in_ev[i]) cudaEventDestroy(ctx->in_ev[i]);
@@ -791,7 +796,7 @@ static int enqueue_part_track(kvfe_ctx* ctx, unsigned long long cond, long long*
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const int cur = ctx->cur_slot, prev = cur ^ 1;
   long long n = 0;
-  n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, s);
+  n += launch_prep(dc, db, ctx->d_cam, ctx->in_ts ? ctx->in_ts : ctx->d_ts, ctx->in_R ? ctx->in_R : ctx->d_Rin, s);
   n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
   n += launch_track_pre(dc, db, s);
   n += launch_lk(dc, db, prev, cur, s);
@@ -964,10 +969,11 @@ extern "C" int kvfe_frontend_step_dev(kvfe_ctx* ctx, const uint8_t* left_dev, co
   // device-to-device placement into the pyramid slot / right buffer (strided destination)
   if (pitch == (size_t)dc.W && dc.pitch == dc.W) {
     // densely packed images: one strided copy per camera for the whole batch (row = one image)
+    // (an SM copy kernel, not two copy-engine operations: those share in-order queues across contexts)
     const size_t img = (size_t)dc.W * dc.H;
-    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, left_dev, img, img, B,
-                         cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpy2DAsync(db.right_raw, dc.img_stride, right_dev, img, img, B, cudaMemcpyDeviceToDevice, s));
+    ctx->launches += launch_fetch(left_dev, right_dev, db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, db.right_raw,
+                                  dc.img_stride, img, (int)B, s);
+    CU(cudaGetLastError());
   } else {
     for (size_t b = 0; b < B; ++b) {
       RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,
@@ -1000,34 +1006,180 @@ static int upload_batch(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t
   return KVFE_OK;
 }
 
-extern "C" int kvfe_frontend_submit(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right, size_t pitch,
-                                    const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets) {
-  if (!ctx || !left || !right || !timestamps || !keyframe_R_cur || !packets) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
-  if (ctx->n_submitted - ctx->n_waited >= 2) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit: two steps already in flight, call kvfe_frontend_wait first");
-  const int slot = (int)(ctx->n_submitted & 1);
-  const size_t bytes = (size_t)ctx->dc.B * ctx->db.packet_bytes;
-  RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
-  RET(upload_batch(ctx, left, right, pitch));
-  RET(enqueue_step(ctx));
-  // pinned (cudaHostAlloc / cudaHostRegister) output buffers receive the packets directly
-  cudaPointerAttributes at{};
-  const bool direct = cudaPointerGetAttributes(&at, packets) == cudaSuccess && at.type == cudaMemoryTypeHost;
-  cudaGetLastError();
-  CU(cudaMemcpyAsync(direct ? packets : ctx->h_pipe[slot], ctx->db.packets, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaEventRecord(ctx->pipe_done[slot], ctx->stream));
-  ctx->pipe_user[slot] = packets; ctx->pipe_direct[slot] = direct;
+// Common tail of a submit (the caller has already enqueued the image copies on ctx->stream): write the
+// step inputs into the pinned I/O block of this pyramid slot and launch the host-step graph: the kernel
+// sequence reading its inputs straight from that (mapped) block, then publish_kernel storing the
+// packets into it.  No copy-engine operation is involved besides the image uploads, and a step
+// costs the host one graph launch and one event record.
+static int launch_host_step(kvfe_ctx* ctx, const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets) {
+  const size_t B = ctx->dc.B;
+  const int slot = ctx->cur_slot, ps = (int)(ctx->n_submitted & 1);
+  unsigned char* io = ctx->h_io[slot];
+  memcpy(io, timestamps, B * sizeof(long long));
+  memcpy(io + B * sizeof(long long), keyframe_R_cur, B * 9 * sizeof(double));
+  const size_t pk_bytes = B * ctx->db.packet_bytes;
+  // pinned allocations are mapped into the device address space (unified addressing)
+  ctx->in_ts = reinterpret_cast<const long long*>(io);
+  ctx->in_R = reinterpret_cast<const double*>(io + B * sizeof(long long));
+  int rc = KVFE_OK;
+  if (ctx->use_graph) {
+    if (!ctx->host_graph_ready[slot]) {
+      cudaGraph_t g = nullptr;
+      long long n = 0;
+      cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+      if (e == cudaSuccess) {
+        rc = enqueue_step_kernels(ctx, &n);
+        n += launch_publish(io + ctx->io_pk_off, ctx->db.packets, pk_bytes, ctx->stream);
+        e = cudaStreamEndCapture(ctx->stream, &g);
+      }
+      if (rc == KVFE_OK && e != cudaSuccess) rc = set_err(ctx, KVFE_ERR_CUDA, "host-step graph capture failed: %s", cudaGetErrorString(e));
+      if (rc == KVFE_OK && cudaGraphInstantiate(&ctx->host_graph[slot], g, 0) != cudaSuccess) rc = set_err(ctx, KVFE_ERR_CUDA, "host-step graph instantiation failed");
+      if (g) cudaGraphDestroy(g);
+      if (rc == KVFE_OK) { ctx->host_graph_ready[slot] = 1; ctx->host_graph_launches = n; }
+    }
+    if (rc == KVFE_OK && cudaGraphLaunch(ctx->host_graph[slot], ctx->stream) != cudaSuccess) rc = set_err(ctx, KVFE_ERR_CUDA, "cudaGraphLaunch failed");
+    if (rc == KVFE_OK) ctx->launches += ctx->host_graph_launches;
+  } else {
+    long long n = 0;
+    rc = enqueue_step_kernels(ctx, &n);
+    if (rc == KVFE_OK) n += launch_publish(io + ctx->io_pk_off, ctx->db.packets, pk_bytes, ctx->stream);
+    ctx->launches += n;
+  }
+  ctx->in_ts = nullptr; ctx->in_R = nullptr;
+  if (rc != KVFE_OK) return rc;
+  ctx->cur_slot ^= 1;
+  CU(cudaEventRecord(ctx->pipe_done[ps], ctx->stream));
+  ctx->pipe_user[ps] = packets; ctx->pipe_io_slot[ps] = slot;
   ++ctx->n_submitted;
   return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_submit(kvfe_ctx* ctx, const uint8_t* const* left, const uint8_t* const* right, size_t pitch,
+                                    const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets) {
+  if (!ctx || !left || !right || !timestamps || !keyframe_R_cur) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (ctx->n_submitted - ctx->n_waited >= 2) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit: two steps already in flight, call kvfe_frontend_wait first");
+  RET(upload_batch(ctx, left, right, pitch));
+  return launch_host_step(ctx, timestamps, keyframe_R_cur, packets);
+}
+
+// ---- staged uploads: frames of a group of contexts travel in ONE H2D copy per camera ----------------
+struct kvfe_upload {
+  int n = 0;
+  std::vector<kvfe_ctx*> ctx;
+  size_t B = 0, img = 0;
+  unsigned char* stage[2][2] = {{nullptr, nullptr}, {nullptr, nullptr}};   // [ring slot][camera]
+  cudaStream_t stream = nullptr;
+  cudaEvent_t up_done[2] = {nullptr, nullptr};
+  std::vector<cudaEvent_t> taken[2];            // [ring slot][member]: the member's slice copies are done
+  std::vector<char> taken_used[2];
+  std::vector<unsigned long long> consumed;     // uploads consumed per member
+  unsigned long long uploaded = 0;
+};
+
+extern "C" void kvfe_upload_destroy(kvfe_upload* u) {
+  if (!u) return;
+  if (u->stream) cudaStreamSynchronize(u->stream);
+  for (kvfe_ctx* c : u->ctx) if (c) cudaStreamSynchronize(c->stream);
+  for (int s = 0; s < 2; ++s) {
+    for (int k = 0; k < 2; ++k) if (u->stage[s][k]) cudaFree(u->stage[s][k]);
+    if (u->up_done[s]) cudaEventDestroy(u->up_done[s]);
+    for (cudaEvent_t e : u->taken[s]) if (e) cudaEventDestroy(e);
+  }
+  if (u->stream) cudaStreamDestroy(u->stream);
+  delete u;
+}
+
+extern "C" int kvfe_upload_create(kvfe_ctx* const* ctxs, int n, kvfe_upload** out) {
+  if (!ctxs || n <= 0 || !out || !ctxs[0]) return KVFE_ERR_INVALID_ARG;
+  kvfe_ctx* ctx = ctxs[0];                               // error sink of the CU() macro
+  const DevCfg& d0 = ctx->dc;
+  if (d0.pitch != d0.W) return set_err(ctx, KVFE_ERR_INVALID_ARG, "upload: the device row pitch must equal the width");
+  for (int i = 0; i < n; ++i)
+    if (!ctxs[i] || ctxs[i]->dc.W != d0.W || ctxs[i]->dc.H != d0.H || ctxs[i]->dc.B != d0.B)
+      return set_err(ctx, KVFE_ERR_INVALID_ARG, "upload: contexts must share image size and batch");
+  kvfe_upload* u = new kvfe_upload();
+  u->n = n; u->ctx.assign(ctxs, ctxs + n); u->B = d0.B; u->img = (size_t)d0.W * d0.H;
+  u->consumed.assign(n, 0);
+  const size_t bytes = (size_t)n * u->B * u->img;
+  cudaError_t e = cudaStreamCreateWithFlags(&u->stream, cudaStreamNonBlocking);
+  for (int s = 0; s < 2 && e == cudaSuccess; ++s) {
+    for (int k = 0; k < 2 && e == cudaSuccess; ++k) e = cudaMalloc((void**)&u->stage[s][k], bytes);
+    if (e == cudaSuccess) e = cudaEventCreateWithFlags(&u->up_done[s], cudaEventDisableTiming);
+    u->taken[s].assign(n, nullptr); u->taken_used[s].assign(n, 0);
+    for (int i = 0; i < n && e == cudaSuccess; ++i) e = cudaEventCreateWithFlags(&u->taken[s][i], cudaEventDisableTiming);
+  }
+  if (e != cudaSuccess) { kvfe_upload_destroy(u); return set_err(ctx, KVFE_ERR_CUDA, "upload_create: %s", cudaGetErrorString(e)); }
+  *out = u;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_upload_frames(kvfe_upload* u, const uint8_t* left, const uint8_t* right, size_t pitch) {
+  if (!u) return KVFE_ERR_INVALID_ARG;
+  kvfe_ctx* ctx = u->ctx[0];
+  if (!left || !right) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (pitch != (size_t)ctx->dc.W) return set_err(ctx, KVFE_ERR_INVALID_ARG, "upload_frames: images must be densely packed (pitch == width)");
+  const unsigned long long seq = u->uploaded;
+  const int slot = (int)(seq & 1);
+  for (int i = 0; i < u->n; ++i) {
+    if (seq >= 2 && u->consumed[i] + 1 < seq)
+      return set_err(ctx, KVFE_ERR_INVALID_ARG, "upload_frames: two uploads are already waiting for member %d", i);
+    // the ring slot may be overwritten once every member has taken its slice of the upload before last
+    if (u->taken_used[slot][i]) CU(cudaStreamWaitEvent(u->stream, u->taken[slot][i], 0));
+  }
+  const size_t bytes = (size_t)u->n * u->B * u->img;
+  CU(cudaMemcpyAsync(u->stage[slot][0], left, bytes, cudaMemcpyHostToDevice, u->stream));
+  CU(cudaMemcpyAsync(u->stage[slot][1], right, bytes, cudaMemcpyHostToDevice, u->stream));
+  CU(cudaEventRecord(u->up_done[slot], u->stream));
+  ++u->uploaded;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_submit_uploaded(kvfe_ctx* ctx, kvfe_upload* u, int member, const int64_t* timestamps,
+                                             const double* keyframe_R_cur, uint8_t* packets) {
+  if (!ctx || !u || !timestamps || !keyframe_R_cur) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (member < 0 || member >= u->n || u->ctx[member] != ctx) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit_uploaded: not a member of this upload group");
+  if (ctx->n_submitted - ctx->n_waited >= 2) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit: two steps already in flight, call kvfe_frontend_wait first");
+  const unsigned long long seq = u->consumed[member];
+  if (seq >= u->uploaded) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit_uploaded: no uploaded frames left for this member");
+  const int slot = (int)(seq & 1);
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  const size_t B = u->B, img = u->img, off = (size_t)member * B * img;
+  CU(cudaStreamWaitEvent(ctx->stream, u->up_done[slot], 0));
+  // slice -> pyramid slot / right buffer with an SM copy kernel: copy-engine operations of different
+  // contexts share in-order queues, a kernel does not
+  ctx->launches += launch_fetch(u->stage[slot][0] + off, u->stage[slot][1] + off, db.pyr[ctx->cur_slot] + dc.lvl_off[0],
+                                dc.pyr_stride, db.right_raw, dc.img_stride, img, (int)B, ctx->stream);
+  CU(cudaGetLastError());
+  CU(cudaEventRecord(u->taken[slot][member], ctx->stream));
+  u->taken_used[slot][member] = 1;
+  ++u->consumed[member];
+  return launch_host_step(ctx, timestamps, keyframe_R_cur, packets);
 }
 
 extern "C" int kvfe_frontend_wait(kvfe_ctx* ctx) {
   if (!ctx) return KVFE_ERR_INVALID_ARG;
   if (ctx->n_waited == ctx->n_submitted) return set_err(ctx, KVFE_ERR_INVALID_ARG, "wait: nothing in flight");
-  const int slot = (int)(ctx->n_waited & 1);
-  CU(cudaEventSynchronize(ctx->pipe_done[slot]));
-  if (!ctx->pipe_direct[slot]) memcpy(ctx->pipe_user[slot], ctx->h_pipe[slot], (size_t)ctx->dc.B * ctx->db.packet_bytes);
+  const int ps = (int)(ctx->n_waited & 1);
+  CU(cudaEventSynchronize(ctx->pipe_done[ps]));
+  const int slot = ctx->pipe_io_slot[ps];
+  if (ctx->pipe_user[ps])
+    memcpy(ctx->pipe_user[ps], ctx->h_io[slot] + ctx->io_pk_off, (size_t)ctx->dc.B * ctx->db.packet_bytes);
+  ctx->last_io_slot = slot;
   ++ctx->n_waited;
   return KVFE_OK;
+}
+
+extern "C" int kvfe_frontend_ready(kvfe_ctx* ctx) {
+  if (!ctx) return KVFE_ERR_INVALID_ARG;
+  if (ctx->n_waited == ctx->n_submitted) return 0;
+  cudaError_t e = cudaEventQuery(ctx->pipe_done[ctx->n_waited & 1]);
+  if (e == cudaSuccess) return 1;
+  if (e == cudaErrorNotReady) { cudaGetLastError(); return 0; }
+  return set_err(ctx, KVFE_ERR_CUDA, "cudaEventQuery failed: %s", cudaGetErrorString(e));
+}
+
+extern "C" const uint8_t* kvfe_frontend_packets_view(const kvfe_ctx* ctx) {
+  return ctx ? ctx->h_io[ctx->last_io_slot] + ctx->io_pk_off : nullptr;
 }
 
 extern "C" int kvfe_frontend_step_multi(kvfe_ctx* const* ctxs, int n, const uint8_t* const* const* left,
@@ -1061,10 +1213,11 @@ extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_d
   RET(stage_inputs(ctx, timestamps, keyframe_R_cur));
   if (pitch == (size_t)dc.W && dc.pitch == dc.W) {
     // densely packed images: one strided copy per camera for the whole batch (row = one image)
+    // (an SM copy kernel, not two copy-engine operations: those share in-order queues across contexts)
     const size_t img = (size_t)dc.W * dc.H;
-    CU(cudaMemcpy2DAsync(db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, left_dev, img, img, B,
-                         cudaMemcpyDeviceToDevice, s));
-    CU(cudaMemcpy2DAsync(db.right_raw, dc.img_stride, right_dev, img, img, B, cudaMemcpyDeviceToDevice, s));
+    ctx->launches += launch_fetch(left_dev, right_dev, db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, db.right_raw,
+                                  dc.img_stride, img, (int)B, s);
+    CU(cudaGetLastError());
   } else {
     for (size_t b = 0; b < B; ++b) {
       RET(copy_image(ctx, db.pyr[ctx->cur_slot] + b * dc.pyr_stride + dc.lvl_off[0], dc.pitch,

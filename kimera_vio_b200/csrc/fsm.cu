@@ -393,6 +393,43 @@ int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, int* kf
   detect_pre_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask, kf_counter);
   return 1;
 }
+// SM-driven copy of the packets into mapped pinned host memory (16-byte stores over the host link).
+// A memcpy node / cudaMemcpyAsync would sit in the copy engine's in-order queue behind the D2H copies
+// of contexts submitted earlier whose (three times longer) keyframe steps are still running, so
+// every context would complete at the pace of the slowest one; a kernel has no such queue.
+__global__ void __launch_bounds__(256) publish_kernel(uint4* __restrict__ dst, const uint4* __restrict__ src, size_t n16) {
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += (size_t)gridDim.x * blockDim.x) dst[i] = src[i];
+}
+int launch_publish(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s) {
+  const size_t n16 = bytes / 16;
+  int blocks = (int)((n16 + 255) / 256);
+  if (blocks > 64) blocks = 64;
+  if (blocks < 1) blocks = 1;
+  publish_kernel<<<blocks, 256, 0, s>>>(reinterpret_cast<uint4*>(dst_host), reinterpret_cast<const uint4*>(src_dev), n16);
+  return 1;
+}
+// SM-driven placement of a sub-batch's images (contiguous in a device staging area) into the pyramid
+// slot (level 0, stride pyr_stride) and the right-image buffer: one launch instead of two strided
+// copy-engine operations.  grid (x, B, 2): y = image of the batch, z = camera.
+__global__ void __launch_bounds__(256) fetch_kernel(const unsigned char* __restrict__ srcL, const unsigned char* __restrict__ srcR,
+                                                    unsigned char* __restrict__ dstL, size_t dstL_stride,
+                                                    unsigned char* __restrict__ dstR, size_t dstR_stride, size_t img) {
+  const unsigned char* src = (blockIdx.z ? srcR : srcL) + (size_t)blockIdx.y * img;
+  unsigned char* dst = blockIdx.z ? dstR + (size_t)blockIdx.y * dstR_stride : dstL + (size_t)blockIdx.y * dstL_stride;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if ((((size_t)src | (size_t)dst) & 15) == 0) {
+    const size_t n16 = img / 16;
+    for (size_t i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+    for (size_t i = n16 * 16 + tid; i < img; i += nth) dst[i] = src[i];
+  } else {
+    for (size_t i = tid; i < img; i += nth) dst[i] = src[i];
+  }
+}
+int launch_fetch(const unsigned char* srcL, const unsigned char* srcR, unsigned char* dstL, size_t dstL_stride,
+                 unsigned char* dstR, size_t dstR_stride, size_t img, int B, cudaStream_t s) {
+  fetch_kernel<<<dim3(24, B, 2), 256, 0, s>>>(srcL, srcR, dstL, dstL_stride, dstR, dstR_stride, img);
+  return 1;
+}
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
   finalize_kernel<<<dc.B, 256, 0, s>>>(dc, db);
   return 1;

@@ -154,9 +154,15 @@ struct kvfe_ctx {
   unsigned char* h_stage;      // 2 * B * img_stride
   unsigned char* h_packets;
   // submit/wait pipeline (depth KVFE_PIPE_DEPTH): pinned packet staging per in-flight step
-  unsigned char* h_pipe[2]; cudaEvent_t pipe_done[2]; unsigned char* pipe_user[2]; bool pipe_direct[2];
+  cudaEvent_t pipe_done[2]; unsigned char* pipe_user[2]; int pipe_io_slot[2]; int last_io_slot;
+  // pinned I/O block per pyramid slot: [ts: B x i64][R: B x 9 f64][pad][packets]; the host-step graph
+  // (host_graph) holds the H2D copy of the inputs, the kernel sequence and the D2H copy of the packets
+  unsigned char* h_io[2]; size_t in_bytes, io_pk_off;
+  unsigned char* d_in;         // device copy of the inputs (d_ts / d_Rin point into it)
+  cudaGraphExec_t host_graph[2]; int host_graph_ready[2]; long long host_graph_launches;
   unsigned long long n_submitted, n_waited;
   long long* d_ts; double* d_Rin;        // step inputs
+  const long long* in_ts; const double* in_R;   // what prep_kernel reads: d_ts/d_Rin, or the mapped pinned I/O block
   long long* h_ts; double* h_Rin;        // KVFE_IN_SLOTS pinned slots each
   cudaEvent_t in_ev[KVFE_IN_SLOTS]; int in_used[KVFE_IN_SLOTS]; int in_slot;
   cudaGraphExec_t step_graph[2];   // captured kernel sequence of one step, per pyramid slot
@@ -211,6 +217,9 @@ int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const
                 const double* Rin, cudaStream_t s);
 int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, cudaStream_t s);
+int launch_fetch(const unsigned char* srcL, const unsigned char* srcR, unsigned char* dstL, size_t dstL_stride,
+                 unsigned char* dstR, size_t dstR_stride, size_t img, int B, cudaStream_t s);
+int launch_publish(void* dst_host, const void* src_dev, size_t bytes, cudaStream_t s);
 int launch_decide(const DevCfg& dc, const DevBuf& db, unsigned long long cond, cudaStream_t s);
 int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, int* kf_counter, cudaStream_t s);
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s);

@@ -65,7 +65,7 @@ __host__ __device__ inline MatchGeom match_geom(int tc, int tr, int sc, int sr) 
   return g;
 }
 
-// grid (cap, B).  TM_SQDIFF(p) = sum S^2 - 2 sum S*T + sum T^2 in exact integers:
+// One keypoint (CTA-wide).  TM_SQDIFF(p) = sum S^2 - 2 sum S*T + sum T^2 in exact integers:
 //  * sum S*T for all shifts of one stripe row band is a GEMM: with p = 8 i + j,
 //      corr[8i + j] = sum_r sum_c' S[r][8i + c'] * T[r][c' - j]        (c' = j + c)
 //    A[i][(r, c')] = stripe bytes (16 x 32 fragments are plain aligned words of the staged stripe),
@@ -73,14 +73,8 @@ __host__ __device__ inline MatchGeom match_geom(int tc, int tr, int sc, int sr) 
 //    template), D = 16 x 8 int32 -> mma.sync m16n8k32 u8.  Warp w takes template rows r = w mod 4
 //    for all M tiles; the partial sums meet in shared memory (integer adds, order-free).
 //  * sum S^2 per shift = difference of a prefix sum over squared column sums.
-__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf db, int mode_mask, int reuse_tracked) {
-  extern __shared__ __align__(16) unsigned char smraw[];
-  const int b = blockIdx.y;
-  const StreamState& s = db.st[b];
-  if (!mode_on(s.mode, mode_mask)) return;
-  const int fs = b * 3 + s.slot_k;
-  const int i = blockIdx.x;
-  if (i >= db.fr.n[fs]) return;
+__device__ void match_one(const DevCfg& dc, const DevBuf& db, unsigned char* smraw, const StreamState& s, const int b,
+                          const int fs, const int i, const int reuse_tracked) {
   const size_t k = (size_t)fs * dc.cap + i;
   const int lst = db.fr.lstat[k];
   // Second reconstruction of a keyframe (StereoVisionImuFrontend.cpp:426): the tracked keypoints
@@ -268,6 +262,22 @@ __global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf 
   }
 }
 
+#define MATCH_KP_PER_CTA 4
+// grid (ceil(cap / MATCH_KP_PER_CTA), B): a CTA walks keypoints blockIdx.x, blockIdx.x + gridDim.x, ...
+// (fewer, longer-lived CTAs: most slots of the capacity-sized grid hold no live keypoint)
+__global__ void __launch_bounds__(MATCH_THREADS) match_kernel(DevCfg dc, DevBuf db, int mode_mask, int reuse_tracked) {
+  extern __shared__ __align__(16) unsigned char smraw[];
+  const int b = blockIdx.y;
+  const StreamState& s = db.st[b];
+  if (!mode_on(s.mode, mode_mask)) return;
+  const int fs = b * 3 + s.slot_k;
+  const int n = db.fr.n[fs];
+  for (int i = blockIdx.x; i < n; i += gridDim.x) {
+    match_one(dc, db, smraw, s, b, fs, i, reuse_tracked);
+    __syncthreads();                       // shared tiles are reused by the next keypoint
+  }
+}
+
 __global__ void __launch_bounds__(128) depth_kernel(DevCfg dc, DevBuf db, const CamModel* __restrict__ cams,
                                                     int mode_mask) {
   const int b = blockIdx.y;
@@ -334,7 +344,7 @@ int launch_sparse_stereo(const DevCfg& dc, const DevBuf& db, const CamModel* d_c
     cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
     attr = sm;
   }
-  match_kernel<<<dim3(dc.cap, dc.B), MATCH_THREADS, sm, s>>>(dc, db, mode_mask, reuse_tracked); ++n;
+  match_kernel<<<dim3((dc.cap + MATCH_KP_PER_CTA - 1) / MATCH_KP_PER_CTA, dc.B), MATCH_THREADS, sm, s>>>(dc, db, mode_mask, reuse_tracked); ++n;
   depth_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); ++n;
   return n;
 }

@@ -113,6 +113,10 @@ def load() -> C.CDLL:
     lib.kvfe_packet_bytes.restype = C.c_size_t
     lib.kvfe_packet_bytes.argtypes = [C.c_void_p]
     lib.kvfe_cuda_stream.restype = C.c_void_p
+    lib.kvfe_upload_destroy.restype = None
+    lib.kvfe_upload_destroy.argtypes = [C.c_void_p]
+    lib.kvfe_frontend_packets_view.restype = C.c_void_p
+    lib.kvfe_frontend_packets_view.argtypes = [C.c_void_p]
     lib.kvfe_cuda_stream.argtypes = [C.c_void_p]
     lib.kvfe_config_default.argtypes = [C.POINTER(Config)]
     lib.kvfe_config_default.restype = None
@@ -406,6 +410,11 @@ class Context:
 
     def wait(self):
         return self.lib.kvfe_frontend_wait(self.h)
+
+    def packets_view(self) -> np.ndarray:
+        """Packets of the last waited step, in place in the context's pinned I/O block (no copy)."""
+        ptr = self.lib.kvfe_frontend_packets_view(self.h)
+        return np.ctypeslib.as_array(C.cast(ptr, C.POINTER(C.c_uint8)), shape=(self.B * self.packet_bytes,))
 
     def sync(self):
         self._chk(self.lib.kvfe_sync(self.h))

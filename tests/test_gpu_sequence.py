@@ -182,10 +182,75 @@ def test_submit_wait_pipeline_matches_step():
         assert ctxB.submit_raw(lp, rp, frames[0][k].left.strides[0], ts_all[k], Rs_all[k], outs[k]) == 0
         if k >= 1:
             assert ctxB.wait() == 0
+            assert np.array_equal(ctxB.packets_view(), ref[k - 1])      # zero-copy view of the same step
     assert ctxB.wait() == 0
     assert ctxB.wait() != 0                       # nothing in flight: must fail loudly
     bad = [k for k in range(N) if not np.array_equal(ref[k], outs[k])]
     H.diag("submit_wait", mismatching_frames=bad, n_kf=int(sum(l > 0 for l in lkf)))
     ctxA.close()
     ctxB.close()
+    assert not bad
+
+
+def test_staged_upload_matches_step():
+    """kvfe_upload_frames (one H2D copy per camera for a group of contexts, issued one step ahead) +
+    kvfe_frontend_submit_uploaded must give byte-identical packets to per-context kvfe_frontend_step."""
+    import ctypes as C
+    NCTX, N = 3, 7
+    setups = [H.euroc_setup(batch=1) for _ in range(2 * NCTX)]
+    ref_ctx = [s_[2] for s_ in setups[:NCTX]]
+    grp_ctx = [s_[2] for s_ in setups[NCTX:]]
+    pkb = ref_ctx[0].packet_bytes
+    streams, frames = [], []
+    for c in range(NCTX):
+        s_, fr = H.synth_frames(N, seed=4242 + 17 * c)
+        streams.append(s_)
+        frames.append(fr)
+    lib = ref_ctx[0].lib
+    # reference pass (blocking step per context) -> packets and the rotations that depend on them
+    lkf = [0] * NCTX
+    ref, Rm_all, ts_all, Ls, Rs = [], [], [], [], []
+    for k in range(N):
+        L = np.ascontiguousarray(np.stack([frames[c][k].left for c in range(NCTX)]))
+        R = np.ascontiguousarray(np.stack([frames[c][k].right for c in range(NCTX)]))
+        ts = [np.array([frames[c][k].timestamp], np.int64) for c in range(NCTX)]
+        Rm = [np.ascontiguousarray(np.asarray(streams[c].kf_rotation(lkf[c], k), np.float64).reshape(1, 9)) for c in range(NCTX)]
+        row = []
+        for c in range(NCTX):
+            buf = np.empty(pkb, np.uint8)
+            lp = (C.c_void_p * 1)(L[c].ctypes.data)
+            rp = (C.c_void_p * 1)(R[c].ctypes.data)
+            assert ref_ctx[c].step_raw(lp, rp, L.shape[2], ts[c], Rm[c], buf) == 0
+            if ref_ctx[c].parse_packets(buf)[0]["is_keyframe"]:
+                lkf[c] = k
+            row.append(buf)
+        ref.append(row); Rm_all.append(Rm); ts_all.append(ts); Ls.append(L); Rs.append(R)
+    up = C.c_void_p()
+    harr = (C.c_void_p * NCTX)(*[c.h.value for c in grp_ctx])
+    assert lib.kvfe_upload_create(harr, C.c_int(NCTX), C.byref(up)) == 0
+    W = Ls[0].shape[2]
+
+    def upload(k):
+        return lib.kvfe_upload_frames(up, C.c_void_p(Ls[k].ctypes.data), C.c_void_p(Rs[k].ctypes.data), C.c_size_t(W))
+
+    bad = []
+    assert upload(0) == 0
+    for k in range(N):
+        if k + 1 < N:
+            assert upload(k + 1) == 0                       # one step ahead of the members
+        if k + 2 < N:
+            assert upload(k + 2) != 0                       # ring of two: must be refused
+        outs = [np.empty(pkb, np.uint8) for _ in range(NCTX)]
+        for c in range(NCTX):
+            rc = lib.kvfe_frontend_submit_uploaded(grp_ctx[c].h, up, C.c_int(c), C.c_void_p(ts_all[k][c].ctypes.data),
+                                                   C.c_void_p(Rm_all[k][c].ctypes.data), C.c_void_p(outs[c].ctypes.data))
+            assert rc == 0, lib.kvfe_last_error(grp_ctx[c].h)
+        for c in range(NCTX):
+            assert grp_ctx[c].wait() == 0
+            if not np.array_equal(ref[k][c], outs[c]):
+                bad.append((k, c))
+    H.diag("staged_upload", mismatches=bad)
+    lib.kvfe_upload_destroy(up)
+    for c in grp_ctx + ref_ctx:
+        c.close()
     assert not bad
