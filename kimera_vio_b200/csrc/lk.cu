@@ -208,6 +208,13 @@ __global__ void __launch_bounds__(LK_WARPS * 32) lk_kernel(DevCfg dc, DevBuf db,
       pdx = dxv; pdy = dyv;
     }
   }
+  if (status) {
+    // the error pass of calcOpticalFlowPyrLK (level 0, `err` requested as the reference does,
+    // Tracker.cpp:137-146): a FINAL position whose window origin left the image clears the status
+    // (the iteration loop only tests the position it starts an iteration from)
+    const int fx = cv_floor(nx - halfWin), fy = cv_floor(ny - halfWin);
+    if (fx < -win || fx >= dc.lvl_w[0] || fy < -win || fy >= dc.lvl_h[0]) status = false;
+  }
   if (lane == 0) {
     db.lk_qx[gi] = nx; db.lk_qy[gi] = ny;
     db.lk_status[gi] = status ? 1 : 0;
@@ -432,6 +439,13 @@ __global__ void __launch_bounds__(LKC_WARPS * 32) lk_kernel_col(DevCfg dc, DevBu
       }
       pdx = dxv; pdy = dyv;
     }
+  }
+  if (status) {
+    // the error pass of calcOpticalFlowPyrLK (level 0, `err` requested as the reference does,
+    // Tracker.cpp:137-146): a FINAL position whose window origin left the image clears the status
+    // (the iteration loop only tests the position it starts an iteration from)
+    const int fx = cv_floor(nx - halfWin), fy = cv_floor(ny - halfWin);
+    if (fx < -WIN || fx >= dc.lvl_w[0] || fy < -WIN || fy >= dc.lvl_h[0]) status = false;
   }
   if (lane == 0) {
     db.lk_qx[gi] = nx; db.lk_qy[gi] = ny;

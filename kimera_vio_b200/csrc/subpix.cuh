@@ -11,13 +11,17 @@ static __device__ void get_rect_subpix(const unsigned char* __restrict__ img, in
                                 float cyf, int pw, int ph, float* __restrict__ buf, int lane) {
   float cx = cxf - (pw - 1) * 0.5f, cy = cyf - (ph - 1) * 0.5f;
   int ipx = cv_floor(cx), ipy = cv_floor(cy);
-  // cv2 4.13: one arithmetic for interior and border patches -- replicate-clamped 4-tap blend
-  // (P00*a11 + P01*a12) + (P10*a21 + P11*a22) in float (order pinned against cv2.getRectSubPix:
-  // 300/300 random centres bit-exact); edge columns outside the image use the 2-tap vertical blend.
+  // cv2 4.13, pinned against cv2.getRectSubPix on 208 border patches + 300 interior ones (all bit-exact):
+  //  * rows and columns of the window that have both taps inside: (P00*a11 + P01*a12) + (P10*a21 + P11*a22);
+  //  * window columns left of / at-or-right-of the last image column: 2-tap vertical blend of the edge column
+  //    -- except that rows ABOVE the image take column W-2 on the right side (a quirk of the library's
+  //    border path, reproduced);
+  //  * window rows above the image / at-or-below the last image row: fma(P01, a, P00 * (1 - a)) of the
+  //    edge row.
   {
     float a = cx - ipx, bq = cy - ipy;
     float a11 = (1.f - a) * (1.f - bq), a12 = a * (1.f - bq), a21 = (1.f - a) * bq, a22 = a * bq;
-    float b1 = 1.f - bq, b2 = bq;
+    float b1 = 1.f - bq, b2 = bq, a1 = 1.f - a;
     int rx, rw, ry, rh;
     if (ipx >= 0) rx = 0; else { rx = -ipx; if (rx > pw) rx = pw; }
     if (ipx < W - pw) rw = pw; else { rw = W - ipx - 1; if (rw < 0) rw = 0; }
@@ -25,16 +29,21 @@ static __device__ void get_rect_subpix(const unsigned char* __restrict__ img, in
     if (ipy < H - ph) rh = ph; else { rh = H - ipy - 1; if (rh < 0) rh = 0; }
     for (int i = lane; i < pw * ph; i += 32) {
       int r = i / pw, j = i - r * pw;
+      const bool row_out = r < ry || r >= rh;
       int y0 = clampi(ipy + r, 0, H - 1);
-      int y1 = (r < ry || r >= rh) ? y0 : clampi(ipy + r + 1, 0, H - 1);
+      int y1 = row_out ? y0 : clampi(ipy + r + 1, 0, H - 1);
       const unsigned char* p0 = img + (size_t)y0 * pitch;
       const unsigned char* p1 = img + (size_t)y1 * pitch;
       float v;
       if (j < rx) { int xc = clampi(ipx + rx, 0, W - 1); v = p0[xc] * b1 + p1[xc] * b2; }
-      else if (j >= rw) { int xc = clampi(ipx + rw, 0, W - 1); v = p0[xc] * b1 + p1[xc] * b2; }
-      else {
+      else if (j >= rw) {
+        int xc = clampi(ipx + rw, 0, W - 1);
+        if (r < ry) xc = max(W - 2, 0);
+        v = p0[xc] * b1 + p1[xc] * b2;
+      } else {
         int x0 = clampi(ipx + j, 0, W - 1), x1 = clampi(ipx + j + 1, 0, W - 1);
-        v = (p0[x0] * a11 + p0[x1] * a12) + (p1[x0] * a21 + p1[x1] * a22);   // order pinned against cv2 (scratch probe: 100% bit-exact)
+        if (row_out) v = fmaf((float)p0[x1], a, p0[x0] * a1);
+        else v = (p0[x0] * a11 + p0[x1] * a12) + (p1[x0] * a21 + p1[x1] * a22);
       }
       buf[i] = v;
     }

@@ -177,3 +177,53 @@ def test_process_first_frame_35_corners():
         assert sf.left_keypoints_rectified[i][0] == ofe.KP_VALID
         assert sf.right_keypoints_rectified[i][0] == ofe.KP_VALID
         assert abs(depth[j] - sf.keypoints_3d[i][2]) <= 4
+
+
+def test_getrectsubpix_border_model_matches_cv2():
+    """The arithmetic subpix.cuh implements for cv::getRectSubPix (u8 -> f32) windows that leave the
+    image, restated in numpy and pinned against cv2 on random border / corner centres: pair-wise 4-tap
+    blend inside, 2-tap vertical blend in columns outside (rows above the image take column W-2 on
+    the right), fma(P01, a, P00*(1-a)) in rows outside."""
+    import cv2
+    f32 = np.float32
+    rng = np.random.default_rng(11)
+    Hh, Ww = 96, 128
+    img = cv2.GaussianBlur((rng.random((Hh, Ww)) * 255).astype(np.uint8), (0, 0), 1.5)
+    I = img.astype(f32)
+
+    def model(cxf, cyf, pw=23, ph=23):
+        cx = f32(f32(cxf) - f32((pw - 1) * 0.5)); cy = f32(f32(cyf) - f32((ph - 1) * 0.5))
+        ipx = int(np.floor(cx)); ipy = int(np.floor(cy))
+        a = f32(cx - f32(ipx)); b = f32(cy - f32(ipy))
+        a11 = f32((f32(1) - a) * (f32(1) - b)); a12 = f32(a * (f32(1) - b)); a21 = f32((f32(1) - a) * b); a22 = f32(a * b)
+        a1 = f32(f32(1) - a); b1 = f32(f32(1) - b)
+        rx = min(max(-ipx, 0), pw); rw = pw if ipx + pw < Ww else max(Ww - ipx - 1, 0)
+        ry = max(-ipy, 0); rh = ph if ipy + ph < Hh else max(Hh - ipy - 1, 0)
+        out = np.zeros((ph, pw), f32)
+        for i in range(ph):
+            outside = i < ry or i >= rh
+            y0 = 0 if i < ry else (Hh - 1 if i >= rh else ipy + i)
+            y1 = y0 if outside else y0 + 1
+            for j in range(pw):
+                if j < rx or j >= rw:
+                    xc = 0 if j < rx else Ww - 1
+                    if i < ry and j >= rw:
+                        xc = Ww - 2
+                    out[i, j] = f32(f32(I[y0, xc] * b1) + f32(I[y1, xc] * b))
+                else:
+                    x = ipx + j
+                    if outside:
+                        out[i, j] = f32(np.float64(I[y0, x + 1]) * np.float64(a) + np.float64(f32(I[y0, x] * a1)))
+                    else:
+                        out[i, j] = f32(f32(I[y0, x] * a11) + f32(I[y0, x + 1] * a12)) + f32(f32(I[y1, x] * a21) + f32(I[y1, x + 1] * a22))
+        return out
+
+    bad = 0
+    for k in range(48):
+        side = k % 8
+        cx = rng.uniform(0, 12) if side in (0, 4, 5) else (rng.uniform(Ww - 12, Ww - 1) if side in (1, 6, 7) else rng.uniform(20, Ww - 20))
+        cy = rng.uniform(0, 12) if side in (2, 4, 6) else (rng.uniform(Hh - 12, Hh - 1) if side in (3, 5, 7) else rng.uniform(20, Hh - 20))
+        cx, cy = float(f32(cx)), float(f32(cy))
+        ref = cv2.getRectSubPix(img, (23, 23), (cx, cy), patchType=cv2.CV_32F)
+        bad += int((model(cx, cy) != ref).sum())
+    assert bad == 0
