@@ -224,6 +224,43 @@ def test_sparse_stereo(env):
         assert rec["rect_mismatch"] == 0
 
 
+@pytest.mark.parametrize("variant", ["subpixel", "extra_rows", "templ_51x7", "near_range"])
+def test_sparse_stereo_param_variants(env, variant):
+    """Stereo-matcher parameter variants (StereoMatchingParams.h:46-60): cornerSubPix on the right match,
+    a stripe taller than the template (several row shifts), a smaller template (other GEMM tiling), a
+    shorter stripe (min_point_dist)."""
+    import dataclasses
+    kw = {"subpixel": dict(subpixel_refinement_stereo=True), "extra_rows": dict(stripe_extra_rows=2),
+          "templ_51x7": dict(templ_cols=51, templ_rows=7), "near_range": dict(min_point_dist=1.0)}[variant]
+    params = dataclasses.replace(env["p"], **kw)
+    p, rig, ctx = H.euroc_setup(batch=1, params=params)
+    o = env["orig"]
+    m = ofe.StereoMatcher(p, o)
+    name, L, R = _images(env)[1]
+    c = cv2.goodFeaturesToTrack(L, 200, 0.001, 20).reshape(-1, 2).astype(np.float32)
+    extra = np.array([[5.2, 4.1], [745.0, 3.0], [3.0, 476.0], [748.9, 478.2], [30.5, 240.5], [720.5, 200.5]], np.float32)
+    kps = np.concatenate([c, extra])
+    sf = ofe.StereoFrame.make(0, 0, L, R, o)
+    sf.left_frame.keypoints = [(np.float32(x), np.float32(y)) for x, y in kps]
+    sf.left_frame.versors = ofe.get_bearing_vectors(sf.left_frame.keypoints, o.left, o.R1)
+    m.sparse_stereo_reconstruction(sf)
+    g = ctx.sparse_stereo(L, R, kps, np.array(sf.left_frame.versors))
+    ers = np.array([s_ for s_, _ in sf.right_keypoints_rectified])
+    erx = np.array([q for _, q in sf.right_keypoints_rectified], np.float32)
+    gx = np.stack([g["right_rect_x"], g["right_rect_y"]], 1)
+    rec = dict(variant=variant, n=len(kps), right_status_mismatch=int((g["right_status"] != ers).sum()),
+               right_xy_max_err=float(np.abs(gx - erx).max()), right_xy_mismatch=int((gx != erx).any(axis=1).sum()),
+               depth_max_rel=float(np.max(np.abs(g["depth"] - np.array(sf.keypoints_depth)) / np.maximum(1e-12, np.abs(np.array(sf.keypoints_depth))))),
+               n_valid=int((ers == 0).sum()))
+    H.diag("sparse_stereo_variant", **rec)
+    ctx.close()
+    assert rec["right_status_mismatch"] == 0
+    if variant == "subpixel":
+        assert rec["right_xy_max_err"] <= 1e-3          # sub-pixel coordinates: tolerance of north_star
+    else:
+        assert rec["right_xy_mismatch"] == 0
+
+
 def test_ransac_2pt(env):
     cam = CameraParams.euroc_left()
     for planar, n_in, n_out in ((False, 80, 0), (False, 80, 20), (True, 80, 20), (False, 200, 100), (False, 1, 0)):
