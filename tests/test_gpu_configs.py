@@ -1,6 +1,7 @@
 """Parity on the larger BASELINE.json configurations (parity-test cases, not bench lines):
-C3-like 1280x720 / 500 features and C4-like 1920x1080 / 1000 features, synthetic stereo, a few
-frames of the whole front-end against the oracle."""
+C3-like 1280x720 / 500 features, C4-like 1920x1080 / 1000 features and the C5 image size
+3840x2160 / 2000 features on ONE GPU (the 8-GPU row tiling of C5 is not built), synthetic stereo, a
+few frames of the whole front-end against the oracle."""
 import dataclasses
 
 import numpy as np
@@ -18,7 +19,7 @@ from test_gpu_sequence import run_sequence
 pytestmark = pytest.mark.gpu
 
 
-@pytest.mark.parametrize("w,h,feats,frames", [(1280, 720, 500, 6), (1920, 1080, 1000, 5)])
+@pytest.mark.parametrize("w,h,feats,frames", [(1280, 720, 500, 6), (1920, 1080, 1000, 5), (3840, 2160, 2000, 3)])
 def test_sequence_larger_configs(w, h, feats, frames):
     left, right = CameraParams.euroc_left().scaled(w, h), CameraParams.euroc_right().scaled(w, h)
     p = dataclasses.replace(FrontendParams.euroc(), max_features_per_frame=feats)
