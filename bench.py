@@ -40,8 +40,11 @@ def frame_pool(n_frames: int, rig: StereoRigSetup):
     """POOL_STREAMS synthetic sequences of n_frames pairs, cached under /tmp (generation is numpy)."""
     cache = "/tmp/kvfe_bench_pool_%dx%d_%d_%d.npz" % (W, H, POOL_STREAMS, n_frames)
     if os.path.exists(cache):
-        z = np.load(cache)
-        return z["left"], z["right"], z["rot"]
+        try:
+            z = np.load(cache)
+            return z["left"], z["right"], z["rot"]
+        except Exception:
+            pass                                   # unreadable cache: regenerate (deterministic)
     left = np.zeros((POOL_STREAMS, n_frames, H, W), np.uint8)
     right = np.zeros_like(left)
     rot = np.zeros((POOL_STREAMS, n_frames, n_frames, 3, 3))     # rot[s, lkf, k]
@@ -54,7 +57,11 @@ def frame_pool(n_frames: int, rig: StereoRigSetup):
             for k in range(n_frames):
                 rot[s, a, k] = st.kf_rotation(a, k)
     try:
-        np.savez(cache, left=left, right=right, rot=rot)
+        # several ranks may build the cache at once: write privately, publish atomically
+        tmp = "%s.%d.tmp" % (cache, os.getpid())
+        with open(tmp, "wb") as fh:
+            np.savez(fh, left=left, right=right, rot=rot)
+        os.replace(tmp, cache)
     except Exception:
         pass
     return left, right, rot
