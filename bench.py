@@ -174,8 +174,9 @@ def run_reference(args):
         "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32/f32/f64 (OpenCV CPU)", "data": "synthetic",
-        "config": {"workload": "Euroc stereo 752x480, 300 feats, %d independent streams on %d host processes "
-                               "(1 thread each), oracle = cv2 CPU front-end" % (nproc, nproc)},
+        "config": {"workload": "Euroc stereo 752x480, %d feats (BASELINE.json configs[1] workload), reference CPU "
+                               "front-end: %d independent streams on %d host processes (1 thread each), "
+                               "oracle = the reference's OpenCV calls through cv2" % (N_FEATS, nproc, nproc)},
         "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": nproc, "kind": "port",
                          "sample": "%d streams x %d timed pairs, one single-threaded process per core" % (nproc, args.steps)},
         "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
