@@ -264,17 +264,48 @@ def run_gpu(args):
                            (C.c_void_p * NC)(*[ts_c[c][k].ctypes.data for c in range(NC)]),
                            (C.c_void_p * NC)(*[R_c[c][k].ctypes.data for c in range(NC)])))
 
+    dev_args = [[(ctxs[c].h, C.c_void_p(dL[c, k].data_ptr()), C.c_void_p(dR[c, k].data_ptr()), C.c_size_t(W),
+                  C.c_void_p(ts_c[c][k].ctypes.data), C.c_void_p(R_c[c][k].ctypes.data), None)
+                 for k in range(n_frames)] for c in range(NC)]
+    dev_api = os.environ.get("KVFE_BENCH_DEV_API", "step_dev")    # "submit_dev": measured slower (48 k vs 57 k)
+
     def run_dev(k0, k1):
+        if dev_api == "step_dev":       # one host call per step enqueues every context; unbounded queue depth
+            for k in range(k0, k1):
+                a = multi_args[k]
+                rc = lib.kvfe_frontend_step_dev_multi(hctx, NC, a[0], a[1], C.c_size_t(W), a[2], a[3])
+                assert rc == 0
+            return
+        # kvfe_frontend_submit_dev: images resident in HBM, no copy-engine operation; up to two steps in
+        # flight per context, the host only waits for the step before last of a context
+        infl = [0] * NC
         for k in range(k0, k1):
-            a = multi_args[k]
-            rc = lib.kvfe_frontend_step_dev_multi(hctx, NC, a[0], a[1], C.c_size_t(W), a[2], a[3])
-            assert rc == 0
+            for c in range(NC):
+                if infl[c] == 2:
+                    rc = lib.kvfe_frontend_wait(ctxs[c].h)
+                    assert rc == 0
+                    infl[c] -= 1
+                rc = lib.kvfe_frontend_submit_dev(*dev_args[c][k])
+                assert rc == 0, lib.kvfe_last_error(ctxs[c].h)
+                infl[c] += 1
+        dev_pending.append(infl)
+
+    dev_pending = []
+
+    def drain_dev():
+        for infl in dev_pending:
+            for c in range(NC):
+                for _ in range(infl[c]):
+                    rc = lib.kvfe_frontend_wait(ctxs[c].h)
+                    assert rc == 0
+        dev_pending.clear()
 
     sampler = ClockSampler(local)
     for ctx in ctxs:
         ctx.reset()
     run_dev(0, Wm)
     barrier()
+    drain_dev()
     launches0 = sum(c.launches for c in ctxs)
     ev0 = torch.cuda.Event(enable_timing=True)
     ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
@@ -288,6 +319,7 @@ def run_gpu(args):
         for e, st in zip(ev1, streams):
             e.record(st)
         barrier()
+    drain_dev()
     dev_ms = max(ev0.elapsed_time(e) for e in ev1)
     launches = sum(c.launches for c in ctxs) - launches0
     clocks = sampler.summary()

@@ -286,6 +286,11 @@ int kvfe_frontend_wait(kvfe_ctx* ctx);
  * advance at the pace of the slowest one of each round. */
 int kvfe_frontend_ready(kvfe_ctx* ctx);
 const uint8_t* kvfe_frontend_packets_view(const kvfe_ctx* ctx);
+/* kvfe_frontend_submit with the batch's images already in device memory (densely packed: image b at
+ * left_dev + b * width * height). */
+int kvfe_frontend_submit_dev(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, size_t pitch,
+                             const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets);
+
 /* Staged uploads.  Copies of a few hundred KB reach well under half of the host link rate, copies of
  * several MB reach it; and the frames of step k+1 do not depend on the results of step k (only the
  * IMU rotation does).  A kvfe_upload couples n contexts (same image size and batch) to a two-slot

@@ -1062,6 +1062,21 @@ extern "C" int kvfe_frontend_submit(kvfe_ctx* ctx, const uint8_t* const* left, c
   return launch_host_step(ctx, timestamps, keyframe_R_cur, packets);
 }
 
+// submit with the images already in device memory (densely packed batch: image b at left_dev +
+// b*W*H): an SM copy kernel places them, then the host-step graph runs.  No copy-engine operation at
+// all, so contexts never queue behind each other; same pipelining rules as kvfe_frontend_submit.
+extern "C" int kvfe_frontend_submit_dev(kvfe_ctx* ctx, const uint8_t* left_dev, const uint8_t* right_dev, size_t pitch,
+                                        const int64_t* timestamps, const double* keyframe_R_cur, uint8_t* packets) {
+  if (!ctx || !left_dev || !right_dev || !timestamps || !keyframe_R_cur) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (ctx->n_submitted - ctx->n_waited >= 2) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit: two steps already in flight, call kvfe_frontend_wait first");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  if (pitch != (size_t)dc.W || dc.pitch != dc.W) return set_err(ctx, KVFE_ERR_INVALID_ARG, "submit_dev: images must be densely packed (pitch == width)");
+  ctx->launches += launch_fetch(left_dev, right_dev, db.pyr[ctx->cur_slot] + dc.lvl_off[0], dc.pyr_stride, db.right_raw,
+                                dc.img_stride, (size_t)dc.W * dc.H, dc.B, ctx->stream);
+  CU(cudaGetLastError());
+  return launch_host_step(ctx, timestamps, keyframe_R_cur, packets);
+}
+
 // ---- staged uploads: frames of a group of contexts travel in ONE H2D copy per camera ----------------
 struct kvfe_upload {
   int n = 0;

@@ -254,3 +254,51 @@ def test_staged_upload_matches_step():
     for c in grp_ctx + ref_ctx:
         c.close()
     assert not bad
+
+
+def test_submit_dev_matches_step():
+    """kvfe_frontend_submit_dev (images already in device memory, two steps in flight) gives
+    byte-identical packets to the blocking host-buffer step."""
+    import ctypes as C
+    import torch
+    B, N = 2, 7
+    p, rig, ctxA = H.euroc_setup(batch=B)
+    _, _, ctxB = H.euroc_setup(batch=B)
+    streams, frames = [], []
+    for b in range(B):
+        s_, fr = H.synth_frames(N, seed=5150 + 13 * b)
+        streams.append(s_)
+        frames.append(fr)
+    pkb = ctxA.packet_bytes
+    lib = ctxA.lib
+    lkf = [0] * B
+    ref, Rs, tss, dLs, dRs = [], [], [], [], []
+    for k in range(N):
+        Lc = np.ascontiguousarray(np.stack([frames[b][k].left for b in range(B)]))
+        Rc = np.ascontiguousarray(np.stack([frames[b][k].right for b in range(B)]))
+        ts = np.array([frames[b][k].timestamp for b in range(B)], np.int64)
+        Rm = np.ascontiguousarray(np.array([streams[b].kf_rotation(lkf[b], k) for b in range(B)]).reshape(B, 9))
+        buf = np.empty(B * pkb, np.uint8)
+        lp = (C.c_void_p * B)(*[Lc[b].ctypes.data for b in range(B)])
+        rp = (C.c_void_p * B)(*[Rc[b].ctypes.data for b in range(B)])
+        assert ctxA.step_raw(lp, rp, Lc.shape[2], ts, Rm, buf) == 0
+        for b, pk in enumerate(ctxA.parse_packets(buf)):
+            if pk["is_keyframe"]:
+                lkf[b] = k
+        ref.append(buf); Rs.append(Rm); tss.append(ts)
+        dLs.append(torch.from_numpy(Lc).cuda()); dRs.append(torch.from_numpy(Rc).cuda())
+    torch.cuda.synchronize()
+    outs = [np.empty(B * pkb, np.uint8) for _ in range(N)]
+    for k in range(N):
+        rc = lib.kvfe_frontend_submit_dev(ctxB.h, C.c_void_p(dLs[k].data_ptr()), C.c_void_p(dRs[k].data_ptr()),
+                                          C.c_size_t(dLs[k].shape[2]), C.c_void_p(tss[k].ctypes.data),
+                                          C.c_void_p(Rs[k].ctypes.data), C.c_void_p(outs[k].ctypes.data))
+        assert rc == 0, lib.kvfe_last_error(ctxB.h)
+        if k >= 1:
+            assert ctxB.wait() == 0
+    assert ctxB.wait() == 0
+    bad = [k for k in range(N) if not np.array_equal(ref[k], outs[k])]
+    H.diag("submit_dev", mismatching_frames=bad)
+    ctxA.close()
+    ctxB.close()
+    assert not bad
