@@ -227,3 +227,32 @@ def test_getrectsubpix_border_model_matches_cv2():
         ref = cv2.getRectSubPix(img, (23, 23), (cx, cy), patchType=cv2.CV_32F)
         bad += int((model(cx, cy) != ref).sum())
     assert bad == 0
+
+
+def test_rotational_flow_predictor_reference_numbers():
+    """RotationalOpticalFlowPredictor::predictSparseFlow on the cube scene of
+    tests/testOpticalFlowPredictor.cpp:40-76,566-612 (cam 1 at z = -4 looking at a unit cube, cam 2
+    rotated by the quaternion (0.985, 0, 0, 0.174) about z): the sixteen coordinates the reference
+    test lists, tolerance 1e-1 px as there."""
+    from oracle import frontend as ofe
+    fx, W, H = 458.654, 752, 480
+    K = np.array([[fx, 0, W // 2], [0, fx, H // 2], [0, 0, 1.0]])
+    lmks = [(0, 0, 0), (0, 1, 0), (1, 0, 0), (1, 1, 0), (0, 0, 1), (0, 1, 1), (1, 0, 1), (1, 1, 1)]
+    kps = []
+    for X, Y, Z in lmks:                       # cam 1: identity rotation, position (0, 0, -4)
+        zc = Z + 4.0
+        kps.append((fx * X / zc + W // 2, fx * Y / zc + H // 2))
+    qw, qx, qy, qz = 0.985, 0.0, 0.0, 0.174    # gtsam::Rot3(w, x, y, z) normalises the quaternion
+    n = np.sqrt(qw * qw + qx * qx + qy * qy + qz * qz)
+    qw, qx, qy, qz = qw / n, qx / n, qy / n, qz / n
+    R = np.array([[1 - 2 * (qy * qy + qz * qz), 2 * (qx * qy - qz * qw), 2 * (qx * qz + qy * qw)],
+                  [2 * (qx * qy + qz * qw), 1 - 2 * (qx * qx + qz * qz), 2 * (qy * qz - qx * qw)],
+                  [2 * (qx * qz - qy * qw), 2 * (qy * qz + qx * qw), 1 - 2 * (qx * qx + qy * qy)]])
+    out = ofe.predict_sparse_flow(kps, R, K, W, H, 1)
+    expected = [(376.00003051757812, 239.99998474121094), (415.302001953125, 347.7138671875),
+                (483.71389770507812, 200.69801330566406), (523.015869140625, 308.41189575195312),
+                (376.00003051757812, 239.99998474121094), (407.44161987304688, 326.17108154296875),
+                (462.17111206054688, 208.55841064453125), (493.61270141601562, 294.7294921875)]
+    assert len(out) == 8
+    for (x, y), (ex, ey) in zip(out, expected):
+        assert abs(float(x) - ex) <= 1e-1 and abs(float(y) - ey) <= 1e-1, ((x, y), (ex, ey))

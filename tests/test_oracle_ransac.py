@@ -118,3 +118,21 @@ def test_backproject2_jacobian_numeric():
         pm, _ = rs.backproject2_jacobian(z0[0] - d[0], z0[1] - d[1], z0[2] - d[2], fx, fy, cx, cy, b)
         Jn[:, k] = (pp - pm) / 2e-5
     assert np.allclose(J, Jn, rtol=1e-5, atol=1e-6)
+
+
+def test_voting_mahalanobis_formula_equivalence():
+    """The closed-form f32 Mahalanobis distance used by the 1-point voting (Tracker.cpp:495-520) equals
+    v' O^-1 v on random SPD matrices (tests/testTracker.cpp:1480-1528, tolerance 1e-2): a pair (i, j)
+    votes for each other exactly when that distance is below the threshold."""
+    rng = np.random.default_rng(12)
+    for _ in range(200):
+        m = rng.uniform(-1, 1, (3, 5))
+        O = (m @ m.T).astype(np.float32)
+        v = rng.uniform(-1, 1, 3).astype(np.float32)
+        ref = float(v.astype(np.float64) @ np.linalg.solve(O.astype(np.float64), v.astype(np.float64)))
+        # two relative translations v and 0 with covariances O and 0: one pair, distance = v' O^-1 v
+        rel = np.stack([v, np.zeros(3, np.float32)])
+        cov = np.stack([O, np.zeros((3, 3), np.float32)])
+        above = rs.voting_1pt(rel, cov, np.float32(ref * (1 - 1e-3) - 1e-2))
+        below = rs.voting_1pt(rel, cov, np.float32(ref * (1 + 1e-3) + 1e-2))
+        assert above[0] == 1 and below[0] == 2, (ref, above[0], below[0])
