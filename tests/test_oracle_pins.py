@@ -256,3 +256,43 @@ def test_rotational_flow_predictor_reference_numbers():
     assert len(out) == 8
     for (x, y), (ex, ey) in zip(out, expected):
         assert abs(float(x) - ex) <= 1e-1 and abs(float(y) - ey) <= 1e-1, ((x, y), (ex, ey))
+
+
+@needs_reference
+def test_mesher_create_mesh_2d_reference_fixture():
+    """tests/testMesher.cpp:147-197: the four corners of chessboard_small.png (UtilsOpenCV::ExtractCorners =
+    goodFeaturesToTrack(100, 0.01, 10, blockSize 3)) give two triangles, vertices in the order
+    (kp2, kp1, kp3) and (kp1, kp2, kp0); no keypoints -> no triangle."""
+    import cv2
+    from oracle import mesher
+    img = cv2.imread(os.path.join(REF_DATA, "chessboard_small.png"), cv2.IMREAD_GRAYSCALE)
+    kps = cv2.goodFeaturesToTrack(img, 100, 0.01, 10, None, None, 3, False, 0.04).reshape(-1, 2)
+    assert len(kps) == 4
+    size = (img.shape[1], img.shape[0])
+    tri = mesher.create_mesh_2d(size, [tuple(k) for k in kps], list(range(len(kps))), list(range(len(kps))))
+    assert tri.shape == (2, 6)
+    assert np.array_equal(tri[0], np.concatenate([kps[2], kps[1], kps[3]]))
+    assert np.array_equal(tri[1], np.concatenate([kps[1], kps[2], kps[0]]))
+    assert mesher.create_mesh_2d(size, [tuple(k) for k in kps], list(range(4)), []).shape == (0, 6)
+
+
+def test_mesher_stereo_filters_invalid_keypoints():
+    from oracle import mesher
+    rng = np.random.default_rng(4)
+    kps = [(float(x), float(y)) for x, y in rng.uniform(5, 95, (30, 2)).astype(np.float32)]
+    lmk = list(range(30))
+    status = [0] * 30
+    lmk[3] = -1
+    status[7] = 2
+    tri, l3d = mesher.create_mesh_2d_stereo((100, 100), lmk, status, kps, rng.normal(size=(30, 3)))
+    verts = {(float(t[2 * j]), float(t[2 * j + 1])) for t in tri for j in range(3)}
+    assert kps[3] not in verts and kps[7] not in verts and len(verts) == 28 and len(l3d) == 28
+    # Delaunay: no input point strictly inside any triangle's circumcircle
+    P = np.array([k for i, k in enumerate(kps) if i not in (3, 7)], np.float64)
+    for t in tri.astype(np.float64):
+        (ax, ay), (bx, by), (cx, cy) = t[0:2], t[2:4], t[4:6]
+        d = 2 * (ax * (by - cy) + bx * (cy - ay) + cx * (ay - by))
+        ux = ((ax * ax + ay * ay) * (by - cy) + (bx * bx + by * by) * (cy - ay) + (cx * cx + cy * cy) * (ay - by)) / d
+        uy = ((ax * ax + ay * ay) * (cx - bx) + (bx * bx + by * by) * (ax - cx) + (cx * cx + cy * cy) * (bx - ax)) / d
+        r2 = (ax - ux) ** 2 + (ay - uy) ** 2
+        assert ((P[:, 0] - ux) ** 2 + (P[:, 1] - uy) ** 2 >= r2 * (1 - 1e-6)).all()
