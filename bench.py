@@ -1,20 +1,30 @@
 #!/usr/bin/env python
-"""bench.py -- stereo front-end frame-pairs/s on synthetic 752x480 Euroc-shaped input.
+"""bench.py -- stereo front-end frame-pairs/s on synthetic Euroc-shaped input (BASELINE.json).
 
-  python bench.py --gpus N --steps K --warmup W          (torchrun for N > 1, one rank per GPU)
-  python bench.py --impl reference ...                   (the reference's OpenCV CPU path: oracle/)
+  python bench.py --gpus N --steps K --warmup W [--config c2|c3|c4]     (torchrun for N > 1, one rank per GPU)
+  python bench.py --impl reference ...                                 (the reference's OpenCV CPU path: oracle/)
 
-A "step" = one pass of the whole hot path over one batch of `--batch` (default 32) stereo
-frame-pairs, one per independent camera stream (BASELINE.json configs[1]).  `value` is measured
-with the batch already resident in HBM (kvfe_frontend_step_dev); `e2e` goes through the
-reference-facing C-ABI call with HOST buffers (kvfe_frontend_step: H2D of both images of every
-pair, D2H of every output packet inside the timed region).  Streams shard across ranks with no
-data-path collective (weak scaling: the per-GPU batch is fixed).
+One PASS = the whole hot path over one batch of `batch` stereo frame-pairs, one per independent camera
+stream.  One STEP = `--inner` consecutive passes (default 128), so that the timed region of the
+driver's `--steps 20` lasts more than a second instead of 11 ms.  Every stream replays a synthetic
+sequence forwards then backwards (continuous motion, any length).  Both measurements go through
+kvfe_pipeline_* (include/kvfe.h), the queue-in / queue-out boundary of the reference's front-end module:
+
+  value  images already resident in HBM (the pipeline reads them in place); outputs -- packets and the
+         keyframes' rectified images -- are still delivered to pinned host memory;
+  e2e    images in pinned HOST memory, pulled over the host link inside the timed region; the same
+         outputs delivered to the host, every delivered byte read by the dispatcher (checksum).
+
+Frames are queued ahead (rotation input mode 1: the front-end accumulates the frame-to-frame IMU
+rotation itself, like the reference's front-end does with the IMU samples of its input packet), so
+neither number assumes an a-priori keyframe schedule.  Streams shard across ranks with no data-path
+collective (weak scaling: the per-GPU batch is fixed).
 """
 from __future__ import annotations
 
 import argparse
 import ctypes as C
+import dataclasses
 import json
 import os
 import subprocess
@@ -27,49 +37,109 @@ import numpy as np
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
+from kimera_vio_b200.hostprobe import sobel_cpu_tail_start  # noqa: E402
 from kimera_vio_b200.params import CameraParams, FrontendParams  # noqa: E402
 from kimera_vio_b200.rig import StereoRigSetup  # noqa: E402
 from kimera_vio_b200.synth import SynthStream  # noqa: E402
 
-W, H, N_FEATS = 752, 480, 300
-POOL_STREAMS = 4              # distinct synthetic streams; batch slot b replays stream b % POOL_STREAMS
 DT_NS = 50_000_000
+T0_NS = 1403715273262142976
+
+# BASELINE.json configs[1..3]; B_alg of SURVEY 8(d) is computed from the measured keyframe ratio
+CONFIGS = {
+    "c2": dict(W=752, H=480, feats=300, batch=32, pool_streams=4, pool_frames=48,
+               workload="Euroc stereo 752x480, 300 feats, 1xB200 batch=32 frame-pairs (BASELINE.json configs[1])"),
+    "c3": dict(W=1280, H=720, feats=500, batch=16, pool_streams=2, pool_frames=24,
+               workload="uHumans2-shaped 720p stereo 1280x720, 500 feats, 1xB200, 16 streams (BASELINE.json configs[2], without the Mesher)"),
+    "c4": dict(W=1920, H=1080, feats=1000, batch=1, pool_streams=1, pool_frames=24,
+               workload="Synthetic 1080p stereo 1920x1080, 1000 feats, one independent stream per B200 (BASELINE.json configs[3])"),
+    "c5": dict(W=3840, H=2160, feats=2000, batch=1, pool_streams=1, pool_frames=10,
+               workload="4K stereo 3840x2160, 2000 feats, one stream on ONE B200 (the single-GPU side of BASELINE.json configs[4])"),
+}
 
 
-def frame_pool(n_frames: int, rig: StereoRigSetup):
-    """POOL_STREAMS synthetic sequences of n_frames pairs, cached under /tmp (generation is numpy)."""
-    cache = "/tmp/kvfe_bench_pool_%dx%d_%d_%d.npz" % (W, H, POOL_STREAMS, n_frames)
+def config_rig(cfg):
+    left, right = CameraParams.euroc_left(), CameraParams.euroc_right()
+    if (cfg["W"], cfg["H"]) != (left.width, left.height):
+        left, right = left.scaled(cfg["W"], cfg["H"]), right.scaled(cfg["W"], cfg["H"])
+    return left, right, StereoRigSetup(left, right)
+
+
+def config_params(cfg):
+    return dataclasses.replace(FrontendParams.euroc(), max_features_per_frame=cfg["feats"])
+
+
+def _gen_stream(args):
+    name, s, n_frames = args
+    cfg = CONFIGS[name]
+    left, right, rig = config_rig(cfg)
+    st = SynthStream(left, right, rig.R1, seed=20240 + 1000 * s)
+    L = np.zeros((n_frames, cfg["H"], cfg["W"]), np.uint8)
+    R = np.zeros_like(L)
+    for k in range(n_frames):
+        f = st.frame(k)
+        L[k], R[k] = f.left, f.right
+    fwd = np.stack([st.kf_rotation(k, k + 1) for k in range(n_frames - 1)])
+    bwd = np.stack([st.kf_rotation(k + 1, k) for k in range(n_frames - 1)])
+    return L, R, fwd, bwd
+
+
+def frame_pool(name: str):
+    """pool_streams synthetic sequences of pool_frames pairs + the frame-to-frame rotations in both
+    directions, cached under /tmp (generation is numpy, one process per sequence)."""
+    cfg = CONFIGS[name]
+    PS, NF = cfg["pool_streams"], cfg["pool_frames"]
+    cache = "/tmp/kvfe_bench_pool_v2_%s_%d_%d.npz" % (name, PS, NF)
     if os.path.exists(cache):
         try:
             z = np.load(cache)
-            return z["left"], z["right"], z["rot"]
+            return z["left"], z["right"], z["fwd"], z["bwd"]
         except Exception:
             pass                                   # unreadable cache: regenerate (deterministic)
-    left = np.zeros((POOL_STREAMS, n_frames, H, W), np.uint8)
-    right = np.zeros_like(left)
-    rot = np.zeros((POOL_STREAMS, n_frames, n_frames, 3, 3))     # rot[s, lkf, k]
-    for s in range(POOL_STREAMS):
-        st = SynthStream(CameraParams.euroc_left(), CameraParams.euroc_right(), rig.R1, seed=20240 + 1000 * s)
-        for k in range(n_frames):
-            f = st.frame(k)
-            left[s, k], right[s, k] = f.left, f.right
-        for a in range(n_frames):
-            for k in range(n_frames):
-                rot[s, a, k] = st.kf_rotation(a, k)
+    import multiprocessing as mp
+    with mp.get_context("fork").Pool(min(PS, 8)) as pool:
+        res = pool.map(_gen_stream, [(name, s, NF) for s in range(PS)])
+    left, right = np.stack([r[0] for r in res]), np.stack([r[1] for r in res])
+    fwd, bwd = np.stack([r[2] for r in res]), np.stack([r[3] for r in res])
     try:
         # several ranks may build the cache at once: write privately, publish atomically
         tmp = "%s.%d.tmp" % (cache, os.getpid())
         with open(tmp, "wb") as fh:
-            np.savez(fh, left=left, right=right, rot=rot)
+            np.savez(fh, left=left, right=right, fwd=fwd, bwd=bwd)
         os.replace(tmp, cache)
     except Exception:
         pass
-    return left, right, rot
+    return left, right, fwd, bwd
 
 
-def slot_timestamp(b: int, k: int) -> int:
+def pass_frame(t: int, NF: int) -> int:
+    """frame of the pool replayed at pass t: 0, 1, ..., NF-1, NF-2, ..., 1, 0, 1, ..."""
+    period = 2 * (NF - 1)
+    u = t % period
+    return u if u < NF else period - u
+
+
+def pass_rotation(fwd, bwd, s: int, t: int, NF: int):
+    """camLrectKm1_R_camLrectK of pass t (identity for the first pass)."""
+    if t == 0:
+        return np.eye(3)
+    a, b = pass_frame(t - 1, NF), pass_frame(t, NF)
+    return fwd[s, a] if b == a + 1 else bwd[s, b]
+
+
+def slot_timestamp(b: int, t: int) -> int:
     # staggers the keyframe cadence across batch slots: slot b's first gap is (1 + b % 4) periods
-    return 1403715273262142976 + (k + (b % 4 if k >= 1 else 0)) * DT_NS
+    return T0_NS + (t + (b % 4 if t >= 1 else 0)) * DT_NS
+
+
+def mat3(a, b):
+    """3x3 product in the device's operation order (common.cuh matmul3: a0*b0 + (a1*b1 + a2*b2))."""
+    a, b = np.asarray(a, np.float64).reshape(3, 3), np.asarray(b, np.float64).reshape(3, 3)
+    c = np.zeros((3, 3))
+    for i in range(3):
+        for j in range(3):
+            c[i, j] = float(a[i, 0]) * float(b[0, j]) + (float(a[i, 1]) * float(b[1, j]) + float(a[i, 2]) * float(b[2, j]))
+    return c
 
 
 class ClockSampler:
@@ -117,68 +187,104 @@ def measured_peaks():
     return {"hbm_gbs": 6650.0}, "fallback"
 
 
+def pin_to_gpu_numa_node(local: int):
+    """Restrict this rank (and the dispatcher threads it will create) to the CPUs next to its GPU."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(local)
+        bus = pynvml.nvmlDeviceGetPciInfo(h).busId
+        bus = bus.decode() if isinstance(bus, bytes) else bus
+        path = "/sys/bus/pci/devices/%s/local_cpulist" % bus.lower()[-12:]
+        txt = open(path).read().strip()
+        cpus = set()
+        for part in txt.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if cpus:
+            os.sched_setaffinity(0, cpus)
+            return {"pci": bus, "cpus": len(cpus)}
+    except Exception as e:                       # no sysfs / NVML: leave the affinity alone
+        return {"error": str(e)[:80]}
+    return None
+
+
 # ------------------------------------------------------------------------------------------------
 # the oracle front-end as the timed CPU baseline (cv2 == the reference's OpenCV code path)
 # ------------------------------------------------------------------------------------------------
 def _oracle_worker(args):
-    stream_id, n_warm, n_timed, threads = args
+    name, slot, n_warm, n_timed, threads, collect = args
     import cv2
     from oracle import frontend as ofe
     from oracle.rig import StereoRig
     cv2.setNumThreads(threads)
-    rig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
-    setup = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
-    left, right, rot = frame_pool(n_warm + n_timed, setup)
-    s = stream_id % POOL_STREAMS
-    fe = ofe.StereoFrontend(FrontendParams.euroc(), rig)
-    lkf = 0
-    t0 = None
-    n_kf = 0
-    for k in range(n_warm + n_timed):
-        if k == n_warm:
+    cfg = CONFIGS[name]
+    lcam, rcam, _ = config_rig(cfg)
+    rig = StereoRig(lcam, rcam)
+    left, right, fwd, bwd = frame_pool(name)
+    PS, NF = cfg["pool_streams"], cfg["pool_frames"]
+    s = slot % PS
+    fe = ofe.StereoFrontend(config_params(cfg), rig)
+    acc = np.eye(3)
+    t0, n_kf, rec = None, 0, []
+    for t in range(n_warm + n_timed):
+        if t == n_warm:
             t0 = time.perf_counter()
-        sf = ofe.StereoFrame.make(k, slot_timestamp(stream_id, k), left[s, k], right[s, k], rig)
-        o = fe.spin(sf, rot[s, lkf, k])
-        if o.is_keyframe:
-            lkf = k
-            n_kf += k >= n_warm
-    return time.perf_counter() - t0, n_timed, n_kf
+        f = pass_frame(t, NF)
+        R = mat3(acc, pass_rotation(fwd, bwd, s, t, NF))
+        sf = ofe.StereoFrame.make(t, slot_timestamp(slot, t), left[s, f], right[s, f], rig)
+        o = fe.spin(sf, R)
+        acc = np.eye(3) if o.is_keyframe else R
+        n_kf += bool(o.is_keyframe) and t >= n_warm
+        if collect and t < collect:
+            lf = o.frame.left_frame
+            rec.append((bool(o.is_keyframe), np.array(lf.keypoints, np.float32).reshape(-1, 2),
+                        np.array(lf.landmarks, np.int64)))
+    return time.perf_counter() - t0, n_timed, n_kf, rec
 
 
-def cpu_baseline_single(n_warm: int, n_timed: int):
-    dt, n, n_kf = _oracle_worker((0, n_warm, n_timed, 1))
+def cpu_baseline_single(name: str, n_warm: int, n_timed: int, collect: int):
+    dt, n, n_kf, rec = _oracle_worker((name, 0, n_warm, n_timed, 1, collect))
     return {"value": n / dt, "unit": "frame-pairs/s", "cores": 1, "kind": "port",
-            "sample": "oracle (cv2 4.13 + numpy RANSAC), 1 stream, %d timed pairs after %d warm-up, %d keyframes, "
-                      "cv2.setNumThreads(1)" % (n, n_warm, n_kf)}
+            "sample": "oracle (cv2 4.13 + numpy RANSAC), stream of batch slot 0, %d timed pairs after %d warm-up, %d keyframes, "
+                      "cv2.setNumThreads(1), %.1f s" % (n, n_warm, n_kf, dt)}, rec
+
+
+REF_INNER = 8
 
 
 def run_reference(args):
     """--impl reference: the reference's own CPU implementation of the path (the oracle: same OpenCV
-    calls), one single-threaded process per host core, one camera stream each."""
+    calls), one single-threaded process per host core, one camera stream each.  A step = REF_INNER
+    passes (frames) of every process."""
     import multiprocessing as mp
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    cfg = CONFIGS[args.config]
     ncores = len(os.sched_getaffinity(0))
     nproc = max(1, min(ncores, 32))     # 32 / 64 / 128 processes were tried on the 128-thread box: 32 is the fastest
-    setup = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
-    frame_pool(args.warmup + args.steps, setup)          # build the cache once
+    frame_pool(args.config)                                  # build the cache once
     t0 = time.perf_counter()
     with mp.get_context("fork").Pool(nproc) as pool:
-        res = pool.map(_oracle_worker, [(i, args.warmup, args.steps, 1) for i in range(nproc)])
+        res = pool.map(_oracle_worker, [(args.config, i, args.warmup * REF_INNER, args.steps * REF_INNER, 1, 0) for i in range(nproc)])
     wall = max(r[0] for r in res)
     total = sum(r[1] for r in res)
     value = total / wall
     line = {
-        "impl": "reference", "metric": "stereo front-end frame-pairs/sec @ 752x480", "value": value,
+        "impl": "reference", "metric": "stereo front-end frame-pairs/sec @ %dx%d" % (cfg["W"], cfg["H"]), "value": value,
         "unit": "frame-pairs/s", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": 1e3 * wall / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "u8/int32/f32/f64 (OpenCV CPU)", "data": "synthetic",
-        "config": {"workload": "Euroc stereo 752x480, %d feats (BASELINE.json configs[1] workload), reference CPU "
-                               "front-end: %d independent streams on %d host processes (1 thread each), "
-                               "oracle = the reference's OpenCV calls through cv2" % (N_FEATS, nproc, nproc)},
+        "config": {"workload": cfg["workload"], "inner_passes_per_step": REF_INNER,
+                   "arm": "reference CPU front-end (oracle = the reference's OpenCV calls through cv2): %d independent "
+                          "streams on %d host processes, 1 thread each" % (nproc, nproc)},
         "cpu_baseline": {"value": value, "unit": "frame-pairs/s", "cores": nproc, "kind": "port",
-                         "sample": "%d streams x %d timed pairs, one single-threaded process per core" % (nproc, args.steps)},
+                         "sample": "%d streams x %d timed pairs, one single-threaded process per core" % (nproc, args.steps * REF_INNER)},
         "e2e": {"value": value, "unit": "frame-pairs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0, "host_cores_available": ncores, "wall_s_incl_setup": time.perf_counter() - t0,
     }
@@ -187,272 +293,160 @@ def run_reference(args):
 
 # ------------------------------------------------------------------------------------------------
 def run_gpu(args):
+    name = args.config
+    cfg = CONFIGS[name]
+    W, H = cfg["W"], cfg["H"]
+    B = args.batch or cfg["batch"]
+    PS, NF = cfg["pool_streams"], cfg["pool_frames"]
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    left, right, fwd, bwd = frame_pool(name)            # before CUDA is initialised (forks)
+    affinity = pin_to_gpu_numa_node(local) if not args.no_pin else None
+
     import torch
     import torch.distributed as dist
     from kimera_vio_b200 import lib as kl
 
-    rank = int(os.environ.get("RANK", "0"))
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    B, K, Wm, NC = args.batch, args.steps, args.warmup, args.contexts
-    assert B % NC == 0
-    Bc = B // NC                                   # streams per context (sub-batch in flight on its own CUDA stream)
-    n_frames = Wm + K
-    rig = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
-    left, right, rot = frame_pool(n_frames, rig)
-    p = FrontendParams.euroc()
-    ctxs = [kl.Context(kl.make_config(p, W, H, batch=Bc), rig.to_c()) for _ in range(NC)]
-    streams = [torch.cuda.ExternalStream(kl.load().kvfe_cuda_stream(c.h)) for c in ctxs]
-    pkb = ctxs[0].packet_bytes
+    K, Wm, R_in = args.steps, args.warmup, args.inner
+    n_warm, n_timed = Wm * R_in, K * R_in
+    n_pass = n_warm + n_timed
+    lcam, rcam, rig = config_rig(cfg)
+    p = config_params(cfg)
+    tail = sobel_cpu_tail_start(W)
+    kcfg = kl.make_config(p, W, H, batch=1, sobel_cpu_tail_start=tail)
+    pipe = kl.Pipeline(kcfg, rig.to_c(), n_streams=B, n_workers=args.workers, queue_depth=n_pass + 8, output_slots=4,
+                       want_rectified=True, rotation_mode=1, checksum_outputs=True, max_in_flight=args.in_flight)
+    pkb = pipe.packet_bytes
+    img = W * H
 
-    def slot(c, i):                                # global batch slot of context c, local stream i
-        return c * Bc + i
+    # device-resident and pinned-host copies of the frame pool
+    dL, dR = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+    pL, pR = torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory()
+    torch.cuda.synchronize()
 
-    # IMU rotations need the last-keyframe index per slot, which depends on the device-side keyframe
-    # decisions: run the sequence once (untimed, host path) to learn the keyframe schedule.
-    ts_all = np.array([[slot_timestamp(rank * B + b, k) for b in range(B)] for k in range(n_frames)], np.int64)
-    lkf = np.zeros(B, np.int64)
-    R_all = np.zeros((n_frames, B, 9))
-    kf_sched = np.zeros((n_frames, B), bool)
-    pk_buf = np.empty(Bc * pkb, np.uint8)
-    n_kp = []
-    for k in range(n_frames):
-        for b in range(B):
-            R_all[k, b] = rot[b % POOL_STREAMS, lkf[b], k].reshape(9)
-        for c, ctx in enumerate(ctxs):
-            lp = (C.c_void_p * Bc)(*[left[slot(c, i) % POOL_STREAMS, k].ctypes.data for i in range(Bc)])
-            rp = (C.c_void_p * Bc)(*[right[slot(c, i) % POOL_STREAMS, k].ctypes.data for i in range(Bc)])
-            tsk = np.ascontiguousarray(ts_all[k, c * Bc:(c + 1) * Bc])
-            Rk = np.ascontiguousarray(R_all[k, c * Bc:(c + 1) * Bc])
-            rc = ctx.step_raw(lp, rp, W, tsk, Rk, pk_buf)
-            assert rc == 0, kl.load().kvfe_last_error(ctx.h)
-            for i, pk in enumerate(ctx.parse_packets(pk_buf)):
-                if pk["is_keyframe"]:
-                    lkf[slot(c, i)] = k
-                    kf_sched[k, slot(c, i)] = True
-                if k == n_frames - 1:
-                    n_kp.append(pk["n"])
-    n_kp_mean = float(np.mean(n_kp))
-    ts_c = [[np.ascontiguousarray(ts_all[k, c * Bc:(c + 1) * Bc]) for k in range(n_frames)] for c in range(NC)]
-    R_c = [[np.ascontiguousarray(R_all[k, c * Bc:(c + 1) * Bc]) for k in range(n_frames)] for c in range(NC)]
+    frame_of = np.array([pass_frame(t, NF) for t in range(n_pass)], np.int64)
+    rot_tab = np.stack([np.stack([pass_rotation(fwd, bwd, s, t, NF).reshape(9) for t in range(n_pass)]) for s in range(PS)])
+    gslot = rank * B + np.arange(B, dtype=np.int64)                     # global batch slot of every local stream
+
+    def plan(base_l: int, base_r: int, t0: int, t1: int):
+        n = (t1 - t0) * B
+        streams = np.tile(np.arange(B, dtype=np.int32), t1 - t0)
+        tt = np.repeat(np.arange(t0, t1, dtype=np.int64), B)
+        ff = frame_of[tt]
+        ss = streams.astype(np.int64) % PS
+        off = (ss * NF + ff) * img
+        lp = (base_l + off).astype(np.uint64)
+        rp = (base_r + off).astype(np.uint64)
+        stagger = np.where(tt >= 1, np.tile(gslot % 4, t1 - t0), 0)
+        ts = (T0_NS + (tt + stagger) * DT_NS).astype(np.int64)
+        Rm = np.ascontiguousarray(rot_tab[ss, tt])
+        return n, streams, lp, rp, ts, Rm, tt.astype(np.uint64)
+
+    out_dt = np.dtype([("stream", "<i4"), ("slot", "<i4"), ("tag", "<u8"), ("is_keyframe", "<i4"), ("n_keypoints", "<i4"),
+                       ("checksum", "<u8"), ("packet", "<u8"), ("rect_left", "<u8"), ("rect_right", "<u8")])
+    assert out_dt.itemsize == C.sizeof(kl.PipelineOutput)
+    lib, ph = pipe.lib, pipe.h
+    OUTS = (kl.PipelineOutput * 1024)()
+    outs_np = np.frombuffer(OUTS, dtype=out_dt)
+
+    def run(pl, keep_packets=0):
+        """Pushes a whole plan (queue-ahead) and pops until everything is done.  Returns per-(pass, slot)
+        arrays of checksum / is_keyframe / n_keypoints (+ parsed packets of slot 0 for the first passes)."""
+        n, streams, lp, rp, ts, Rm, tags = pl
+        t_first = int(tags[0])
+        chk = np.zeros((n // B, B), np.uint64)
+        kf = np.zeros((n // B, B), bool)
+        nkp = np.zeros((n // B, B), np.int32)
+        kept = {}
+        acc = lib.kvfe_pipeline_push_many(ph, n, streams.ctypes.data, lp.ctypes.data, rp.ctypes.data, W, ts.ctypes.data,
+                                          Rm.ctypes.data, tags.ctypes.data)
+        assert acc == n, (acc, n, lib.kvfe_pipeline_last_error(ph))
+        done = 0
+        while done < n:
+            m = lib.kvfe_pipeline_pop(ph, OUTS, 1024, 2000)
+            assert m > 0, "pipeline stalled: %s" % lib.kvfe_pipeline_last_error(ph)
+            o = outs_np[:m]
+            ti = (o["tag"] - t_first).astype(np.int64)
+            chk[ti, o["stream"]] = o["checksum"]
+            kf[ti, o["stream"]] = o["is_keyframe"] != 0
+            nkp[ti, o["stream"]] = o["n_keypoints"]
+            if keep_packets:
+                for i in np.nonzero((o["stream"] == 0) & (o["tag"] < keep_packets))[0]:
+                    kept[int(o["tag"][i])] = pipe.parse(OUTS[int(i)], copy_rect=False)
+            lib.kvfe_pipeline_release(ph, OUTS, m)
+            done += m
+        return chk, kf, nkp, kept
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    # ---------------- device-resident measurement (value) ----------------
-    dL = torch.empty((NC, n_frames, Bc, H, W), dtype=torch.uint8, device="cuda")
-    dR = torch.empty_like(dL)
-    for c in range(NC):
-        for k in range(n_frames):
-            for i in range(Bc):
-                dL[c, k, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
-                dR[c, k, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
-    torch.cuda.synchronize()
-
-    # one host call per step enqueues all sub-batches (kvfe_frontend_step_dev_multi)
-    lib = kl.load()
-    hctx = (C.c_void_p * NC)(*[c.h for c in ctxs])
-    multi_args = []
-    for k in range(n_frames):
-        multi_args.append(((C.c_void_p * NC)(*[dL[c, k].data_ptr() for c in range(NC)]),
-                           (C.c_void_p * NC)(*[dR[c, k].data_ptr() for c in range(NC)]),
-                           (C.c_void_p * NC)(*[ts_c[c][k].ctypes.data for c in range(NC)]),
-                           (C.c_void_p * NC)(*[R_c[c][k].ctypes.data for c in range(NC)])))
-
-    dev_args = [[(ctxs[c].h, C.c_void_p(dL[c, k].data_ptr()), C.c_void_p(dR[c, k].data_ptr()), C.c_size_t(W),
-                  C.c_void_p(ts_c[c][k].ctypes.data), C.c_void_p(R_c[c][k].ctypes.data), None)
-                 for k in range(n_frames)] for c in range(NC)]
-    dev_api = os.environ.get("KVFE_BENCH_DEV_API", "step_dev")    # "submit_dev": measured slower (48 k vs 57 k)
-
-    def run_dev(k0, k1):
-        if dev_api == "step_dev":       # one host call per step enqueues every context; unbounded queue depth
-            for k in range(k0, k1):
-                a = multi_args[k]
-                rc = lib.kvfe_frontend_step_dev_multi(hctx, NC, a[0], a[1], C.c_size_t(W), a[2], a[3])
-                assert rc == 0
-            return
-        # kvfe_frontend_submit_dev: images resident in HBM, no copy-engine operation; up to two steps in
-        # flight per context, the host only waits for the step before last of a context
-        infl = [0] * NC
-        for k in range(k0, k1):
-            for c in range(NC):
-                if infl[c] == 2:
-                    rc = lib.kvfe_frontend_wait(ctxs[c].h)
-                    assert rc == 0
-                    infl[c] -= 1
-                rc = lib.kvfe_frontend_submit_dev(*dev_args[c][k])
-                assert rc == 0, lib.kvfe_last_error(ctxs[c].h)
-                infl[c] += 1
-        dev_pending.append(infl)
-
-    dev_pending = []
-
-    def drain_dev():
-        for infl in dev_pending:
-            for c in range(NC):
-                for _ in range(infl[c]):
-                    rc = lib.kvfe_frontend_wait(ctxs[c].h)
-                    assert rc == 0
-        dev_pending.clear()
-
-    sampler = ClockSampler(local)
-    for ctx in ctxs:
-        ctx.reset()
-    run_dev(0, Wm)
-    barrier()
-    drain_dev()
-    launches0 = sum(c.launches for c in ctxs)
-    ev0 = torch.cuda.Event(enable_timing=True)
-    ev1 = [torch.cuda.Event(enable_timing=True) for _ in ctxs]
-    with sampler:
-        ev0.record(streams[0])
-        for st in streams[1:]:
-            st.wait_event(ev0)
-        t_enq = time.perf_counter()
-        run_dev(Wm, n_frames)
-        t_enq = time.perf_counter() - t_enq
-        for e, st in zip(ev1, streams):
-            e.record(st)
+    N_PAR = 24            # passes of slot 0 compared with the oracle (parity self-check)
+    res = {}
+    for label, bl, br in (("value", dL.data_ptr(), dR.data_ptr()), ("e2e", pL.data_ptr(), pR.data_ptr())):
+        pipe.reset()
+        warm = run(plan(bl, br, 0, n_warm), keep_packets=N_PAR if (label == "e2e" and rank == 0) else 0)
+        pl = plan(bl, br, n_warm, n_pass)
         barrier()
-    drain_dev()
-    dev_ms = max(ev0.elapsed_time(e) for e in ev1)
-    launches = sum(c.launches for c in ctxs) - launches0
-    clocks = sampler.summary()
+        st0 = pipe.stats()
+        sampler = ClockSampler(local)
+        ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        with sampler:
+            ev0.record()
+            t0 = time.perf_counter()
+            timed = run(pl)
+            ev1.record()
+            barrier()
+            wall = time.perf_counter() - t0
+        st1 = pipe.stats()
+        res[label] = dict(ms_events=ev0.elapsed_time(ev1), wall_s=wall, warm=warm, timed=timed, clocks=sampler.summary(),
+                          graph_launches=st1["graph_launches"] - st0["graph_launches"],
+                          kernel_launches=st1["kernel_launches"] - st0["kernel_launches"],
+                          launch_cpu_s=st1["launch_seconds"] - st0["launch_seconds"], staged=st1["staged_copies"])
+    # the two runs process the same frames: every output (packet + rectified images) must be byte-identical
+    same_outputs = bool(np.array_equal(res["value"]["timed"][0], res["e2e"]["timed"][0]) and
+                        np.array_equal(res["value"]["warm"][0], res["e2e"]["warm"][0]))
+    kf_all = np.concatenate([res["e2e"]["warm"][1], res["e2e"]["timed"][1]])
+    rho = float(res["e2e"]["timed"][1].mean())
+    n_kp_mean = float(res["e2e"]["timed"][2].mean())
+    n_kf_timed = int(res["e2e"]["timed"][1].sum())
 
     # ---------------- dominant kernel (LK) launch duration, live CUDA events ----------------
-    # one context holding the whole batch; the step is run stage by stage with events on the
-    # library stream (kvfe_frontend_step_dev_timed); inputs: the same fresh device buffers.
+    # one context holding the whole batch, the step run stage by stage with events on the library stream
+    # (kvfe_frontend_step_dev_timed); keyframe_R_cur accumulated on the host from the schedule observed above
     lk_ms, stage_ms = None, None
     if rank == 0:
-        big = kl.Context(kl.make_config(p, W, H, batch=B), rig.to_c())
-        tsB = [np.ascontiguousarray(ts_all[k]) for k in range(n_frames)]
-        RB = [np.ascontiguousarray(R_all[k]) for k in range(n_frames)]
-        dLb = dL.permute(1, 0, 2, 3, 4).reshape(n_frames, B, H, W).contiguous()
-        dRb = dR.permute(1, 0, 2, 3, 4).reshape(n_frames, B, H, W).contiguous()
-        acc = []
-        for k in range(n_frames):
-            ms = big.step_dev_timed(dLb[k].data_ptr(), dRb[k].data_ptr(), W, tsB[k], RB[k])
-            if k >= Wm:
-                acc.append(ms)
-        stage_ms = np.mean(acc, axis=0)
+        T_LK = min(28, n_warm)
+        big = kl.Context(kl.make_config(p, W, H, batch=B, sobel_cpu_tail_start=tail), rig.to_c())
+        acc = [np.eye(3) for _ in range(B)]
+        stages = []
+        for t in range(T_LK):
+            f = pass_frame(t, NF)
+            idx = torch.tensor([(b % PS) for b in range(B)], device="cuda")
+            bl, br = dL[idx, f].contiguous(), dR[idx, f].contiguous()
+            Rk = np.zeros((B, 9))
+            for b in range(B):
+                Rb = mat3(acc[b], pass_rotation(fwd, bwd, b % PS, t, NF))
+                Rk[b] = Rb.reshape(9)
+                acc[b] = np.eye(3) if kf_all[t, b] else Rb
+            tsk = np.array([slot_timestamp(rank * B + b, t) for b in range(B)], np.int64)
+            ms = big.step_dev_timed(bl.data_ptr(), br.data_ptr(), W, tsk, np.ascontiguousarray(Rk))
+            if t >= 4:
+                stages.append(ms)
+        stage_ms = np.mean(stages, axis=0)
         lk_ms = float(stage_ms[8])
         big.close()
-        del dLb, dRb
 
-    # ---------------- end-to-end measurement through host buffers (e2e) ----------------
-    # host frames: for every frame k the images of all sub-batches are contiguous (group uploads)
-    pinL = torch.empty((n_frames, NC, Bc, H, W), dtype=torch.uint8).pin_memory()
-    pinR = torch.empty_like(pinL).pin_memory()
-    for c in range(NC):
-        for k in range(n_frames):
-            for i in range(Bc):
-                pinL[k, c, i].copy_(torch.from_numpy(left[slot(c, i) % POOL_STREAMS, k]))
-                pinR[k, c, i].copy_(torch.from_numpy(right[slot(c, i) % POOL_STREAMS, k]))
-    # two pinned packet buffers per context (a step's buffer is owned by the library until wait returns)
-    pk_pin = [[torch.empty(Bc * pkb, dtype=torch.uint8).pin_memory() for _ in range(2)] for _ in range(NC)]
-    sub_args = [[(ctxs[c].h,
-                  (C.c_void_p * Bc)(*[pinL[k, c, i].data_ptr() for i in range(Bc)]),
-                  (C.c_void_p * Bc)(*[pinR[k, c, i].data_ptr() for i in range(Bc)]),
-                  C.c_size_t(W), C.c_void_p(ts_c[c][k].ctypes.data), C.c_void_p(R_c[c][k].ctypes.data),
-                  None) for k in range(n_frames)] for c in range(NC)]     # packets: read in place (packets_view)
-    hs = [c.h for c in ctxs]
-
-    # staged uploads: the frames of G consecutive sub-batches travel in one H2D copy per camera, issued one
-    # step ahead (kvfe_upload_frames); G = 1 falls back to per-context image copies (kvfe_frontend_submit)
-    G = max(1, min(args.upload_group, NC))
-    ugroups = [list(range(g, min(g + G, NC))) for g in range(0, NC, G)]
-    HT = max(1, min(args.host_threads, len(ugroups)))
-    uploads, up_args, subu_args = [], [], {}
-    if G > 1:
-        for cs in ugroups:
-            up = C.c_void_p()
-            rc = lib.kvfe_upload_create((C.c_void_p * len(cs))(*[ctxs[c].h.value for c in cs]), C.c_int(len(cs)), C.byref(up))
-            assert rc == 0, lib.kvfe_last_error(hs[cs[0]])
-            uploads.append(up)
-            up_args.append([(up, C.c_void_p(pinL[k, cs[0]].data_ptr()), C.c_void_p(pinR[k, cs[0]].data_ptr()), C.c_size_t(W))
-                            for k in range(n_frames)])
-            for m, c in enumerate(cs):
-                subu_args[c] = [(hs[c], up, C.c_int(m), C.c_void_p(ts_c[c][k].ctypes.data),
-                                 C.c_void_p(R_c[c][k].ctypes.data), None) for k in range(n_frames)]
-
-    host_prof = [0.0, 0.0, 0.0, 0]          # [unused, unused, seconds inside submit, number of polls] (diagnostic)
-
-    def run_host_thread(gis, k0, k1):
-        # one dispatcher thread serving its contexts in COMPLETION order: poll (kvfe_frontend_ready), collect the
-        # finished step (kvfe_frontend_wait, packets read in place), submit the context's next frame at once.  A
-        # context never has more than one step in flight -- the IMU rotation of frame k depends on frame k-1's
-        # keyframe decision -- but contexts advance independently (a keyframe step takes ~3x a tracking step), and
-        # with staged uploads (G > 1) the frames of a group travel one step ahead in one H2D copy per camera.
-        cs_all = [c for gi in gis for c in ugroups[gi]]
-        nxt = {c: k0 for c in cs_all}
-        busy = {c: 0 for c in cs_all}
-        depth = 1
-        up_next = {gi: k0 for gi in gis}
-        remaining = len(cs_all) * (k1 - k0)
-        ready, wait, submit, submit_u, upload = (lib.kvfe_frontend_ready, lib.kvfe_frontend_wait, lib.kvfe_frontend_submit,
-                                                 lib.kvfe_frontend_submit_uploaded, lib.kvfe_upload_frames)
-        prof = host_prof
-        while remaining:
-            for gi in gis:
-                cs = ugroups[gi]
-                if G > 1:
-                    # keep the upload ring one step ahead of the slowest member of the group
-                    lo = min(nxt[c] for c in cs)
-                    while up_next[gi] < k1 and up_next[gi] <= lo + 1:
-                        rc = upload(*up_args[gi][up_next[gi]])
-                        assert rc == 0, lib.kvfe_last_error(hs[cs[0]])
-                        up_next[gi] += 1
-                for c in cs:
-                    if busy[c]:
-                        prof[3] += 1
-                        if ready(hs[c]) == 1:
-                            rc = wait(hs[c])
-                            assert rc == 0
-                            busy[c] -= 1
-                            remaining -= 1
-                    k = nxt[c]
-                    if busy[c] < depth and k < k1 and (G == 1 or k < up_next[gi]):
-                        t_a = time.perf_counter()
-                        rc = submit_u(*subu_args[c][k]) if G > 1 else submit(*sub_args[c][k])
-                        prof[2] += time.perf_counter() - t_a
-                        assert rc == 0, lib.kvfe_last_error(hs[c])
-                        nxt[c] = k + 1
-                        busy[c] += 1
-
-    def run_host(k0, k1):
-        parts = [list(range(len(ugroups)))[t::HT] for t in range(HT)]
-        if HT == 1:
-            return run_host_thread(parts[0], k0, k1)
-        th = [threading.Thread(target=run_host_thread, args=(g, k0, k1)) for g in parts]
-        for t in th:
-            t.start()
-        for t in th:
-            t.join()
-
-    for ctx in ctxs:
-        ctx.reset()
-    run_host(0, Wm)
-    barrier()
-    host_prof[:] = [0.0, 0.0, 0.0, 0]
-    t0 = time.perf_counter()
-    run_host(Wm, n_frames)
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    print("[e2e host profile] total %.3f s, %d polls, %.3f s inside submit calls" % (e2e_s, host_prof[3], host_prof[2]), file=sys.stderr)
-    for up in uploads:
-        lib.kvfe_upload_destroy(up)
-
-    # ---------------- host link rate (what bounds e2e) and single-stream latency ----------------
+    # ---------------- host link rate and single-stream latency ----------------
     link, latency = None, None
     if rank == 0:
-        # pinned -> device copy of one step's input volume on one stream, CUDA events
-        nb = 2 * B * W * H                                   # one step's H2D volume, contiguous
-        hbuf, dbuf = pinL.reshape(-1)[:nb], dL.reshape(-1)[:nb]
+        nb = min(2 * B * img, pL.numel())
+        hbuf, dbuf = pL.reshape(-1)[:nb], dL.reshape(-1)[:nb].clone()
         c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dbuf.copy_(hbuf, non_blocking=True)
         torch.cuda.synchronize()
@@ -461,80 +455,110 @@ def run_gpu(args):
             dbuf.copy_(hbuf, non_blocking=True)
         c1.record()
         torch.cuda.synchronize()
-        link = {"h2d_gbs_measured": 8 * hbuf.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9,
-                "copy_bytes": int(hbuf.numel())}
-        # one stream alone on the GPU (batch 1, one context): per-frame latency of the host-buffer call
-        one = kl.Context(kl.make_config(p, W, H, batch=1), rig.to_c())
-        pk1 = np.empty(pkb, np.uint8)
+        link = {"h2d_gbs_copy_engine": 8 * hbuf.numel() / (c0.elapsed_time(c1) * 1e-3) / 1e9, "copy_bytes": int(hbuf.numel())}
+        one = kl.Pipeline(kcfg, rig.to_c(), n_streams=1, n_workers=1, queue_depth=2, output_slots=2, want_rectified=True,
+                          rotation_mode=1, checksum_outputs=False)
         lat, lat_kf = [], []
-        for k in range(n_frames):
-            lp = (C.c_void_p * 1)(pinL[k, 0, 0].data_ptr())
-            rp = (C.c_void_p * 1)(pinR[k, 0, 0].data_ptr())
+        for t in range(64):
+            f = pass_frame(t, NF)
+            Rm = np.ascontiguousarray(pass_rotation(fwd, bwd, 0, t, NF))
             t1 = time.perf_counter()
-            rc = one.step_raw(lp, rp, W, ts_c[0][k][:1], R_c[0][k][:1], pk1)
+            one.push(0, pL[0, f].data_ptr(), pR[0, f].data_ptr(), W, slot_timestamp(0, t), Rm, tag=t)
+            outs = one.pop(timeout_ms=5000)
             dt = (time.perf_counter() - t1) * 1e3
-            assert rc == 0
-            if k >= Wm:
-                (lat_kf if one.parse_packets(pk1)[0]["is_keyframe"] else lat).append(dt)
+            assert len(outs) == 1
+            if t >= 8:
+                (lat_kf if outs[0].is_keyframe else lat).append(dt)
+            one.release(outs)
         one.close()
         allv = np.array(lat + lat_kf)
-        latency = {"what": "kvfe_frontend_step, host buffers, batch 1, stream alone on the GPU [ms]",
+        latency = {"what": "kvfe_pipeline push -> pop, host buffers, one stream alone on the GPU [ms]",
                    "p50": float(np.percentile(allv, 50)), "p99": float(np.percentile(allv, 99)),
                    "non_keyframe_p50": float(np.median(lat)) if lat else None,
                    "keyframe_p50": float(np.median(lat_kf)) if lat_kf else None, "frames": int(allv.size)}
 
-    times = torch.tensor([dev_ms, e2e_s * 1e3], dtype=torch.float64, device="cuda")
+    times = torch.tensor([res["value"]["ms_events"], res["e2e"]["wall_s"] * 1e3], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(times, op=dist.ReduceOp.MAX)
     dev_ms, e2e_ms = float(times[0]), float(times[1])
 
     if rank == 0:
-        pairs = world * B * K
+        pairs = world * B * n_timed
         value = pairs / (dev_ms * 1e-3)
         e2e_value = pairs / (e2e_ms * 1e-3)
-        rho = float(kf_sched[Wm:].mean())
-        b_alg = (1 - rho) * W * H + rho * 4 * W * H + 112 * n_kp_mean      # SURVEY 8(d), measured rho
+        b_alg = (1 - rho) * img + rho * 4 * img + 112 * n_kp_mean             # SURVEY 8(d), measured rho
         peaks, which = measured_peaks()
-        # LK kernel: compulsory traffic per launch = previous + current pyramids of every stream
-        # (levels 0..4, 1.33 * W * H bytes each); DESIGN.md section 3
-        pyr_bytes = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(5))
-        lk_alg_bytes = 2 * pyr_bytes * B
-        achieved = lk_alg_bytes / (lk_ms * 1e-3) / 1e9
-        step_achieved = b_alg * (B * K / (dev_ms * 1e-3)) / 1e9          # whole step, per GPU
+        # LK launch: (i) the compulsory bytes of SURVEY 8(d) for the B frame-pairs one launch serves;
+        # (ii) what the kernel itself must read: previous + current pyramids of every stream
+        lk_alg = b_alg * B
+        pyr_bytes = sum(((W + (1 << l) - 1) >> l) * ((H + (1 << l) - 1) >> l) for l in range(p.klt_max_level + 1))
+        lk_kernel_bytes = 2 * pyr_bytes * B
+        achieved = lk_alg / (lk_ms * 1e-3) / 1e9
+        step_achieved = b_alg * (B * n_timed / (dev_ms * 1e-3)) / 1e9            # whole path, per GPU
+        traffic, traffic_src = None, None
+        tp = os.path.join(ROOT, "profiles", "lk_traffic.json")
+        if os.path.exists(tp) and name == "c2":
+            tj = json.load(open(tp))
+            traffic, traffic_src = tj.get("dram_bytes_per_launch"), tj.get("source")
+        # parity self-check: the first passes of slot 0 against the oracle fed the same frames and rotations
+        parity, cpu = None, None
+        if world == 1 and not args.no_cpu_baseline:
+            cpu, rec = cpu_baseline_single(name, 8, args.cpu_pairs, N_PAR)
+            kept = res["e2e"]["warm"][3]
+            bad = []
+            for t, (okf, okp, olm) in enumerate(rec):
+                g = kept.get(t)
+                if g is None or g["n"] != len(okp) or bool(g["is_keyframe"]) != okf or not np.array_equal(g["landmark"], olm):
+                    bad.append(t)
+                elif len(okp) and np.abs(np.stack([g["kp_x"], g["kp_y"]], 1) - okp).max() > 1e-3:
+                    bad.append(t)
+            parity = {"passes_compared": len(rec), "slot": 0, "mismatching_passes": bad,
+                      "fields": "n, is_keyframe, landmark ids (exact), keypoints (1e-3 px)"}
+        r_v, r_e = res["value"], res["e2e"]
         line = {
-            "metric": "stereo front-end frame-pairs/sec @ 752x480", "value": value, "unit": "frame-pairs/s",
+            "metric": "stereo front-end frame-pairs/sec @ %dx%d" % (W, H), "value": value, "unit": "frame-pairs/s",
             "n_gpus": world, "steps": K, "warmup": Wm, "ms_per_step": dev_ms / K, "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "u8/int32 images, f32 LK+response, f64 geometry",
             "data": "synthetic",
-            "config": {"workload": "Euroc stereo 752x480, %d feats, 1xB200 batch=%d frame-pairs per step "
-                                   "(BASELINE.json configs[1]); %d independent streams per GPU" % (N_FEATS, B, B),
-                       "batch_per_gpu": B, "sub_batches_in_flight": NC, "e2e_dispatcher_threads": HT, "e2e_upload_group": G, "keyframe_ratio": rho,
-                       "mean_keypoints": n_kp_mean,
-                       "timing": "CUDA events on the library streams, max over ranks; every step reads fresh "
-                                 "device-resident inputs (%d MB per rank > L2), no L2 flush" %
-                                 (2 * n_frames * B * H * W // 2 ** 20)},
-            "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": e2e_ms / K,
-                    "h2d_bytes_per_step": int(2 * B * W * H + B * 80),
-                    "d2h_bytes_per_step": int(B * pkb)},
-            "gpu_launches": int(launches),
-            "host_enqueue_ms_per_step": 1e3 * t_enq / K,
+            "config": {"workload": cfg["workload"], "inner_passes_per_step": R_in, "ms_per_pass": dev_ms / n_timed,
+                       "batch_per_gpu": B, "streams_in_flight": B, "dispatcher_threads": pipe.pc.n_workers,
+                       "steps_in_flight_per_stream": pipe.pc.max_in_flight, "rotation_input": "frame-to-frame (mode 1), accumulated on the device",
+                       "keyframe_ratio": rho, "mean_keypoints": n_kp_mean, "numa_affinity": affinity,
+                       "timing": "value: CUDA events around the timed region (device idle on both sides), max over ranks; e2e: "
+                                 "wall clock between barriers; every pass reads other frames of a %d MB frame pool (> L2), no L2 flush" %
+                                 ((2 * left.nbytes) // 2 ** 20)},
+            "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": e2e_ms / K, "ms_per_pass": e2e_ms / n_timed,
+                    "h2d_bytes_per_step": int(R_in * B * (2 * img + 80)),
+                    "d2h_bytes_per_step": int((n_timed * B * pkb + n_kf_timed * 2 * img) / K),
+                    "what": "kvfe_pipeline push/pop, images in pinned host memory read over the link inside the step graph; packets "
+                            "+ keyframe rectified pairs stored into pinned host memory and checksummed by the dispatcher",
+                    "outputs_identical_to_value_run": same_outputs},
+            "gpu_launches": int(r_v["kernel_launches"]),
+            "graph_launches": int(r_v["graph_launches"]),
+            "host_enqueue_ms_per_pass": {"value": 1e3 * r_v["launch_cpu_s"] / n_timed, "e2e": 1e3 * r_e["launch_cpu_s"] / n_timed,
+                                         "note": "CPU time inside the launch path summed over the dispatcher threads"},
+            "device_ms_e2e_events": r_e["ms_events"], "staged_copies": int(r_e["staged"]),
             "host_link": link, "latency_ms": latency,
-            "clocks": clocks,
-            "roofline": {"bound": "hbm", "kernel": "lk_kernel_col<24> (pyramidal LK, dominant: 70% of the step's warp instructions, 27% of its serialised kernel time)",
-                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s",
-                         "frac": achieved / peaks["hbm_gbs"], "traffic": 30850048, "peak_source": which + " (burst copy)",
-                         "algorithmic_bytes_per_launch": lk_alg_bytes, "launch_ms": lk_ms,
-                         "traffic_source": "profiles/r01_ncu_final.txt: dram__bytes_read.sum + dram__bytes_write.sum, one launch, batch 32",
+            "clocks": r_v["clocks"], "clocks_e2e": r_e["clocks"],
+            "roofline": {"bound": "hbm", "kernel": "lk_kernel_col<24> (pyramidal LK: ~70% of the path's warp instructions)",
+                         "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": which + " (burst copy)",
+                         "algorithmic_bytes_per_launch": lk_alg, "launch_ms": lk_ms,
+                         "bytes_definition": "SURVEY 8(d) compulsory bytes per frame-pair x %d frame-pairs per launch" % B,
+                         "kernel_input_bytes": {"bytes_per_launch": lk_kernel_bytes,
+                                                "achieved": lk_kernel_bytes / (lk_ms * 1e-3) / 1e9,
+                                                "frac": lk_kernel_bytes / (lk_ms * 1e-3) / 1e9 / peaks["hbm_gbs"],
+                                                "what": "previous + current pyramids of every stream (what LK itself must read)"},
                          "whole_step": {"algorithmic_bytes_per_frame_pair": b_alg, "achieved": step_achieved,
                                         "frac": step_achieved / peaks["hbm_gbs"]},
                          "stage_ms": [float(v) for v in stage_ms],
                          "note": "latency/issue-bound: serial float chains imposed by bit-exactness, see DESIGN.md"},
         }
-        if world == 1 and not args.no_cpu_baseline:
-            line["cpu_baseline"] = cpu_baseline_single(4, 24)
+        if cpu is not None:
+            line["cpu_baseline"] = cpu
+            line["parity_check"] = parity
         print(json.dumps(line))
-    for ctx in ctxs:
-        ctx.close()
+    pipe.close()
     if world > 1:
         dist.destroy_process_group()
 
@@ -542,14 +566,17 @@ def run_gpu(args):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=16)
-    ap.add_argument("--warmup", type=int, default=4)
-    ap.add_argument("--batch", type=int, default=32)
-    ap.add_argument("--upload-group", type=int, default=8, help="sub-batches that share one H2D copy per camera (e2e loop)")
-    ap.add_argument("--host-threads", type=int, default=1, help="dispatcher threads of the end-to-end (host buffer) loop")
-    ap.add_argument("--contexts", type=int, default=32, help="sub-batches in flight on separate CUDA streams")
+    ap.add_argument("--steps", type=int, default=8)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--inner", type=int, default=128, help="passes (batches of frame-pairs) per step")
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--batch", type=int, default=0, help="streams per GPU (0: the config's)")
+    ap.add_argument("--workers", type=int, default=0, help="dispatcher threads (0: library default)")
+    ap.add_argument("--in-flight", type=int, default=0, help="steps in flight per stream, 1 or 2 (0: library default)")
+    ap.add_argument("--cpu-pairs", type=int, default=300, help="timed frame-pairs of the CPU baseline sample")
     ap.add_argument("--impl", default="kvfe", choices=["kvfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pin", action="store_true", help="do not pin the rank to the GPU's NUMA node")
     args = ap.parse_args()
     if args.warmup < 3:
         args.warmup = 3

@@ -22,7 +22,7 @@
 extern "C" {
 #endif
 
-#define KVFE_VERSION 1
+#define KVFE_VERSION 2
 
 typedef struct kvfe_ctx kvfe_ctx;
 
@@ -104,6 +104,12 @@ typedef struct {
   int32_t min_number_features;
   int32_t use_stereo_tracking, use_ransac;
   double max_disparity_since_lkf;
+  /* Mesher (next row downstream of the packet): Mesher::createMesh2dStereo + createMesh2dImpl
+   * (src/mesh/Mesher.cpp:1849-1886, :1712-1817) on every keyframe -- cv::Subdiv2D Delaunay triangulation of the
+   * keypoints with a VALID right match and a live landmark; the triangle list joins the packet. */
+  int32_t mesh_2d;                      /* 0 off (default), 1 on */
+  float subdiv_bounding_factor;         /* cv::Subdiv2D::initDelaunay: outer triangle at factor * max(w, h);
+                                           0 = 6 (OpenCV 4.13, this repo's oracle); OpenCV <= 4.5 used 3 */
 } kvfe_config;
 
 /* Stereo rig after cv::stereoRectify -- what StereoCamera::StereoCamera hands to its two
@@ -192,6 +198,14 @@ int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint8_t* right,
                        kvfe_stereo_out* out, uint8_t* left_rect, uint8_t* right_rect,
                        size_t rect_pitch);
 
+/* Mesher::createMesh2dImpl (src/mesh/Mesher.cpp:1712-1817): cv::Subdiv2D(rect(0, 0, width, height)), insert the
+ * keypoints that lie inside the image, getTriangleList, keep the triangles with all vertices inside.  triangles:
+ * 6 floats each (x0 y0 x1 y1 x2 y2) in cv::Subdiv2D's order; n_triangles may exceed max_triangles (then only the
+ * first max_triangles were written).  One mesh is inherently sequential (incremental insertion); the frame-level
+ * path builds the meshes of all streams of a batch concurrently (cfg.mesh_2d). */
+int kvfe_mesh_2d(kvfe_ctx* ctx, const float* kp_x, const float* kp_y, int n, float* triangles, int max_triangles,
+                 int* n_triangles);
+
 /* Tracker::geometricOutlierRejection2d2d (src/frontend/Tracker.cpp:213-319) on matched bearing
  * pairs: 2-point (TranslationOnlySacProblem, R12 given) or 5-point Nister (R12 == NULL).
  * inliers: ascending match indices; pose: row-major 3x4 [R|t]; status: kvfe_tracking_status. */
@@ -227,6 +241,8 @@ typedef struct {
   int64_t frame_id, timestamp;
   double lkf_T_k_mono[12], lkf_T_k_stereo[12], info_stereo[9];
   double median_disparity;
+  int32_t n_mesh_triangles;  /* cfg.mesh_2d: triangles of the keyframe's 2-D mesh (0 otherwise) */
+  int32_t reserved;
 } kvfe_packet_header;
 
 /* Byte layout of one stream's packet in the flat output buffer (cap = kvfe_max_keypoints()):
@@ -234,8 +250,10 @@ typedef struct {
  *   kp_x f32, kp_y f32, landmark i64, age i32, score f64 (always 0), versor f64 x3,
  *   left_status i32, left_rect_x f32, left_rect_y f32, right_status i32, right_rect_x f32,
  *   right_rect_y f32, depth f64, point3d f64 x3, right_x f32, right_y f32,
- *   smart_lmk i64, smart_uL f64, smart_uR f64, smart_v f64.
- * kvfe_packet_bytes() gives the stride; kvfe_packet_offsets() the offsets in that order. */
+ *   smart_lmk i64, smart_uL f64, smart_uR f64, smart_v f64,
+ *   mesh_tri f32 x6 (x0 y0 x1 y1 x2 y2 per triangle, 2*cap triangles; empty unless cfg.mesh_2d).
+ * kvfe_packet_bytes() gives the stride; kvfe_packet_offsets() the KVFE_PACKET_ARRAYS offsets in that order. */
+#define KVFE_PACKET_ARRAYS 21
 size_t kvfe_packet_bytes(const kvfe_ctx* ctx);
 int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries);
 
@@ -321,6 +339,82 @@ int kvfe_frontend_read_rectified(kvfe_ctx* ctx, int stream, uint8_t* rect_left,
                                  uint8_t* rect_right, size_t rect_pitch);
 int kvfe_sync(kvfe_ctx* ctx);
 void* kvfe_cuda_stream(kvfe_ctx* ctx);   /* cudaStream_t the context launches on */
+
+/* ---------------------------------------------------------------------------------------------
+ * Pipeline: the queue-in / queue-out shape the reference puts around its front-end
+ * (include/kimera-vio/pipeline/PipelineModule.h:190-232 spin(): getInputPacket -> spinOnce ->
+ * pushOutputPacket; :359-416 the SIMO module's input queue and output callbacks), for `n_streams`
+ * independent camera streams served by native dispatcher threads inside the library.
+ *
+ *   push   enqueues one stereo frame of one stream (FrontendInputPacketBase: images, timestamp and the
+ *          rotation the IMU front-end integrated) and returns at once;
+ *   pop    returns finished frames in COMPLETION order: the output packet (kvfe_packet_header + SoA
+ *          arrays, exactly the layout of kvfe_frontend_step) and, for keyframes, the rectified image
+ *          pair the reference materialises inside the StereoFrame (StereoFrame.h:71-87) -- all in
+ *          pinned host memory owned by the pipeline until kvfe_pipeline_release.
+ *
+ * One stream == one device-resident context; a frame costs the host one ~100-byte write into a
+ * mapped I/O block and ONE cudaGraphLaunch.  Images in pinned (cudaHostAlloc / cudaHostRegister'ed)
+ * memory are read by the SMs over the host link (zero-copy: no copy-engine queue between streams);
+ * images in pageable memory are staged through a pinned slot first; device pointers are read in
+ * place.  Input images must stay valid until the frame's output has been popped.  Outputs travel as
+ * SM stores into mapped host memory; completion is a sequence number the last kernel publishes, so
+ * the dispatchers issue no CUDA call besides the graph launch.
+ *
+ * rotation_mode 0: R = camLrectLkf_R_camLrectK (StereoVisionImuFrontend.cpp:149-150), which the caller
+ *   can only form after it has seen frame k-1's keyframe decision (one frame in flight per stream);
+ * rotation_mode 1: R = camLrectKm1_R_camLrectK, the rotation integrated between two consecutive frames;
+ *   the front-end accumulates it since the last keyframe itself, as the reference's front-end does with
+ *   the IMU measurements of its input packet (StereoVisionImuFrontend.cpp:140-150, :196-203), so
+ *   frames can be queued ahead without a host round trip.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct kvfe_pipeline kvfe_pipeline;
+typedef struct {
+  int32_t n_streams;        /* independent camera streams (cfg->batch is ignored: one context per stream) */
+  int32_t n_workers;        /* dispatcher threads (0 = default) */
+  int32_t queue_depth;      /* input queue capacity per stream (frames) */
+  int32_t output_slots;     /* output buffers per stream (>= 2); a stream stalls when all are unreleased */
+  int32_t want_rectified;   /* deliver the rectified image pair of every keyframe */
+  int32_t rotation_mode;    /* 0 / 1, see above */
+  int32_t checksum_outputs; /* the dispatcher reads every delivered byte (packet, rectified images) and
+                               returns a 64-bit checksum with the output */
+  int32_t max_in_flight;    /* steps in flight per stream on the GPU, 1 or 2 (0 = default 2) */
+} kvfe_pipeline_config;
+typedef struct {
+  int32_t stream, slot;     /* slot: pass back to kvfe_pipeline_release */
+  uint64_t tag;             /* the tag given at push */
+  int32_t is_keyframe, n_keypoints;
+  uint64_t checksum;        /* checksum_outputs: sum of the 64-bit words of the used part of the packet
+                               (+ the rectified images of a keyframe) */
+  const uint8_t* packet;    /* kvfe_pipeline_packet_bytes() bytes */
+  const uint8_t* rect_left; /* width*height dense, NULL unless want_rectified and is_keyframe */
+  const uint8_t* rect_right;
+} kvfe_pipeline_output;
+typedef struct {
+  int64_t frames_pushed, frames_done, graph_launches, kernel_launches;
+  double launch_seconds;    /* host time spent inside the launch path (I/O block write + cudaGraphLaunch) */
+  int64_t staged_copies;    /* frames whose images were in pageable memory and had to be staged */
+} kvfe_pipeline_stats;
+int kvfe_pipeline_create(const kvfe_config* cfg, const kvfe_rig* rig, const kvfe_pipeline_config* pc,
+                         kvfe_pipeline** out);
+void kvfe_pipeline_destroy(kvfe_pipeline* p);
+const char* kvfe_pipeline_last_error(const kvfe_pipeline* p);
+size_t kvfe_pipeline_packet_bytes(const kvfe_pipeline* p);
+int kvfe_pipeline_packet_offsets(const kvfe_pipeline* p, size_t* offsets, int max_entries);
+int kvfe_pipeline_max_keypoints(const kvfe_pipeline* p);
+/* KVFE_ERR_CAPACITY when the stream's input queue is full (nothing enqueued; retry later). */
+int kvfe_pipeline_push(kvfe_pipeline* p, int stream, const uint8_t* left, const uint8_t* right, size_t pitch,
+                       int64_t timestamp, const double* R, uint64_t tag);
+/* n frames with one call; returns the number accepted (stops at the first full queue) or < 0. */
+int kvfe_pipeline_push_many(kvfe_pipeline* p, int n, const int32_t* streams, const uint8_t* const* left,
+                            const uint8_t* const* right, size_t pitch, const int64_t* timestamps,
+                            const double* R, const uint64_t* tags);
+/* Up to max_n finished frames; blocks up to timeout_ms (0: poll) while none is ready.  Returns the count. */
+int kvfe_pipeline_pop(kvfe_pipeline* p, kvfe_pipeline_output* outs, int max_n, int timeout_ms);
+int kvfe_pipeline_release(kvfe_pipeline* p, const kvfe_pipeline_output* outs, int n);
+/* All streams back to the bootstrap state; the pipeline must be idle (every pushed frame popped). */
+int kvfe_pipeline_reset(kvfe_pipeline* p);
+int kvfe_pipeline_get_stats(kvfe_pipeline* p, kvfe_pipeline_stats* st);
 
 /* Debug taps of the last step for parity tests (stream-major, cap entries per stream). */
 int kvfe_debug_lk(kvfe_ctx* ctx, int stream, float* pred_x, float* pred_y, float* next_x,

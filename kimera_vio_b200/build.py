@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkvfe.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "rectify.cu", "pyramid.cu", "lk.cu", "gftt.cu", "select.cu", "stereo.cu", "ransac.cu", "fsm.cu"]
+SOURCES = ["api.cu", "pipeline.cu", "rectify.cu", "pyramid.cu", "lk.cu", "gftt.cu", "select.cu", "stereo.cu", "ransac.cu", "fsm.cu", "mesh.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-fmad=false",                       # IEEE op-by-op arithmetic; FMAs only where written
@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
             if verbose:
                 sys.stderr.write(r.stderr)
             objs.append(obj)
-    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart"]
+    cmd = [NVCC, "-shared", "-o", OUT, *objs, "-lcudart", "-lpthread"]
     r = subprocess.run(cmd, capture_output=True, text=True)
     if r.returncode != 0:
         sys.stderr.write(r.stdout + r.stderr)

@@ -23,6 +23,14 @@ static int set_err(kvfe_ctx* ctx, int code, const char* fmt, ...) {
   va_end(ap);
   return code;
 }
+int kvfe_set_err(kvfe_ctx* ctx, int code, const char* fmt, ...) {
+  char* dst = ctx ? ctx->err : g_create_err;
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(dst, 512, fmt, ap);
+  va_end(ap);
+  return code;
+}
 
 #define CU(call)                                                                              \
   do {                                                                                        \
@@ -62,6 +70,7 @@ extern "C" void kvfe_config_default(kvfe_config* c) {
   c->min_intra_keyframe_time_ns = 200000000LL; c->max_intra_keyframe_time_ns = 5000000000LL;
   c->min_number_features = 0; c->use_stereo_tracking = 1; c->use_ransac = 1;
   c->max_disparity_since_lkf = 1000.0;
+  c->mesh_2d = 0; c->subdiv_bounding_factor = 0.f;
 }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -85,10 +94,11 @@ static void make_cam(CamModel& c, const double* K, const double* D, const double
   t[6] = (S[3] * S[7] - S[4] * S[6]) * d; t[7] = (S[1] * S[6] - S[0] * S[7]) * d; t[8] = (S[0] * S[4] - S[1] * S[3]) * d;
 }
 
-static void packet_layout(int cap, size_t* off, size_t* total) {
-  const size_t sz[20] = {4, 4, 8, 4, 8, 24, 4, 4, 4, 4, 4, 4, 8, 24, 4, 4, 8, 8, 8, 8};
+static void packet_layout(int cap, bool mesh, size_t* off, size_t* total) {
+  // per keypoint-capacity unit; the mesh holds up to 2 * cap triangles of 6 floats
+  const size_t sz[KVFE_PACKET_ARRAYS] = {4, 4, 8, 4, 8, 24, 4, 4, 4, 4, 4, 4, 8, 24, 4, 4, 8, 8, 8, 8, mesh ? 48u : 0u};
   size_t o = round_up(sizeof(kvfe_packet_header), 16);
-  for (int i = 0; i < 20; ++i) { off[i] = o; o = round_up(o + sz[i] * (size_t)cap, 16); }
+  for (int i = 0; i < KVFE_PACKET_ARRAYS; ++i) { off[i] = o; o = round_up(o + sz[i] * (size_t)cap, 16); }
   *total = o;
 }
 
@@ -121,6 +131,19 @@ static std::vector<int> circle_half_widths(int r) {
   return hw;
 }
 
+// kvfe_create's failure path: the message goes where the caller can read it (kvfe_last_error(NULL)) and
+// everything allocated so far is released
+#define CUC(call)                                                                               \
+  do {                                                                                          \
+    cudaError_t e_ = (call);                                                                    \
+    if (e_ != cudaSuccess) {                                                                    \
+      set_err(nullptr, KVFE_ERR_CUDA, "%s failed: %s (%s:%d)", #call, cudaGetErrorString(e_),   \
+              __FILE__, __LINE__);                                                              \
+      kvfe_destroy(ctx);                                                                        \
+      return KVFE_ERR_CUDA;                                                                     \
+    }                                                                                           \
+  } while (0)
+extern "C" void kvfe_destroy(kvfe_ctx* ctx);
 extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx** out) {
   kvfe_ctx* ctx = nullptr;
   if (!cfg || !rig || !out) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "null argument");
@@ -144,6 +167,9 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   if (c.ransac_max_iterations < 1 || c.ransac_max_iterations > KVFE_MAX_RANSAC_ITERS)
     return set_err(nullptr, KVFE_ERR_INVALID_ARG, "ransac_max_iterations out of range");
   if ((c.templ_cols & 1) == 0 || (c.templ_rows & 1) == 0) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "template size must be odd");
+  if (c.pose_2d2d_algorithm != 1) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "pose_2d2d_algorithm must be 1 (NISTER)");
+  if (c.klt_max_level < 0 || c.klt_max_level >= KVFE_MAX_LEVELS) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "klt_max_level must be in [0,%d]", KVFE_MAX_LEVELS - 1);
+  if (c.min_distance < 0) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "min_distance must be >= 0");
 
   ctx = new kvfe_ctx();
   memset(ctx, 0, sizeof(*ctx));
@@ -217,35 +243,39 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   make_cam(ctx->cam[0], rig->K_left, rig->D_left, rig->R1, rig->P1);
   make_cam(ctx->cam[1], rig->K_right, rig->D_right, rig->R2, rig->P2);
 
-  CU(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
+  CUC(cudaGetDevice(&ctx->device));
+  CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));
   const size_t B = dc.B;
-  CU(dmalloc(&ctx->d_cam, 2));
-  CU(cudaMemcpy(ctx->d_cam, ctx->cam, sizeof(CamModel) * 2, cudaMemcpyHostToDevice));
-  for (int k = 0; k < 2; ++k) CU(dmalloc(&db.pyr[k], B * dc.pyr_stride));
-  CU(dmalloc(&db.right_raw, B * dc.img_stride));
+  CUC(dmalloc(&ctx->d_cam, 2));
+  CUC(cudaMemcpy(ctx->d_cam, ctx->cam, sizeof(CamModel) * 2, cudaMemcpyHostToDevice));
+  for (int k = 0; k < 2; ++k) CUC(dmalloc(&db.pyr[k], B * dc.pyr_stride));
+  CUC(dmalloc(&db.right_raw, B * dc.img_stride));
   // fixed-point remap tables (cv::convertMaps-style: integer source pixel + 5+5 fractional bits),
   // computed once per rig from the in-register f64 map model
   for (int k = 0; k < 2; ++k) {
-    CU(dmalloc(&db.rmap[k], (size_t)dc.W * dc.H));
+    CUC(dmalloc(&db.rmap[k], (size_t)dc.W * dc.H));
     launch_rmap_table(dc, ctx->d_cam, k, db.rmap[k], ctx->stream);
   }
-  CU(cudaStreamSynchronize(ctx->stream));
-  CU(cudaGetLastError());
-  CU(dmalloc(&db.rectL, B * dc.img_stride));
-  CU(dmalloc(&db.rectR, B * dc.img_stride));
-  CU(dmalloc(&db.mask, B * dc.img_stride));
-  CU(dmalloc(&db.eig, B * (size_t)dc.W * dc.H));
-  CU(dmalloc(&db.eig_max, B));
-  CU(dmalloc(&db.cand, B * (size_t)dc.cand_cap));
-  CU(dmalloc(&db.cand_n, B));
-  CU(dmalloc(&db.corner_idx, B * (size_t)dc.max_before_anms));
-  CU(dmalloc(&db.corner_n, B));
-  CU(dmalloc(&db.new_x, B * cap)); CU(dmalloc(&db.new_y, B * cap)); CU(dmalloc(&db.new_n, B));
+  CUC(cudaStreamSynchronize(ctx->stream));
+  CUC(cudaGetLastError());
+  CUC(dmalloc(&db.rectL, B * dc.img_stride));
+  CUC(dmalloc(&db.rectR, B * dc.img_stride));
+  CUC(dmalloc(&db.mask, B * dc.img_stride));
+  CUC(dmalloc(&db.eig, B * (size_t)dc.W * dc.H));
+  CUC(dmalloc(&db.eig_max, B));
+  CUC(dmalloc(&db.cand, B * (size_t)dc.cand_cap));
+  CUC(dmalloc(&db.cand_n, B));
+  CUC(dmalloc(&db.corner_idx, B * (size_t)dc.max_before_anms));
+  CUC(dmalloc(&db.corner_n, B));
+  CUC(dmalloc(&db.new_x, B * cap)); CUC(dmalloc(&db.new_y, B * cap)); CUC(dmalloc(&db.new_n, B));
   {
     int cell = std::max(dc.min_distance, 1);
     size_t ncells = (size_t)((dc.W + cell - 1) / cell) * ((dc.H + cell - 1) / cell);
-    db.scratch_stride = round_up(3 * (size_t)dc.cand_cap + ncells + 64 + 5 * (size_t)(dc.ransac_iters + 1) + cap, 64);
-    CU(dmalloc(&db.scratch_i, B * db.scratch_stride));
+    // sort_greedy_kernel's global sections: cstart[ncells+1] | head[ncells] | newacc[ncells] | state[cand_cap bytes] |
+    // tmp[cand_cap u64]; the RANSAC kernels use 5 * (iters + 1) + cap ints of the same block
+    const size_t greedy = 3 * ncells + 8 + (size_t)dc.cand_cap / 4 + 2 + 2 * (size_t)dc.cand_cap;
+    db.scratch_stride = round_up(std::max(greedy, 3 * (size_t)dc.cand_cap + ncells) + 64 + 5 * (size_t)(dc.ransac_iters + 1) + cap, 64);
+    CUC(dmalloc(&db.scratch_i, B * db.scratch_stride));
   }
   // all-equal-keys std::sort permutations (cv::sortIdx descending): perm(N) at offset N(N-1)/2
   {
@@ -259,8 +289,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
       std::reverse(idx.begin(), idx.end());
       for (int i = 0; i < N; ++i) tab[(size_t)N * (N - 1) / 2 + i] = (unsigned short)idx[i];
     }
-    CU(dmalloc(&db.sort_perm, tab.size()));
-    CU(cudaMemcpy(db.sort_perm, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
+    CUC(dmalloc(&db.sort_perm, tab.size()));
+    CUC(cudaMemcpy(db.sort_perm, tab.data(), tab.size() * sizeof(unsigned short), cudaMemcpyHostToDevice));
   }
   // OpenGV rnd(): uniform_int_distribution<int>(0, INT_MAX)(mt19937(12345)), both libstdc++ algorithms
   {
@@ -273,60 +303,64 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
       else if (r < 0x80000000u) tab[i++] = (int)r;
     }
     db.rnd_n = n;
-    CU(dmalloc(&db.rnd_table, n));
-    CU(cudaMemcpy(db.rnd_table, tab.data(), n * sizeof(int), cudaMemcpyHostToDevice));
+    CUC(dmalloc(&db.rnd_table, n));
+    CUC(cudaMemcpy(db.rnd_table, tab.data(), n * sizeof(int), cudaMemcpyHostToDevice));
   }
   {
     std::vector<float> m = subpix_mask_table(std::max(dc.subpix_win, 1));
-    CU(dmalloc(&db.subpix_mask, m.size()));
-    CU(cudaMemcpy(db.subpix_mask, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUC(dmalloc(&db.subpix_mask, m.size()));
+    CUC(cudaMemcpy(db.subpix_mask, m.data(), m.size() * sizeof(float), cudaMemcpyHostToDevice));
     std::vector<float> m2 = subpix_mask_table(10);
-    CU(dmalloc(&db.subpix_mask_stereo, m2.size()));
-    CU(cudaMemcpy(db.subpix_mask_stereo, m2.data(), m2.size() * sizeof(float), cudaMemcpyHostToDevice));
+    CUC(dmalloc(&db.subpix_mask_stereo, m2.size()));
+    CUC(cudaMemcpy(db.subpix_mask_stereo, m2.data(), m2.size() * sizeof(float), cudaMemcpyHostToDevice));
   }
   {
     int r = std::max(dc.min_distance, 0);
     std::vector<int> hw = circle_half_widths(r);
     ctx->circle_r = r;
-    CU(dmalloc(&ctx->circle_hw, hw.size()));
-    CU(cudaMemcpy(ctx->circle_hw, hw.data(), hw.size() * sizeof(int), cudaMemcpyHostToDevice));
+    CUC(dmalloc(&ctx->circle_hw, hw.size()));
+    CUC(cudaMemcpy(ctx->circle_hw, hw.data(), hw.size() * sizeof(int), cudaMemcpyHostToDevice));
   }
-  CU(dmalloc(&db.lk_px, B * cap)); CU(dmalloc(&db.lk_py, B * cap));
-  CU(dmalloc(&db.lk_qx, B * cap)); CU(dmalloc(&db.lk_qy, B * cap));
-  CU(dmalloc(&db.lk_pred_x, B * cap)); CU(dmalloc(&db.lk_pred_y, B * cap));
-  CU(dmalloc(&db.lk_src, B * cap)); CU(dmalloc(&db.lk_status, B * cap));
-  CU(dmalloc(&db.m_ref, B * cap)); CU(dmalloc(&db.m_cur, B * cap)); CU(dmalloc(&db.m_n, B));
-  CU(dmalloc(&db.inl, B * cap)); CU(dmalloc(&db.inl_n, B));
+  CUC(dmalloc(&db.lk_px, B * cap)); CUC(dmalloc(&db.lk_py, B * cap));
+  CUC(dmalloc(&db.lk_qx, B * cap)); CUC(dmalloc(&db.lk_qy, B * cap));
+  CUC(dmalloc(&db.lk_pred_x, B * cap)); CUC(dmalloc(&db.lk_pred_y, B * cap));
+  CUC(dmalloc(&db.lk_src, B * cap)); CUC(dmalloc(&db.lk_status, B * cap));
+  CUC(dmalloc(&db.m_ref, B * cap)); CUC(dmalloc(&db.m_cur, B * cap)); CUC(dmalloc(&db.m_n, B));
+  CUC(dmalloc(&db.inl, B * cap)); CUC(dmalloc(&db.inl_n, B));
   db.rs_stride = round_up(6 * (size_t)cap + 12 * (size_t)std::max(dc.ransac_iters + 1, 32) + 16 * (size_t)cap, 32);
-  CU(dmalloc(&db.rs_d, B * db.rs_stride));
+  CUC(dmalloc(&db.rs_d, B * db.rs_stride));
   {
     FrameSoA& f = db.fr;
     size_t n = B * 3 * cap;
-    CU(dmalloc(&f.n, B * 3)); CU(dmalloc(&f.timestamp, B * 3)); CU(dmalloc(&f.frame_id, B * 3));
-    CU(dmalloc(&f.kx, n)); CU(dmalloc(&f.ky, n)); CU(dmalloc(&f.lmk, n)); CU(dmalloc(&f.age, n));
-    CU(dmalloc(&f.versor, 3 * n)); CU(dmalloc(&f.lstat, n)); CU(dmalloc(&f.lrx, n)); CU(dmalloc(&f.lry, n));
-    CU(dmalloc(&f.rstat, n)); CU(dmalloc(&f.mstat, n)); CU(dmalloc(&f.rrx, n)); CU(dmalloc(&f.rry, n)); CU(dmalloc(&f.depth, n));
-    CU(dmalloc(&f.p3d, 3 * n)); CU(dmalloc(&f.rkx, n)); CU(dmalloc(&f.rky, n));
+    CUC(dmalloc(&f.n, B * 3)); CUC(dmalloc(&f.timestamp, B * 3)); CUC(dmalloc(&f.frame_id, B * 3));
+    CUC(dmalloc(&f.kx, n)); CUC(dmalloc(&f.ky, n)); CUC(dmalloc(&f.lmk, n)); CUC(dmalloc(&f.age, n));
+    CUC(dmalloc(&f.versor, 3 * n)); CUC(dmalloc(&f.lstat, n)); CUC(dmalloc(&f.lrx, n)); CUC(dmalloc(&f.lry, n));
+    CUC(dmalloc(&f.rstat, n)); CUC(dmalloc(&f.mstat, n)); CUC(dmalloc(&f.rrx, n)); CUC(dmalloc(&f.rry, n)); CUC(dmalloc(&f.depth, n));
+    CUC(dmalloc(&f.p3d, 3 * n)); CUC(dmalloc(&f.rkx, n)); CUC(dmalloc(&f.rky, n));
   }
-  CU(dmalloc(&db.st, B));
-  packet_layout(cap, db.pk_off, &db.packet_bytes);
-  CU(dmalloc(&db.packets, B * db.packet_bytes));
-  CU(cudaMallocHost((void**)&ctx->h_stage, 2 * B * dc.img_stride));
-  CU(cudaMallocHost((void**)&ctx->h_packets, B * db.packet_bytes));
+  CUC(dmalloc(&db.st, B));
+  dc.mesh_on = c.mesh_2d ? 1 : 0;
+  dc.subdiv_factor = c.subdiv_bounding_factor > 0.f ? c.subdiv_bounding_factor : 6.f;
+  packet_layout(cap, dc.mesh_on != 0, db.pk_off, &db.packet_bytes);
+  launch_mesh_init(dc);
+  if (!mesh_fits_smem(dc)) CUC(dmalloc(&db.mesh_ws, (dc.mesh_on ? B : 1) * mesh_global_ws_ints(dc)));
+  CUC(dmalloc(&db.packets, B * db.packet_bytes));
+  CUC(cudaMallocHost((void**)&ctx->h_stage, 2 * B * dc.img_stride));
+  CUC(cudaMallocHost((void**)&ctx->h_packets, B * db.packet_bytes));
   ctx->io_pk_off = (B * (sizeof(long long) + 9 * sizeof(double)) + 255) & ~(size_t)255;
   for (int i = 0; i < 2; ++i) {
-    CU(cudaMallocHost((void**)&ctx->h_io[i], ctx->io_pk_off + B * db.packet_bytes));
-    CU(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
+    CUC(cudaMallocHost((void**)&ctx->h_io[i], ctx->io_pk_off + B * db.packet_bytes));
+    CUC(cudaEventCreateWithFlags(&ctx->pipe_done[i], cudaEventDisableTiming));
   }
-  CU(cudaMallocHost((void**)&ctx->h_ts, KVFE_IN_SLOTS * B * sizeof(long long)));
-  CU(cudaMallocHost((void**)&ctx->h_Rin, KVFE_IN_SLOTS * B * 9 * sizeof(double)));
-  for (int i = 0; i < KVFE_IN_SLOTS; ++i) CU(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
+  CUC(cudaMallocHost((void**)&ctx->h_ts, KVFE_IN_SLOTS * B * sizeof(long long)));
+  CUC(cudaMallocHost((void**)&ctx->h_Rin, KVFE_IN_SLOTS * B * 9 * sizeof(double)));
+  for (int i = 0; i < KVFE_IN_SLOTS; ++i) CUC(cudaEventCreateWithFlags(&ctx->in_ev[i], cudaEventDisableTiming));
   ctx->in_bytes = B * (sizeof(long long) + 9 * sizeof(double));
-  CU(dmalloc(&ctx->d_in, ctx->in_bytes));
+  CUC(dmalloc(&ctx->d_in, ctx->in_bytes));
   ctx->d_ts = reinterpret_cast<long long*>(ctx->d_in);
   ctx->d_Rin = reinterpret_cast<double*>(ctx->d_in + B * sizeof(long long));
   ctx->launches += launch_reset(dc, db, ctx->stream);
-  CU(cudaStreamSynchronize(ctx->stream));
+  CUC(cudaStreamSynchronize(ctx->stream));
   ctx->cur_slot = 0;
   {
     const char* e = getenv("KVFE_NO_GRAPH");
@@ -336,7 +370,13 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
     const char* c = getenv("KVFE_GRAPH_COND");
     ctx->use_cond = (c && c[0] == '1');
   }
-  CU(dmalloc(&ctx->d_kf_steps, 1));
+  CUC(dmalloc(&ctx->d_kf_steps, 1));
+  CUC(dmalloc(&ctx->d_pub_count, 1));
+  for (int i = 0; i < 2; ++i) {
+    const size_t bytes = KVFE_STEPIO_ARRAYS + B * (sizeof(long long) + 9 * sizeof(double));
+    CUC(cudaMallocHost((void**)&ctx->pio[i], bytes));
+    memset(ctx->pio[i], 0, bytes);
+  }
   *out = ctx;
   return KVFE_OK;
 }
@@ -345,7 +385,11 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   if (!ctx) return;
   cudaStreamSynchronize(ctx->stream);
   DevBuf& db = ctx->db;
-  void* ptrs[] = {ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->pipe_graph_ready[i]) cudaGraphExecDestroy(ctx->pipe_graph[i]);
+    if (ctx->pio[i]) cudaFreeHost(ctx->pio[i]);
+  }
+  void* ptrs[] = {db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
                   db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
@@ -385,7 +429,7 @@ extern "C" int kvfe_kernel_launches(const kvfe_ctx* ctx) {
 extern "C" size_t kvfe_packet_bytes(const kvfe_ctx* ctx) { return ctx ? ctx->db.packet_bytes : 0; }
 extern "C" int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries) {
   if (!ctx || !offsets) return KVFE_ERR_INVALID_ARG;
-  int n = std::min(max_entries, 20);
+  int n = std::min(max_entries, KVFE_PACKET_ARRAYS);
   for (int i = 0; i < n; ++i) offsets[i] = ctx->db.pk_off[i];
   return n;
 }
@@ -597,7 +641,7 @@ extern "C" int kvfe_track(kvfe_ctx* ctx, const uint8_t* ref_img, const uint8_t* 
   RET(upload_image(ctx, db.pyr[1] + dc.lvl_off[0], dc.pitch, cur_img, pitch));
   ctx->launches += launch_pyramid(dc, db.pyr[0], 1, ctx->stream);
   ctx->launches += launch_pyramid(dc, db.pyr[1], 1, ctx->stream);
-  ctx->launches += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, ctx->stream);
+  ctx->launches += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, nullptr, ctx->stream);
   ctx->launches += launch_track_pre(dc, db, ctx->stream);
   ctx->launches += launch_lk(dc, db, 0, 1, ctx->stream);
   CHECK_LAUNCH();
@@ -681,6 +725,31 @@ extern "C" int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint
   if (left_rect) RET(download_image(ctx, left_rect, rect_pitch, db.rectL, dc.pitch));
   if (right_rect) RET(download_image(ctx, right_rect, rect_pitch, db.rectR, dc.pitch));
   CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_mesh_2d(kvfe_ctx* ctx, const float* kp_x, const float* kp_y, int n, float* triangles, int max_triangles,
+                            int* n_triangles) {
+  if (!ctx || !kp_x || !kp_y || !triangles || !n_triangles || max_triangles < 0) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc;
+  if (n < 0 || n > dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, dc.cap);
+  *n_triangles = 0;
+  if (n == 0) return KVFE_OK;                     // Mesher.cpp:1716
+  float* d = nullptr;
+  const size_t mt = (size_t)std::min(max_triangles, 2 * n + 8);
+  CU(cudaMalloc((void**)&d, (2 * (size_t)n + 6 * mt + 2) * sizeof(float)));
+  float* dtri = d + 2 * n; int* dn = reinterpret_cast<int*>(dtri + 6 * mt);
+  CU(cudaMemcpyAsync(d, kp_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(d + n, kp_y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_mesh_raw(dc, ctx->db, d, d + n, n, dtri, (int)mt, dn, ctx->stream);
+  CHECK_LAUNCH();
+  int nt = 0;
+  CU(cudaMemcpyAsync(&nt, dn, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  const size_t copy = std::min((size_t)nt, mt);
+  if (copy) CU(cudaMemcpy(triangles, dtri, copy * 6 * sizeof(float), cudaMemcpyDeviceToHost));
+  cudaFree(d);
+  *n_triangles = nt;
   return KVFE_OK;
 }
 
@@ -792,11 +861,11 @@ extern "C" int kvfe_frontend_reset(kvfe_ctx* ctx) {
 // pyr[cur_slot] level 0 (left) and right_raw (right).  Three parts: (1) tracking up to the keyframe
 // decision, (2) the keyframe / detection part (every kernel of it exits at entry for a stream in
 // plain tracking mode), (3) packet assembly.
-static int enqueue_part_track(kvfe_ctx* ctx, unsigned long long cond, long long* n_launch) {
+static int enqueue_part_track(kvfe_ctx* ctx, unsigned long long cond, long long* n_launch, const StepIO* io = nullptr) {
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const int cur = ctx->cur_slot, prev = cur ^ 1;
   long long n = 0;
-  n += launch_prep(dc, db, ctx->d_cam, ctx->in_ts ? ctx->in_ts : ctx->d_ts, ctx->in_R ? ctx->in_R : ctx->d_Rin, s);
+  n += launch_prep(dc, db, ctx->d_cam, ctx->in_ts ? ctx->in_ts : ctx->d_ts, ctx->in_R ? ctx->in_R : ctx->d_Rin, io, s);
   n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
   n += launch_track_pre(dc, db, s);
   n += launch_lk(dc, db, prev, cur, s);
@@ -835,6 +904,7 @@ __global__ void kvfe_empty_kernel() {}
 
 static int enqueue_part_finalize(kvfe_ctx* ctx, long long* n_launch) {
   *n_launch += launch_finalize(ctx->dc, ctx->db, ctx->stream);
+  if (ctx->dc.mesh_on) *n_launch += launch_mesh(ctx->dc, ctx->db, ctx->stream);
   if (const char* e = getenv("KVFE_EXTRA_LAUNCHES"))      // diagnostic: dispatch-rate sensitivity
     for (int i = 0; i < atoi(e); ++i) kvfe_empty_kernel<<<1, 32, 0, ctx->stream>>>();
   CU(cudaGetLastError());
@@ -844,6 +914,13 @@ static int enqueue_part_finalize(kvfe_ctx* ctx, long long* n_launch) {
 static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch) {
   *n_launch = 0;
   RET(enqueue_part_track(ctx, 0ull, n_launch));
+  RET(enqueue_part_keyframe(ctx, nullptr, n_launch));
+  return enqueue_part_finalize(ctx, n_launch);
+}
+// the same sequence with the step inputs taken from a pipeline I/O block (pipeline.cu)
+int kvfe_enqueue_step_kernels(kvfe_ctx* ctx, const StepIO* io, long long* n_launch) {
+  *n_launch = 0;
+  RET(enqueue_part_track(ctx, 0ull, n_launch, io));
   RET(enqueue_part_keyframe(ctx, nullptr, n_launch));
   return enqueue_part_finalize(ctx, n_launch);
 }
@@ -1248,7 +1325,7 @@ extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_d
   for (auto& e : ev) CU(cudaEventCreate(&e));
   long long n = 0;
   CU(cudaEventRecord(ev[0], s));
-  n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, s);
+  n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, nullptr, s);
   n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
   CU(cudaEventRecord(ev[1], s));
   n += launch_track_pre(dc, db, s);
@@ -1273,6 +1350,7 @@ extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_d
   CU(cudaEventRecord(ev[7], s));
   n += launch_sparse_stereo(dc, db, ctx->d_cam, M_BOOT | M_KF, 1, s);
   n += launch_finalize(dc, db, s);
+  if (dc.mesh_on) n += launch_mesh(dc, db, s);
   CU(cudaEventRecord(ev[8], s));
   CU(cudaGetLastError());
   CU(cudaStreamSynchronize(s));

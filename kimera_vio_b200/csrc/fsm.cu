@@ -24,18 +24,36 @@ __global__ void reset_kernel(DevCfg dc, DevBuf db) {
   s.lmk_next = 0; s.need = 0; s.n_existing = 0; s.n_ref = 0; s.n_new = 0; s.use_pred = 0; s.given_rot = 0;
   s.nr_tracked = s.nr_mono_put = s.nr_mono_inl = s.nr_stereo_put = s.nr_stereo_inl = 0;
   s.median_disparity = 0;
-  for (int i = 0; i < 9; ++i) { s.kf_R_ref[i] = (i % 4 == 0) ? 1.0 : 0.0; s.info_stereo[i] = 0; }
+  for (int i = 0; i < 9; ++i) { s.kf_R_ref[i] = (i % 4 == 0) ? 1.0 : 0.0; s.acc_R[i] = s.kf_R_ref[i]; s.info_stereo[i] = 0; }
   for (int i = 0; i < 12; ++i) { s.pose_mono[i] = (i % 5 == 0) ? 1.0 : 0.0; s.pose_stereo[i] = s.pose_mono[i]; }
   for (int k = 0; k < 3; ++k) db.fr.n[b * 3 + k] = 0;
 }
 
+// `io` (may be null): the step inputs come from the pipeline's mapped I/O block instead of ts / Rin; with
+// io->rot_mode == 1 the rotation given is km1_R_cur (what the gyroscope integrates between two frames) and
+// keyframe_R_cur is accumulated here, exactly like the IMU front-end's preintegration that the reference's
+// front-end owns and resets at keyframes (StereoVisionImuFrontend.cpp:140-150, :196-203).
 __global__ void prep_kernel(DevCfg dc, DevBuf db, const CamModel* __restrict__ cams,
-                            const long long* __restrict__ ts, const double* __restrict__ Rin) {
+                            const long long* __restrict__ ts, const double* __restrict__ Rin,
+                            const StepIO* __restrict__ io) {
   int b = blockIdx.x * blockDim.x + threadIdx.x;
   if (b >= dc.B) return;
   StreamState& s = db.st[b];
+  int rot_mode = 0;
+  if (io) {
+    const unsigned char* arr = reinterpret_cast<const unsigned char*>(io) + KVFE_STEPIO_ARRAYS;
+    ts = reinterpret_cast<const long long*>(arr);
+    Rin = reinterpret_cast<const double*>(arr + (size_t)dc.B * sizeof(long long));
+    rot_mode = io->rot_mode;
+  }
   s.timestamp = ts[b];
-  for (int i = 0; i < 9; ++i) s.kf_R_cur[i] = Rin[9 * b + i];
+  if (rot_mode == 1) {
+    double Rk[9];
+    for (int i = 0; i < 9; ++i) Rk[i] = Rin[9 * b + i];
+    matmul3(s.acc_R, Rk, s.kf_R_cur);
+  } else {
+    for (int i = 0; i < 9; ++i) s.kf_R_cur[i] = Rin[9 * b + i];
+  }
   s.n_ref = 0; s.n_new = 0;
   if (s.frame_count == 0) {
     s.mode = 0; s.slot_k = 0; s.slot_km1 = 0; s.slot_lkf = 0;
@@ -352,6 +370,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(DevCfg dc, DevBuf db) {
     for (int i = 0; i < 12; ++i) { h->lkf_T_k_mono[i] = s.pose_mono[i]; h->lkf_T_k_stereo[i] = s.pose_stereo[i]; }
     for (int i = 0; i < 9; ++i) h->info_stereo[i] = s.info_stereo[i];
     h->median_disparity = s.median_disparity;
+    h->n_mesh_triangles = 0; h->reserved = 0;          // mesh_kernel fills it in on keyframes (cfg.mesh_2d)
+    // rotation accumulated since the last keyframe (rotation input mode 1)
+    for (int i = 0; i < 9; ++i) s.acc_R[i] = is_kf ? ((i % 4 == 0) ? 1.0 : 0.0) : s.kf_R_cur[i];
     // state update (StereoVisionImuFrontend.cpp:268-271, :317-319, :447-475)
     if (mode == 0) { s.slot_km1 = s.slot_k; s.slot_lkf = s.slot_k; }
     else if (mode == 3) { s.slot_km1 = s.slot_k; }
@@ -373,8 +394,8 @@ int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
   return 1;
 }
 int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const long long* ts,
-                const double* Rin, cudaStream_t s) {
-  prep_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, d_cam, ts, Rin);
+                const double* Rin, const StepIO* io, cudaStream_t s) {
+  prep_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, d_cam, ts, Rin, io);
   return 1;
 }
 int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
@@ -428,6 +449,102 @@ __global__ void __launch_bounds__(256) fetch_kernel(const unsigned char* __restr
 int launch_fetch(const unsigned char* srcL, const unsigned char* srcR, unsigned char* dstL, size_t dstL_stride,
                  unsigned char* dstR, size_t dstR_stride, size_t img, int B, cudaStream_t s) {
   fetch_kernel<<<dim3(24, B, 2), 256, 0, s>>>(srcL, srcR, dstL, dstL_stride, dstR, dstR_stride, img);
+  return 1;
+}
+// ---- pipeline step: image fetch and output publication through the mapped I/O block -----------------
+// The source pointers are read from the I/O block, so ONE captured graph serves every step.  A source in
+// pinned host memory is read by the SMs over the host link (zero-copy): no copy-engine operation, hence
+// no in-order copy queue shared between contexts and no small-copy inefficiency (a 361 KB cudaMemcpyAsync
+// reaches well under half of the link rate).  Every thread keeps four 16-byte loads in flight.
+// grid (x, B, 2): y = image of the batch, z = camera.
+__global__ void __launch_bounds__(256) fetch_io_kernel(DevCfg dc, const StepIO* __restrict__ io, unsigned char* __restrict__ dstL,
+                                                       unsigned char* __restrict__ dstR) {
+  const size_t sp = (size_t)io->src_pitch;
+  const unsigned char* src = (blockIdx.z ? io->srcR : io->srcL) + (size_t)blockIdx.y * sp * dc.H;
+  unsigned char* dst = blockIdx.z ? dstR + (size_t)blockIdx.y * dc.img_stride : dstL + (size_t)blockIdx.y * dc.pyr_stride;
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if (sp == (size_t)dc.W && dc.pitch == dc.W && (((size_t)src | (size_t)dst) & 15) == 0) {
+    const size_t img = (size_t)dc.W * dc.H, n16 = img / 16;
+    const uint4* s4 = reinterpret_cast<const uint4*>(src);
+    uint4* d4 = reinterpret_cast<uint4*>(dst);
+    for (size_t i = tid; i < n16; i += 4 * nth) {
+      uint4 v[4];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (i + u * nth < n16) v[u] = s4[i + u * nth];
+#pragma unroll
+      for (int u = 0; u < 4; ++u) if (i + u * nth < n16) d4[i + u * nth] = v[u];
+    }
+    for (size_t i = n16 * 16 + tid; i < img; i += nth) dst[i] = src[i];
+  } else {
+    const size_t n = (size_t)dc.W * dc.H;
+    for (size_t i = tid; i < n; i += nth) {
+      const size_t y = i / dc.W, x = i - y * dc.W;
+      dst[y * dc.pitch + x] = src[y * sp + x];
+    }
+  }
+}
+int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s) {
+  const int gx = (int)(((size_t)dc.W * dc.H / 16 + 4 * 256 - 1) / (4 * 256));
+  fetch_io_kernel<<<dim3(gx < 1 ? 1 : (gx > 96 ? 96 : gx), dc.B, 2), 256, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw);
+  return 1;
+}
+
+// Last kernel of a pipeline step: the SMs store the packets and -- for the streams whose frame became a
+// keyframe -- the rectified image pair (part of the output StereoFrame, include/kimera-vio/frontend/
+// StereoFrame.h:71-87) into the mapped host buffers the I/O block names; the last CTA to finish fences
+// and publishes the step's sequence number, which is all the dispatcher polls.
+__global__ void __launch_bounds__(256) publish_io_kernel(DevCfg dc, DevBuf db, StepIO* io, unsigned int* counter) {
+  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
+  if (io->dst_packets) {
+    // header, then of every array only the entries in use (a packet's capacity is ~2.3x its typical content)
+    const unsigned sz[KVFE_PACKET_ARRAYS] = {4, 4, 8, 4, 8, 24, 4, 4, 4, 4, 4, 4, 8, 24, 4, 4, 8, 8, 8, 8, 24};
+    for (int b = 0; b < dc.B; ++b) {
+      const unsigned char* src = db.packets + (size_t)b * db.packet_bytes;
+      unsigned char* dst = io->dst_packets + (size_t)b * db.packet_bytes;
+      const kvfe_packet_header* h = reinterpret_cast<const kvfe_packet_header*>(src);
+      const int n = h->n, ns = h->n_smart, nt = h->n_mesh_triangles;
+      for (int a = -1; a < KVFE_PACKET_ARRAYS; ++a) {
+        const size_t off = a < 0 ? 0 : db.pk_off[a];
+        const size_t bytes = a < 0 ? sizeof(kvfe_packet_header) : (size_t)sz[a] * (size_t)(a == 20 ? nt : a >= 16 ? ns : n);
+        const size_t n16 = (bytes + 15) / 16;       // arrays start 16-byte aligned and are padded to 16 bytes
+        const uint4* s4 = reinterpret_cast<const uint4*>(src + off);
+        uint4* d4 = reinterpret_cast<uint4*>(dst + off);
+        for (size_t i = tid; i < n16; i += nth) d4[i] = s4[i];
+      }
+    }
+  }
+  if (io->dst_rectL && io->dst_rectR) {
+    const size_t img = (size_t)dc.W * dc.H;
+    for (int b = 0; b < dc.B; ++b) {
+      const int mode = db.st[b].mode;
+      if (!(mode == 0 || mode == 2)) continue;
+      for (int cam = 0; cam < 2; ++cam) {
+        const unsigned char* src = (cam ? db.rectR : db.rectL) + (size_t)b * dc.img_stride;
+        unsigned char* dst = (cam ? io->dst_rectR : io->dst_rectL) + (size_t)b * img;
+        if (dc.pitch == dc.W && (((size_t)dst) & 15) == 0) {
+          const size_t n16 = img / 16;
+          for (size_t i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
+          for (size_t i = n16 * 16 + tid; i < img; i += nth) dst[i] = src[i];
+        } else {
+          for (size_t i = tid; i < img; i += nth) { const size_t y = i / dc.W, x = i - y * dc.W; dst[i] = src[y * dc.pitch + x]; }
+        }
+      }
+    }
+  }
+  __threadfence_system();
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    const unsigned int done = atomicAdd(counter, 1u);
+    if (done == gridDim.x - 1) {
+      *counter = 0;
+      __threadfence_system();
+      io->done_seq = io->seq;
+      __threadfence_system();
+    }
+  }
+}
+int launch_publish_io(const DevCfg& dc, const DevBuf& db, StepIO* io, unsigned int* counter, cudaStream_t s) {
+  publish_io_kernel<<<16, 256, 0, s>>>(dc, db, io, counter);
   return 1;
 }
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {

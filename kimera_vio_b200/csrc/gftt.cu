@@ -289,12 +289,16 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   // bookkeeping arrays: shared memory when the grid and the candidate list fit, else global scratch
   unsigned char* sm_tail = reinterpret_cast<unsigned char*>(skeys + smem_keys + GREEDY_ACC_MAX);
   const bool small = (ncells + 1 <= GREEDY_SMEM_CELLS) && (n <= smem_keys);
+  // global-scratch sections are sized from the cell grid (min_distance 1 gives one cell per pixel);
+  // kvfe_create sizes scratch_stride with the same formula (greedy_scratch_ints)
+  const int o_head = (ncells + 1 + 3) & ~3, o_new = o_head + ncells, o_state = o_new + ncells;
+  const int o_tmp = (o_state + dc.cand_cap / 4 + 1) & ~1;
   int* cstart = small ? reinterpret_cast<int*>(sm_tail) : sc;                                   // [ncells + 1]
-  int* head = small ? cstart + GREEDY_SMEM_CELLS : sc + (dc.cand_cap / 4);                      // [ncells]
-  int* newacc = small ? head + GREEDY_SMEM_CELLS : sc + 2 * (dc.cand_cap / 4);                  // [ncells]
+  int* head = small ? cstart + GREEDY_SMEM_CELLS : sc + o_head;                                 // [ncells]
+  int* newacc = small ? head + GREEDY_SMEM_CELLS : sc + o_new;                                  // [ncells]
   unsigned char* state = small ? reinterpret_cast<unsigned char*>(newacc + GREEDY_SMEM_CELLS)
-                               : reinterpret_cast<unsigned char*>(sc + 3 * (dc.cand_cap / 4)); // [n]
-  unsigned long long* tmp = reinterpret_cast<unsigned long long*>(sc + dc.cand_cap);            // [cand_cap] keys by cell
+                               : reinterpret_cast<unsigned char*>(sc + o_state);                // [n]
+  unsigned long long* tmp = reinterpret_cast<unsigned long long*>(sc + o_tmp);                  // [cand_cap] keys by cell
   unsigned long long* sk = (n <= smem_keys) ? skeys : gk;
   // ---- 1. bucket by cell (counting sort) into tmp
   for (int i = tid; i <= ncells; i += blockDim.x) cstart[i] = 0;

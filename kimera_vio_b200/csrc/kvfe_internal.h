@@ -63,7 +63,30 @@ struct StreamState {     // one per stream, device resident
   double median_disparity;
   int given_rot;
   int nr_tracked, nr_mono_put, nr_mono_inl, nr_stereo_put, nr_stereo_inl;
+  double acc_R[9];       // rotation input mode 1 (frame-to-frame rotations): lkf_R_km1 accumulated on the
+                         // device like the IMU front-end's preintegration (reset at every keyframe)
 };
+
+// Per-step I/O block in pinned, mapped host memory (one per pyramid slot of a context): the host fills
+// it and launches the pipeline step graph; the first kernels of the graph read their inputs -- image
+// source pointers included -- straight from it, the last one stores the outputs through the pointers it
+// names and then publishes `done_seq`.  Layout: this header, then at KVFE_STEPIO_ARRAYS: ts[B] (i64),
+// R[B*9] (f64).
+#define KVFE_STEPIO_ARRAYS 256
+struct StepIO {
+  const unsigned char* srcL;     // batch images, image b at srcL + b * src_pitch * H (device or mapped host memory)
+  const unsigned char* srcR;
+  unsigned long long src_pitch;
+  unsigned char* dst_packets;    // B * packet_bytes (mapped host memory), may be null
+  unsigned char* dst_rectL;      // B * W * H dense: rectified images of the keyframes of this step, may be null
+  unsigned char* dst_rectR;
+  unsigned long long seq;        // echoed into done_seq by the last kernel of the step
+  int rot_mode;                  // 0: R = lkf_R_cur (StereoVisionImuFrontend.cpp:149-150); 1: R = km1_R_cur
+  int pad0;
+  unsigned long long pad1[8];
+  volatile unsigned long long done_seq;   // device -> host, own 64-byte line
+};
+static_assert(sizeof(StepIO) <= KVFE_STEPIO_ARRAYS, "StepIO header must fit before the arrays");
 
 struct DevCfg {          // passed by value to kernels
   int W, H, pitch;       // level-0 geometry; pitch in bytes (multiple of 16)
@@ -95,6 +118,8 @@ struct DevCfg {          // passed by value to kernels
   long long min_kf_ns, max_kf_ns; int min_features;
   // rectified calibration
   double fx, fy, cxr, cyr, baseline;
+  // mesher
+  int mesh_on; float subdiv_factor;
 };
 
 struct DevBuf {
@@ -137,6 +162,7 @@ struct DevBuf {
   unsigned char* packets;      // B * packet_bytes
   size_t packet_bytes;
   size_t pk_off[32];
+  int* mesh_ws;                // quad-edge workspace of the mesh kernel when it does not fit shared memory
 };
 
 struct kvfe_ctx {
@@ -172,6 +198,11 @@ struct kvfe_ctx {
   int* d_kf_steps;             // device counter: executions of the IF body
   int* circle_hw;              // device: half widths of the filled-circle raster rows (2r+1)
   int circle_r;
+  int device;                  // CUDA device the context lives on
+  // pipeline step (pipeline.cu): I/O blocks in mapped pinned memory, one graph per pyramid slot
+  unsigned char* pio[2];
+  cudaGraphExec_t pipe_graph[2]; int pipe_graph_ready[2]; long long pipe_graph_launches;
+  unsigned int* d_pub_count;   // last-block-done counter of publish_io_kernel
 };
 
 // ---- launchers (each returns the number of kernels it launched) ------------------------------
@@ -214,7 +245,9 @@ int launch_ransac_3pt_raw(const DevCfg& dc, const DevBuf& db, const double* p_re
                           int n, int* inl, int* n_inl, double* pose, int* status, cudaStream_t s);
 // fsm.cu
 int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const long long* ts,
-                const double* Rin, cudaStream_t s);
+                const double* Rin, const StepIO* io, cudaStream_t s);
+int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s);
+int launch_publish_io(const DevCfg& dc, const DevBuf& db, StepIO* io, unsigned int* counter, cudaStream_t s);
 int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, cudaStream_t s);
 int launch_fetch(const unsigned char* srcL, const unsigned char* srcR, unsigned char* dstL, size_t dstL_stride,
@@ -224,3 +257,13 @@ int launch_decide(const DevCfg& dc, const DevBuf& db, unsigned long long cond, c
 int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, int* kf_counter, cudaStream_t s);
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
+// mesh.cu
+bool mesh_fits_smem(const DevCfg& dc);
+size_t mesh_global_ws_ints(const DevCfg& dc);
+int launch_mesh_init(const DevCfg& dc);
+int launch_mesh(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
+int launch_mesh_raw(const DevCfg& dc, const DevBuf& db, const float* x, const float* y, int n, float* tri, int max_tri,
+                    int* n_tri, cudaStream_t s);
+// api.cu (shared with pipeline.cu)
+int kvfe_set_err(kvfe_ctx* ctx, int code, const char* fmt, ...);
+int kvfe_enqueue_step_kernels(kvfe_ctx* ctx, const StepIO* io, long long* n_launch);

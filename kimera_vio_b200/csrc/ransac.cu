@@ -297,10 +297,8 @@ __device__ __forceinline__ double* ws_tmp(const DevCfg& dc, const DevBuf& db, in
 
 // outlierRejectionMono (VisionImuFrontend.cpp:90-113) -> geometricOutlierRejection2d2d(Frame*, Frame*, Pose3)
 template <int PROBLEM>
-__global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevBuf db, int mode_mask) {
-  const int b = blockIdx.x;
+__device__ void mono_ransac_body(const DevCfg& dc, const DevBuf& db, const int b) {
   StreamState& s = db.st[b];
-  if (!mode_on(s.mode, mode_mask) || !dc.use_ransac) return;
   const int fs_ref = b * 3 + s.slot_lkf, fs_cur = b * 3 + s.slot_k;
   int* m_ref = db.m_ref + (size_t)b * dc.cap;
   int* m_cur = db.m_cur + (size_t)b * dc.cap;
@@ -320,11 +318,7 @@ __global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevB
       a[3 * i + k] = db.fr.versor[3 * ((size_t)fs_ref * dc.cap + m_ref[i]) + k];
       bb[3 * i + k] = db.fr.versor[3 * ((size_t)fs_cur * dc.cap + m_cur[i]) + k];
     }
-  if (threadIdx.x < 9) {
-    // 2-point with the IMU rotation when usable, else with R = I (VisionImuFrontend.cpp:97-112)
-    bool imu_ok = s.given_rot != 0;
-    R12[threadIdx.x] = imu_ok ? s.kf_R_cur[threadIdx.x] : ((threadIdx.x % 4 == 0) ? 1.0 : 0.0);
-  }
+  if (threadIdx.x < 9) R12[threadIdx.x] = s.kf_R_cur[threadIdx.x];   // used by the 2-point problem only
   __syncthreads();
   int* wi = db.scratch_i + (size_t)b * db.scratch_stride;
   SacResult r = sac_run<PROBLEM>(a, bb, n, R12, dc.thr_mono, dc.ransac_iters, dc.ransac_prob,
@@ -350,6 +344,18 @@ __global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevB
     // tracker_status_summary_.lkf_T_k_mono_ only updated when VALID (StereoVisionImuFrontend.cpp:358-360)
     if (status == KVFE_TRK_VALID) for (int i = 0; i < 12; ++i) s.pose_mono[i] = model[i];
   }
+}
+
+// VisionImuFrontend::outlierRejectionMono (src/frontend/VisionImuFrontend.cpp:90-113): the 2-point problem
+// needs BOTH ransac_use_2point_mono and a usable IMU rotation (keyframe_R_cur != identity); every other
+// case -- the flag off, or an identity rotation as in the reference's unit tests and in exactly stationary
+// preintegration -- is 5-point Nister.  Chosen per stream (the branch is CTA-uniform).
+__global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevBuf db, int mode_mask) {
+  const int b = blockIdx.x;
+  const StreamState& s = db.st[b];
+  if (!mode_on(s.mode, mode_mask) || !dc.use_ransac) return;
+  if (dc.use_2pt && s.given_rot) mono_ransac_body<0>(dc, db, b);
+  else mono_ransac_body<2>(dc, db, b);
 }
 
 // Eigen::Matrix3d::inverse() (cofactor formula, compute_inverse_size3_helper)
@@ -608,8 +614,7 @@ __global__ void __launch_bounds__(RS_THREADS) vote_raw_kernel(DevCfg dc, DevBuf 
 }
 
 int launch_ransac_mono(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s) {
-  if (dc.use_2pt) mono_ransac_kernel<0><<<dc.B, RS_THREADS, 0, s>>>(dc, db, mode_mask);
-  else mono_ransac_kernel<2><<<dc.B, RS_THREADS, 0, s>>>(dc, db, mode_mask);
+  mono_ransac_kernel<<<dc.B, RS_THREADS, 0, s>>>(dc, db, mode_mask);
   return 1;
 }
 int launch_ransac_stereo(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s) {

@@ -58,6 +58,7 @@ class Config(C.Structure):
         ("min_number_features", C.c_int32),
         ("use_stereo_tracking", C.c_int32), ("use_ransac", C.c_int32),
         ("max_disparity_since_lkf", C.c_double),
+        ("mesh_2d", C.c_int32), ("subdiv_bounding_factor", C.c_float),
     ]
 
 
@@ -79,7 +80,8 @@ class PacketHeader(C.Structure):
                 ("nr_failed_arun_rkp", C.c_int32), ("mode", C.c_int32),
                 ("frame_id", C.c_int64), ("timestamp", C.c_int64),
                 ("lkf_T_k_mono", C.c_double * 12), ("lkf_T_k_stereo", C.c_double * 12),
-                ("info_stereo", C.c_double * 9), ("median_disparity", C.c_double)]
+                ("info_stereo", C.c_double * 9), ("median_disparity", C.c_double),
+                ("n_mesh_triangles", C.c_int32), ("reserved", C.c_int32)]
 
 
 class StereoOut(C.Structure):
@@ -96,7 +98,8 @@ PACKET_FIELDS = [("kp_x", np.float32, 1), ("kp_y", np.float32, 1), ("landmark", 
                  ("right_status", np.int32, 1), ("right_rect_x", np.float32, 1), ("right_rect_y", np.float32, 1),
                  ("depth", np.float64, 1), ("point3d", np.float64, 3), ("right_x", np.float32, 1),
                  ("right_y", np.float32, 1), ("smart_lmk", np.int64, 1), ("smart_uL", np.float64, 1),
-                 ("smart_uR", np.float64, 1), ("smart_v", np.float64, 1)]
+                 ("smart_uR", np.float64, 1), ("smart_v", np.float64, 1), ("mesh_tri", np.float32, 6)]
+N_PACKET_ARRAYS = len(PACKET_FIELDS)
 
 _lib = None
 
@@ -131,7 +134,7 @@ def _p(a: Optional[np.ndarray]):
 
 
 def make_config(p: FrontendParams, width: int, height: int, batch: int = 1, max_keypoints: int = 0,
-                rnd_libstdcxx: str = "lemire", sobel_cpu_tail_start: int = -1) -> Config:
+                rnd_libstdcxx: str = "lemire", sobel_cpu_tail_start: int = -1, mesh_2d: bool = False) -> Config:
     c = Config()
     load().kvfe_config_default(C.byref(c))
     c.width, c.height, c.batch, c.max_keypoints = width, height, batch, max_keypoints
@@ -169,6 +172,7 @@ def make_config(p: FrontendParams, width: int, height: int, batch: int = 1, max_
     c.min_number_features = p.min_number_features
     c.use_stereo_tracking, c.use_ransac = int(p.use_stereo_tracking), int(p.use_ransac)
     c.max_disparity_since_lkf = p.max_disparity_since_lkf
+    c.mesh_2d = int(mesh_2d)
     return c
 
 
@@ -200,8 +204,8 @@ class Context:
         self.W, self.H, self.B = cfg.width, cfg.height, cfg.batch
         self.cap = self.lib.kvfe_max_keypoints(self.h)
         self.packet_bytes = int(self.lib.kvfe_packet_bytes(self.h))
-        offs = (C.c_size_t * 20)()
-        self.lib.kvfe_packet_offsets(self.h, offs, 20)
+        offs = (C.c_size_t * N_PACKET_ARRAYS)()
+        self.lib.kvfe_packet_offsets(self.h, offs, N_PACKET_ARRAYS)
         self.packet_offsets = [int(o) for o in offs]
 
     def close(self):
@@ -326,6 +330,15 @@ class Context:
         res["left_rect"], res["right_rect"] = rl, rr
         return res
 
+    def mesh_2d(self, kps_xy):
+        xy = np.asarray(kps_xy, np.float32).reshape(-1, 2)
+        n = len(xy)
+        x, y = np.ascontiguousarray(xy[:, 0]), np.ascontiguousarray(xy[:, 1])
+        tri = np.zeros((2 * n + 8, 6), np.float32)
+        m = C.c_int()
+        self._chk(self.lib.kvfe_mesh_2d(self.h, _p(x), _p(y), n, _p(tri), len(tri), C.byref(m)))
+        return tri[:min(m.value, len(tri))].copy()
+
     def ransac_mono(self, f_ref, f_cur, R12=None):
         a = np.ascontiguousarray(np.asarray(f_ref, np.float64).reshape(-1, 3))
         b = np.ascontiguousarray(np.asarray(f_cur, np.float64).reshape(-1, 3))
@@ -435,9 +448,9 @@ class Context:
             d["info_stereo"] = np.array(h.info_stereo).reshape(3, 3)
             n = h.n
             for (name, dt, w), off in zip(PACKET_FIELDS, self.packet_offsets):
-                cnt = (h.n_smart if name.startswith("smart") else n) * w
+                cnt = (h.n_mesh_triangles if name == "mesh_tri" else h.n_smart if name.startswith("smart") else n) * w
                 a = np.frombuffer(raw.tobytes(), dtype=dt, count=cnt, offset=off).copy()
-                d[name] = a.reshape(-1, 3) if w == 3 else a
+                d[name] = a.reshape(-1, w) if w > 1 else a
             out.append(d)
         return out
 
@@ -448,3 +461,123 @@ class Context:
         self._chk(self.lib.kvfe_debug_lk(self.h, stream, _p(px), _p(py), _p(nx), _p(ny), _p(st), C.byref(n)))
         m = n.value
         return np.stack([px[:m], py[:m]], 1), np.stack([nx[:m], ny[:m]], 1), st[:m].copy()
+
+
+# ---- pipeline (kvfe_pipeline_*) ---------------------------------------------------------------------
+class PipelineConfig(C.Structure):
+    _fields_ = [("n_streams", C.c_int32), ("n_workers", C.c_int32), ("queue_depth", C.c_int32),
+                ("output_slots", C.c_int32), ("want_rectified", C.c_int32), ("rotation_mode", C.c_int32),
+                ("checksum_outputs", C.c_int32), ("max_in_flight", C.c_int32)]
+
+
+class PipelineOutput(C.Structure):
+    _fields_ = [("stream", C.c_int32), ("slot", C.c_int32), ("tag", C.c_uint64),
+                ("is_keyframe", C.c_int32), ("n_keypoints", C.c_int32), ("checksum", C.c_uint64),
+                ("packet", C.c_void_p), ("rect_left", C.c_void_p), ("rect_right", C.c_void_p)]
+
+
+class PipelineStats(C.Structure):
+    _fields_ = [("frames_pushed", C.c_int64), ("frames_done", C.c_int64), ("graph_launches", C.c_int64),
+                ("kernel_launches", C.c_int64), ("launch_seconds", C.c_double), ("staged_copies", C.c_int64)]
+
+
+def _pipeline_protos(lib):
+    if getattr(lib, "_kvfe_pipe_protos", False):
+        return
+    lib.kvfe_pipeline_create.argtypes = [C.POINTER(Config), C.POINTER(Rig), C.POINTER(PipelineConfig), C.POINTER(C.c_void_p)]
+    lib.kvfe_pipeline_destroy.argtypes = [C.c_void_p]
+    lib.kvfe_pipeline_destroy.restype = None
+    lib.kvfe_pipeline_last_error.argtypes = [C.c_void_p]
+    lib.kvfe_pipeline_last_error.restype = C.c_char_p
+    lib.kvfe_pipeline_packet_bytes.argtypes = [C.c_void_p]
+    lib.kvfe_pipeline_packet_bytes.restype = C.c_size_t
+    lib.kvfe_pipeline_packet_offsets.argtypes = [C.c_void_p, C.POINTER(C.c_size_t), C.c_int]
+    lib.kvfe_pipeline_max_keypoints.argtypes = [C.c_void_p]
+    lib.kvfe_pipeline_push.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_size_t, C.c_int64, C.c_void_p, C.c_uint64]
+    lib.kvfe_pipeline_push_many.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_void_p, C.c_void_p, C.c_size_t,
+                                            C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.kvfe_pipeline_pop.argtypes = [C.c_void_p, C.POINTER(PipelineOutput), C.c_int, C.c_int]
+    lib.kvfe_pipeline_release.argtypes = [C.c_void_p, C.POINTER(PipelineOutput), C.c_int]
+    lib.kvfe_pipeline_reset.argtypes = [C.c_void_p]
+    lib.kvfe_pipeline_get_stats.argtypes = [C.c_void_p, C.POINTER(PipelineStats)]
+    lib._kvfe_pipe_protos = True
+
+
+class Pipeline:
+    """kvfe_pipeline: n_streams camera streams behind input / output queues (include/kvfe.h)."""
+
+    def __init__(self, cfg: Config, rig: Rig, n_streams: int, n_workers: int = 0, queue_depth: int = 4,
+                 output_slots: int = 4, want_rectified: bool = True, rotation_mode: int = 0,
+                 checksum_outputs: bool = False, max_in_flight: int = 0):
+        self.lib = load()
+        _pipeline_protos(self.lib)
+        self.pc = PipelineConfig(n_streams, n_workers, queue_depth, output_slots, int(want_rectified), rotation_mode,
+                                 int(checksum_outputs), max_in_flight)
+        h = C.c_void_p()
+        rc = self.lib.kvfe_pipeline_create(C.byref(cfg), C.byref(rig), C.byref(self.pc), C.byref(h))
+        if rc != 0:
+            raise KvfeError("kvfe_pipeline_create failed (%d): %s" % (rc, self.lib.kvfe_pipeline_last_error(None).decode()))
+        self.h = h
+        self.n_streams, self.W, self.H = n_streams, cfg.width, cfg.height
+        self.B = 1
+        self.cap = self.lib.kvfe_pipeline_max_keypoints(self.h)
+        self.packet_bytes = int(self.lib.kvfe_pipeline_packet_bytes(self.h))
+        offs = (C.c_size_t * N_PACKET_ARRAYS)()
+        self.lib.kvfe_pipeline_packet_offsets(self.h, offs, N_PACKET_ARRAYS)
+        self.packet_offsets = [int(o) for o in offs]
+        self._outs = (PipelineOutput * max(64, 2 * n_streams))()
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.kvfe_pipeline_destroy(self.h)
+            self.h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _chk(self, rc: int):
+        if rc < 0:
+            raise KvfeError("kvfe_pipeline error %d: %s" % (rc, self.lib.kvfe_pipeline_last_error(self.h).decode()))
+        return rc
+
+    def push(self, stream: int, left_ptr: int, right_ptr: int, pitch: int, timestamp: int, R: np.ndarray, tag: int = 0) -> bool:
+        """Returns False when the stream's input queue is full."""
+        R = np.ascontiguousarray(np.asarray(R, np.float64).reshape(9))
+        rc = self.lib.kvfe_pipeline_push(self.h, stream, left_ptr, right_ptr, pitch, int(timestamp), R.ctypes.data, int(tag))
+        if rc == -4:
+            return False
+        self._chk(rc)
+        return True
+
+    def pop(self, max_n: int = 0, timeout_ms: int = 1000):
+        """Raw outputs (ctypes structs, valid until release)."""
+        max_n = min(max_n or len(self._outs), len(self._outs))
+        n = self._chk(self.lib.kvfe_pipeline_pop(self.h, self._outs, max_n, timeout_ms))
+        return [self._outs[i] for i in range(n)]
+
+    def release(self, outs):
+        if not outs:
+            return
+        arr = (PipelineOutput * len(outs))(*outs)
+        self._chk(self.lib.kvfe_pipeline_release(self.h, arr, len(outs)))
+
+    def parse(self, out: PipelineOutput, copy_rect: bool = True):
+        """Packet of one output as a dict (same fields as Context.parse_packets), plus the rectified pair."""
+        raw = np.ctypeslib.as_array(C.cast(out.packet, C.POINTER(C.c_uint8)), shape=(self.packet_bytes,)).copy()
+        d = Context.parse_packets(self, raw)[0]
+        d["stream"], d["tag"], d["checksum"] = out.stream, out.tag, out.checksum
+        if out.rect_left and copy_rect:
+            d["left_rect"] = np.ctypeslib.as_array(C.cast(out.rect_left, C.POINTER(C.c_uint8)), shape=(self.H, self.W)).copy()
+            d["right_rect"] = np.ctypeslib.as_array(C.cast(out.rect_right, C.POINTER(C.c_uint8)), shape=(self.H, self.W)).copy()
+        return d
+
+    def reset(self):
+        self._chk(self.lib.kvfe_pipeline_reset(self.h))
+
+    def stats(self) -> dict:
+        st = PipelineStats()
+        self._chk(self.lib.kvfe_pipeline_get_stats(self.h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in PipelineStats._fields_}

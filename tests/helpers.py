@@ -31,33 +31,7 @@ def diag(name, **kw):
         f.write(json.dumps({"test": name, **{k: conv(v) for k, v in kw.items()}}) + "\n")
 
 
-def sobel_cpu_tail_start(width: int) -> int:
-    """Detects where THIS host's cv2 switches to the scalar (non-FMA) Sobel row-filter tail
-     by probing cv2.Sobel on a random image; -1 when no tail is used."""
-    rng = np.random.default_rng(5)
-    img = rng.integers(0, 256, (64, width), dtype=np.uint8)
-    dy = cv2.Sobel(img, cv2.CV_32F, 0, 1, ksize=3, scale=1 / 3060.0)
-    I = img.astype(np.float32)
-    s = np.float32(1 / 3060.0)
-    s2 = np.float32(2) * s
-    xs = np.arange(width)
-    xm, xp = np.abs(xs - 1), np.where(xs + 1 >= width, 2 * (width - 1) - (xs + 1), xs + 1)
-    ys = np.arange(64)
-    ym, yp = np.abs(ys - 1), np.where(ys + 1 >= 64, 2 * 63 - (ys + 1), ys + 1)
-    t0 = s * I[:, xm]
-    t1 = (I.astype(np.float64) * np.float64(s2) + t0.astype(np.float64)).astype(np.float32)
-    t_fma = (I[:, xp].astype(np.float64) * np.float64(s) + t1.astype(np.float64)).astype(np.float32)
-    t_nofma = (s * I[:, xm] + s2 * I) + s * I[:, xp]
-    dy_fma = t_fma[yp] - t_fma[ym]
-    dy_no = t_nofma[yp] - t_nofma[ym]
-    col_fma_ok = np.all(dy_fma == dy, axis=0)
-    col_no_ok = np.all(dy_no == dy, axis=0)
-    # the scalar tail is the suffix of columns that only the non-FMA formula explains
-    if col_fma_ok.all():
-        return -1
-    start = int(np.argmin(col_fma_ok))
-    assert col_no_ok[start:].all() and col_fma_ok[:start].all(), "unexpected cv2.Sobel arithmetic on this host"
-    return start
+from kimera_vio_b200.hostprobe import sobel_cpu_tail_start  # noqa: E402,F401
 
 
 def euroc_setup(batch=1, params=None, **cfg_kw):
@@ -87,3 +61,18 @@ def synth_frames(n, seed=20240):
         s = SynthStream(CameraParams.euroc_left(), CameraParams.euroc_right(), rig.R1, seed=seed)
         _synth_cache[key] = (s, [s.frame(k) for k in range(n)])
     return _synth_cache[key]
+
+
+def shipped_rig(name: str):
+    """FrontendParams + left/right CameraParams of one of the reference's shipped rigs (params/<name>/*.yaml),
+    from tests/golden/rigs.json (values parsed from the reference YAMLs by tests/golden/make_rigs.py)."""
+    with open(os.path.join(ROOT, "tests", "golden", "rigs.json")) as f:
+        d = json.load(f)[name]
+    fp = dict(d["frontend"])
+    fp["binning_mask"] = np.asarray(fp["binning_mask"], np.float64)
+    cams = []
+    for side in ("left", "right"):
+        c = dict(d[side])
+        c["T_BS"] = np.asarray(c["T_BS"], np.float64)
+        cams.append(CameraParams(**c))
+    return FrontendParams(**fp), cams[0], cams[1]

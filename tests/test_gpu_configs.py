@@ -34,3 +34,21 @@ def test_sequence_larger_configs(w, h, feats, frames):
                       lambda b, k, l: s.kf_rotation(l, k), "cfg%dx%d" % (w, h))
     ctx.close()
     assert ok
+
+
+@pytest.mark.parametrize("rig_name,frames", [("uHumans2", 12), ("D455", 10)])
+def test_sequence_shipped_rigs(rig_name, frames):
+    """The reference's own params/uHumans2 (720x480, no distortion, maxFeatureAge 15, min_distance 8,
+    max_disparity_since_lkf 200) and params/D455 (640x480 radtan, 5-point + 3-point RANSAC) parameter and
+    camera files -- values from tests/golden/rigs.json -- on a synthetic stream rendered with that rig."""
+    p, left, right = H.shipped_rig(rig_name)
+    rig = StereoRigSetup(left, right)
+    cfg = kl.make_config(p, rig.W, rig.H, batch=1, sobel_cpu_tail_start=H.sobel_cpu_tail_start(rig.W))
+    ctx = kl.Context(cfg, rig.to_c())
+    s = SynthStream(left, right, rig.R1, seed=4242)
+    fr = [s.frame(k) for k in range(frames)]
+    fe = ofe.StereoFrontend(p, StereoRig(left, right))
+    ok = run_sequence(ctx, [fe], [[(f.left, f.right, f.timestamp) for f in fr]],
+                      lambda b, k, l: s.kf_rotation(l, k), "rig_" + rig_name)
+    ctx.close()
+    assert ok

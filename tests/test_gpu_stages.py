@@ -224,6 +224,37 @@ def test_sparse_stereo(env):
         assert rec["rect_mismatch"] == 0
 
 
+def test_sparse_stereo_near_tie_divergence_is_counted(env):
+    """cv::matchTemplate(TM_SQDIFF) evaluates the squared difference through a float DFT (absolute error up
+    to ~32 at magnitudes of 5e6..8e6), the GPU matcher in exact int32.  The arg-min can only
+    differ where two shifts are tied to within that error.  On textured input the divergence count is asserted
+    ZERO (here and over whole sequences in test_gpu_long.py); on a sensor-noise-only pair -- hundreds of nearly
+    tied shifts per keypoint, the worst case -- it is COUNTED, reported and bounded."""
+    p, o, ctx = env["p"], env["orig"], env["ctx"]
+    m = ofe.StereoMatcher(p, o)
+    rng = np.random.default_rng(5)
+    noise = np.clip(110 + rng.normal(0, 2.0, env["lefts"][0].shape), 0, 255).astype(np.uint8)
+    cases = [("euroc", env["lefts"][1], env["rights"][1], 0), ("synth", env["synth"][1].left, env["synth"][1].right, 0),
+             ("noise_only", noise, noise.copy(), None)]
+    for name, L, R, allowed in cases:
+        c = cv2.goodFeaturesToTrack(L, 300, 0.001, 20).reshape(-1, 2).astype(np.float32)
+        sf = ofe.StereoFrame.make(0, 0, L, R, o)
+        sf.left_frame.keypoints = [(np.float32(x), np.float32(y)) for x, y in c]
+        sf.left_frame.versors = ofe.get_bearing_vectors(sf.left_frame.keypoints, o.left, o.R1)
+        m.sparse_stereo_reconstruction(sf)
+        g = ctx.sparse_stereo(L, R, c, np.array(sf.left_frame.versors))
+        ers = np.array([s for s, _ in sf.right_keypoints_rectified])
+        erx = np.array([q for _, q in sf.right_keypoints_rectified], np.float32).reshape(-1, 2)
+        gx = np.stack([g["right_rect_x"], g["right_rect_y"]], 1)
+        matched = (ers == 0) | (g["right_status"] == 0)
+        div = int((((gx != erx).any(axis=1)) & matched).sum() + (g["right_status"] != ers).sum())
+        H.diag("stereo_near_tie", image=name, keypoints=len(c), matched=int(matched.sum()), divergent=div)
+        if allowed is not None:
+            assert div == allowed, (name, div)
+        else:
+            assert div <= max(3, len(c) // 25), (name, div, len(c))     # measured in round 1: 2 of 286
+
+
 @pytest.mark.parametrize("variant", ["subpixel", "extra_rows", "templ_51x7", "near_range"])
 def test_sparse_stereo_param_variants(env, variant):
     """Stereo-matcher parameter variants (StereoMatchingParams.h:46-60): cornerSubPix on the right match,
@@ -351,7 +382,7 @@ def test_ransac_5pt_nister():
     ctx.close()
 
 
-@pytest.mark.parametrize("variant", ["no_nms", "topn", "binning_mask", "min_distance_8", "quality_1e-10"])
+@pytest.mark.parametrize("variant", ["no_nms", "topn", "binning_mask", "min_distance_8", "min_distance_3", "min_distance_1", "quality_1e-10"])
 def test_detector_param_variants(variant):
     """The detector configurations of the reference's own tests (tests/testFeatureDetector.cpp:26-258:
     no NMS, TopN, Binning with a bin mask, quality 1e-10) and the uHumans2 min_distance (8, which
@@ -371,6 +402,10 @@ def test_detector_param_variants(variant):
                                 enable_subpixel_corner_refinement=False)
     elif variant == "min_distance_8":
         p = dataclasses.replace(base, min_distance=8)
+    elif variant in ("min_distance_3", "min_distance_1"):
+        # small cells: the greedy selection's cell grid (22 560 / 360 960 cells at 752x480) no longer fits the
+        # shared-memory path and its global-scratch sections must be sized from the grid
+        p = dataclasses.replace(base, min_distance=int(variant[-1]), quality_level=1e-10)
     else:
         p = dataclasses.replace(base, quality_level=1e-10)
     p, rig, ctx = H.euroc_setup(batch=1, params=p)

@@ -8,7 +8,7 @@ import torch
 import torch.distributed as dist
 import torch.multiprocessing as mp
 
-from conftest import REF, needs_reference
+from conftest import REF, ROOT, needs_reference
 from kimera_vio_b200 import dist as kd
 from kimera_vio_b200.params import CameraParams, FrontendParams
 from kimera_vio_b200.rig import StereoRigSetup
@@ -104,3 +104,47 @@ def test_gloo_world2_gather_packets():
     assert ids == [0, 1, 2, 3, 4, 5]          # stream-major order: rank 0's block, then rank 1's
     assert tags == [1, 2]
     assert ms == 11.0                          # max over ranks
+
+
+def _dt_host_lib():
+    """Builds tests/native/dt_host.cpp (the mesh kernel's quad-edge code, delaunay.cuh, compiled for the host)."""
+    import ctypes as C
+    import shutil
+    import subprocess
+    if not shutil.which("g++"):
+        pytest.skip("g++ not available")
+    out = os.path.join(ROOT, "tests", "_build")
+    os.makedirs(out, exist_ok=True)
+    so = os.path.join(out, "libdt_host.so")
+    subprocess.check_call(["g++", "-O2", "-shared", "-fPIC", "-o", so, os.path.join(ROOT, "tests", "native", "dt_host.cpp")])
+    return C.CDLL(so)
+
+
+def test_delaunay_restatement_matches_subdiv2d():
+    """delaunay.cuh (what mesh_kernel executes) against cv2.Subdiv2D through oracle/mesher.py: identical triangle
+    LISTS -- order and first vertex included -- on random sub-pixel points, integer corners (collinear and
+    cocircular sets), a coarse grid with duplicates, and points partly outside the image."""
+    import ctypes as C
+    from oracle.mesher import create_mesh_2d_impl
+    lib = _dt_host_lib()
+    rng = np.random.default_rng(1)
+    for trial in range(120):
+        w, h = (752, 480) if trial % 2 else (1280, 720)
+        n = int(rng.integers(1, 600))
+        kind = trial % 4
+        if kind == 0:
+            pts = rng.uniform(0, [w, h], (n, 2))
+        elif kind == 1:
+            pts = np.floor(rng.uniform(0, [w, h], (n, 2)))
+        elif kind == 2:
+            pts = np.floor(rng.uniform(0, [w / 20, h / 20], (n, 2))) * 20
+        else:
+            pts = rng.uniform(-5, [w + 5, h + 5], (n, 2))
+        pts = np.ascontiguousarray(pts, np.float32)
+        tri = np.zeros((4 * n + 16, 6), np.float32)
+        nq = C.c_int()
+        m = lib.dt_host_mesh(w, h, pts.ctypes.data_as(C.c_void_p), n, tri.ctypes.data_as(C.c_void_p), len(tri), C.byref(nq))
+        assert m >= 0
+        ref = create_mesh_2d_impl((w, h), [tuple(p) for p in pts])
+        assert tri[:m].shape == ref.shape and np.array_equal(tri[:m], ref), (trial, kind, n)
+        assert nq.value <= 3 * n + 16
