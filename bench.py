@@ -36,6 +36,9 @@ import numpy as np
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+# one hardware work queue per camera stream (read by the driver when torch creates the CUDA context, i.e.
+# before libkvfe.so -- which sets the same default at load -- is loaded): see csrc/api.cu kvfe_on_load
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
 
 from kimera_vio_b200.hostprobe import sobel_cpu_tail_start  # noqa: E402
 from kimera_vio_b200.params import CameraParams, FrontendParams  # noqa: E402

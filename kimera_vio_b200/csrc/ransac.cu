@@ -318,7 +318,8 @@ __device__ void mono_ransac_body(const DevCfg& dc, const DevBuf& db, const int b
       a[3 * i + k] = db.fr.versor[3 * ((size_t)fs_ref * dc.cap + m_ref[i]) + k];
       bb[3 * i + k] = db.fr.versor[3 * ((size_t)fs_cur * dc.cap + m_cur[i]) + k];
     }
-  if (threadIdx.x < 9) R12[threadIdx.x] = s.kf_R_cur[threadIdx.x];   // used by the 2-point problem only
+  // used by the 2-point problem only; without a usable IMU rotation the reference passes Pose3() (exact identity)
+  if (threadIdx.x < 9) R12[threadIdx.x] = s.given_rot ? s.kf_R_cur[threadIdx.x] : ((threadIdx.x & 3) == 0 ? 1.0 : 0.0);
   __syncthreads();
   int* wi = db.scratch_i + (size_t)b * db.scratch_stride;
   SacResult r = sac_run<PROBLEM>(a, bb, n, R12, dc.thr_mono, dc.ransac_iters, dc.ransac_prob,
@@ -346,15 +347,18 @@ __device__ void mono_ransac_body(const DevCfg& dc, const DevBuf& db, const int b
   }
 }
 
-// VisionImuFrontend::outlierRejectionMono (src/frontend/VisionImuFrontend.cpp:90-113): the 2-point problem
-// needs BOTH ransac_use_2point_mono and a usable IMU rotation (keyframe_R_cur != identity); every other
-// case -- the flag off, or an identity rotation as in the reference's unit tests and in exactly stationary
-// preintegration -- is 5-point Nister.  Chosen per stream (the branch is CTA-uniform).
+// VisionImuFrontend::outlierRejectionMono (src/frontend/VisionImuFrontend.cpp:90-113) calls
+// geometricOutlierRejection2d2d with the IMU rotation when it is usable (keyframe_R_cur != identity) and with
+// the DEFAULT pose otherwise (Tracker.h:97-100: cam_lkf_Pose_cam_kf = gtsam::Pose3()).  The solver itself is
+// chosen inside that function from the PARAMETER alone (Tracker.cpp:248-276): ransac_use_2point_mono -> the
+// 2-point problem with R12 = that pose's rotation -- the identity in the second case, whatever the "5-point
+// RANSAC" comment at VisionImuFrontend.cpp:108 says -- else 5-point Nister.  (The stereo side is different:
+// outlierRejectionStereo really switches between two functions, see stereo_ransac_kernel.)
 __global__ void __launch_bounds__(RS_THREADS) mono_ransac_kernel(DevCfg dc, DevBuf db, int mode_mask) {
   const int b = blockIdx.x;
   const StreamState& s = db.st[b];
   if (!mode_on(s.mode, mode_mask) || !dc.use_ransac) return;
-  if (dc.use_2pt && s.given_rot) mono_ransac_body<0>(dc, db, b);
+  if (dc.use_2pt) mono_ransac_body<0>(dc, db, b);
   else mono_ransac_body<2>(dc, db, b);
 }
 

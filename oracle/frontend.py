@@ -484,7 +484,10 @@ class Tracker:
 
     # --- a12
     def outlier_rejection_2d2d(self, ref: Frame, cur: Frame, R: Optional[np.ndarray]):
-        """Tracker::geometricOutlierRejection2d2d (Tracker.cpp:213-378).  R=None -> identity."""
+        """Tracker::geometricOutlierRejection2d2d (Tracker.cpp:213-378).  R=None -> the default argument
+        gtsam::Pose3() (Tracker.h:97-100).  The solver is chosen from ransac_use_2point_mono ALONE
+        (Tracker.cpp:248-276): the call outlierRejectionMono labels "5-point RANSAC" (VisionImuFrontend.cpp:108)
+        is the 2-point problem with R12 = identity whenever that parameter is set."""
         p = self.p
         matches = find_matching_keypoints(ref, cur)
         ident = np.hstack([np.eye(3), np.zeros((3, 1))])

@@ -304,16 +304,19 @@ def test_submit_dev_matches_step():
     assert not bad
 
 
-def test_sequence_identity_rotation_is_5pt():
-    """Euroc parameters (2-point / 1-point RANSAC enabled) with keyframe_R_cur == identity on every frame --
-    no IMU, the reference's own unit tests, exactly stationary preintegration: the reference falls back to
-    5-point Nister and 3-point Arun per call (VisionImuFrontend.cpp:97-112, :131-151)."""
+def test_sequence_identity_rotation():
+    """Euroc parameters (2-point / 1-point RANSAC enabled) with keyframe_R_cur == identity on every frame -- no
+    IMU, the reference's own unit tests, exactly stationary preintegration.  Mono: outlierRejectionMono passes
+    the default Pose3() and geometricOutlierRejection2d2d still picks the 2-POINT problem from the parameter
+    (Tracker.cpp:248-276), now with R12 = identity -- nearly every match of a rotating camera becomes an outlier,
+    which is what the reference does.  Stereo: outlierRejectionStereo really falls back to 3-point Arun
+    (VisionImuFrontend.cpp:131-151).  Both behaviours must match the oracle frame by frame."""
     N = 10
     p, rig, ctx = H.euroc_setup(batch=2)
     orig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
     s, fr = H.synth_frames(N, seed=20240)
     frames = [[(f.left, f.right, f.timestamp) for f in fr]] * 2
-    # stream 0: identity rotations (5-point / 3-point); stream 1: the IMU rotations (2-point / 1-point) in the same batch
+    # stream 0: identity rotations (2-point with R = I / 3-point); stream 1: the IMU rotations (2-point / 1-point), same batch
     oracles = [ofe.StereoFrontend(p, orig) for _ in range(2)]
     ok = run_sequence(ctx, oracles, frames, lambda b, k, l: np.eye(3) if b == 0 else s.kf_rotation(l, k), "identityR")
     ctx.close()
