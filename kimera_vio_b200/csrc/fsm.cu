@@ -11,7 +11,9 @@
 //   detect_pre   FeatureDetector::featureDetection(Frame*, R) :98-115 (ages, n_existing, need)
 //   finalize     slot rotation, keyframe_R_ref_frame_ update (:462-475), getSmartStereoMeasurements
 //                (:485-531), StereoFrame::checkStatusRightKeypoints (StereoFrame.cpp:106-143), packing.
+#include <cstdlib>
 #include "common.cuh"
+#include "tma.cuh"
 #include "matches.cuh"
 
 
@@ -453,80 +455,135 @@ int launch_fetch(const unsigned char* srcL, const unsigned char* srcR, unsigned 
 }
 // ---- pipeline step: image fetch and output publication through the mapped I/O block -----------------
 // The source pointers are read from the I/O block, so ONE captured graph serves every step.  A source in
-// pinned host memory is read by the SMs over the host link (zero-copy): no copy-engine operation, hence
-// no in-order copy queue shared between contexts and no small-copy inefficiency (a 361 KB cudaMemcpyAsync
-// reaches well under half of the link rate).  Every thread keeps four 16-byte loads in flight.
-// grid (x, B, 2): y = image of the batch, z = camera.
-__global__ void __launch_bounds__(256) fetch_io_kernel(DevCfg dc, const StepIO* __restrict__ io, unsigned char* __restrict__ dstL,
-                                                       unsigned char* __restrict__ dstR) {
+// pinned host memory is pulled over the host link by the SM's TMA unit (zero-copy): no copy-engine
+// operation, hence no in-order copy queue shared between contexts and no small-copy inefficiency (a 361 KB
+// cudaMemcpyAsync reaches well under half of the link rate).
+//
+// Bulk asynchronous copies (cp.async.bulk, tma.cuh): ONE warp per CTA streams its share of the image through a
+// two-stage 8 KB shared-memory ring -- global/host -> shared on an mbarrier, shared -> global as a bulk
+// group.  The first version of this kernel parked 44 CTAs x 256 threads per stream on 16-byte loads over the
+// host link; with 32 streams in flight those threads took the SM slots of the compute kernels (measured on
+// B200, 32 streams: 0.91 -> 0.83 ms per pass just by shrinking that grid to 8 CTAs).  grid (x, B, 2):
+// y = image of the batch, z = camera; chunk c is handled by CTA c % gridDim.x.
+#define FETCH_CHUNK 8192
+#define FETCH_STAGES 2
+struct BulkRing {
+  unsigned char buf[FETCH_STAGES][FETCH_CHUNK];
+  unsigned long long bar[FETCH_STAGES];
+};
+// one thread: initialise the ring's barriers (once per kernel)
+__device__ __forceinline__ void bulk_ring_init(BulkRing& r) {
+  for (int st = 0; st < FETCH_STAGES; ++st) tma::mbar_init(reinterpret_cast<uint64_t*>(&r.bar[st]), 1);
+  tma::fence_barrier_init();
+}
+// one thread: copies chunks first, first + stride, ... of [src, src + total) to dst through the ring.
+// `uses` counts the completed phases of every stage's barrier across calls (phase parity of the next wait).
+__device__ __forceinline__ void bulk_stream_copy(BulkRing& r, unsigned int (&uses)[FETCH_STAGES], unsigned char* dst,
+                                                 const unsigned char* src, size_t total, int first, int stride) {
+  const int nchunks = (int)((total + FETCH_CHUNK - 1) / FETCH_CHUNK);
+  const int n_my = first < nchunks ? (nchunks - first + stride - 1) / stride : 0;
+  auto chunk_off = [&](int i) { return (size_t)(first + i * stride) * FETCH_CHUNK; };
+  auto chunk_bytes = [&](int i) { const size_t o = chunk_off(i); return (uint32_t)(total - o < FETCH_CHUNK ? total - o : FETCH_CHUNK); };
+  auto load = [&](int i) {
+    uint64_t* bar = reinterpret_cast<uint64_t*>(&r.bar[i % FETCH_STAGES]);
+    tma::mbar_expect_tx(bar, chunk_bytes(i));
+    tma::bulk_g2s(r.buf[i % FETCH_STAGES], src + chunk_off(i), chunk_bytes(i), bar);
+  };
+  for (int i = 0; i < FETCH_STAGES && i < n_my; ++i) load(i);
+  for (int i = 0; i < n_my; ++i) {
+    const int st = i % FETCH_STAGES;
+    tma::mbar_wait(reinterpret_cast<uint64_t*>(&r.bar[st]), uses[st] & 1u);
+    ++uses[st];
+    tma::bulk_s2g(dst + chunk_off(i), r.buf[st], chunk_bytes(i));
+    tma::bulk_commit();
+    if (i + FETCH_STAGES < n_my) {
+      tma::bulk_wait_read<0>();            // the store has drained this stage: refill it
+      load(i + FETCH_STAGES);
+    }
+  }
+  tma::bulk_wait<0>();                     // every global write of this thread's bulk groups performed
+  asm volatile("fence.proxy.async;" ::: "memory");
+}
+
+__global__ void __launch_bounds__(32) fetch_io_kernel(DevCfg dc, const StepIO* __restrict__ io, unsigned char* __restrict__ dstL,
+                                                      unsigned char* __restrict__ dstR) {
+  __shared__ __align__(128) BulkRing ring;
   const size_t sp = (size_t)io->src_pitch;
   const unsigned char* src = (blockIdx.z ? io->srcR : io->srcL) + (size_t)blockIdx.y * sp * dc.H;
   unsigned char* dst = blockIdx.z ? dstR + (size_t)blockIdx.y * dc.img_stride : dstL + (size_t)blockIdx.y * dc.pyr_stride;
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  if (sp == (size_t)dc.W && dc.pitch == dc.W && (((size_t)src | (size_t)dst) & 15) == 0) {
-    const size_t img = (size_t)dc.W * dc.H, n16 = img / 16;
-    const uint4* s4 = reinterpret_cast<const uint4*>(src);
-    uint4* d4 = reinterpret_cast<uint4*>(dst);
-    for (size_t i = tid; i < n16; i += 4 * nth) {
-      uint4 v[4];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) if (i + u * nth < n16) v[u] = s4[i + u * nth];
-#pragma unroll
-      for (int u = 0; u < 4; ++u) if (i + u * nth < n16) d4[i + u * nth] = v[u];
+  const size_t img = (size_t)dc.W * dc.H;
+  if (sp == (size_t)dc.W && dc.pitch == dc.W && ((((size_t)src | (size_t)dst) | img) & 15) == 0) {
+    if (threadIdx.x == 0) {
+      unsigned int uses[FETCH_STAGES] = {0};
+      bulk_ring_init(ring);
+      bulk_stream_copy(ring, uses, dst, src, img, blockIdx.x, gridDim.x);
     }
-    for (size_t i = n16 * 16 + tid; i < img; i += nth) dst[i] = src[i];
   } else {
-    const size_t n = (size_t)dc.W * dc.H;
-    for (size_t i = tid; i < n; i += nth) {
+    // row pitch or alignment the bulk unit cannot take: plain byte copy by the warp (rare: ROI views)
+    for (size_t i = (size_t)blockIdx.x * 32 + threadIdx.x; i < img; i += (size_t)gridDim.x * 32) {
       const size_t y = i / dc.W, x = i - y * dc.W;
       dst[y * dc.pitch + x] = src[y * sp + x];
     }
   }
 }
+static int bulk_grid(const DevCfg& dc) {
+  const int nchunks = (int)(((size_t)dc.W * dc.H + FETCH_CHUNK - 1) / FETCH_CHUNK);
+  static const int env_ctas = getenv("KVFE_FETCH_CTAS") ? atoi(getenv("KVFE_FETCH_CTAS")) : 0;   // diagnostic
+  // measured on B200, 32 streams x 752x480 (45 chunks): 4 CTAs per image 0.80 ms per pass end to end, 11 CTAs
+  // 0.91, 22 CTAs 0.97 -- a few resident warps per image keep the host link busy, more only crowd the SMs
+  const int g = env_ctas > 0 ? env_ctas : nchunks / 11;
+  return g < 2 ? 2 : (g > 16 ? 16 : g);
+}
 int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s) {
-  const int gx = (int)(((size_t)dc.W * dc.H / 16 + 4 * 256 - 1) / (4 * 256));
-  fetch_io_kernel<<<dim3(gx < 1 ? 1 : (gx > 96 ? 96 : gx), dc.B, 2), 256, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw);
+  fetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, 2), 32, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw);
   return 1;
 }
 
-// Last kernel of a pipeline step: the SMs store the packets and -- for the streams whose frame became a
-// keyframe -- the rectified image pair (part of the output StereoFrame, include/kimera-vio/frontend/
-// StereoFrame.h:71-87) into the mapped host buffers the I/O block names; the last CTA to finish fences
-// and publishes the step's sequence number, which is all the dispatcher polls.
-__global__ void __launch_bounds__(256) publish_io_kernel(DevCfg dc, DevBuf db, StepIO* io, unsigned int* counter) {
-  const size_t tid = (size_t)blockIdx.x * blockDim.x + threadIdx.x, nth = (size_t)gridDim.x * blockDim.x;
-  if (io->dst_packets) {
-    // header, then of every array only the entries in use (a packet's capacity is ~2.3x its typical content)
-    const unsigned sz[KVFE_PACKET_ARRAYS] = {4, 4, 8, 4, 8, 24, 4, 4, 4, 4, 4, 4, 8, 24, 4, 4, 8, 8, 8, 8, 24};
-    for (int b = 0; b < dc.B; ++b) {
-      const unsigned char* src = db.packets + (size_t)b * db.packet_bytes;
-      unsigned char* dst = io->dst_packets + (size_t)b * db.packet_bytes;
-      const kvfe_packet_header* h = reinterpret_cast<const kvfe_packet_header*>(src);
-      const int n = h->n, ns = h->n_smart, nt = h->n_mesh_triangles;
-      for (int a = -1; a < KVFE_PACKET_ARRAYS; ++a) {
-        const size_t off = a < 0 ? 0 : db.pk_off[a];
-        const size_t bytes = a < 0 ? sizeof(kvfe_packet_header) : (size_t)sz[a] * (size_t)(a == 20 ? nt : a >= 16 ? ns : n);
-        const size_t n16 = (bytes + 15) / 16;       // arrays start 16-byte aligned and are padded to 16 bytes
-        const uint4* s4 = reinterpret_cast<const uint4*>(src + off);
-        uint4* d4 = reinterpret_cast<uint4*>(dst + off);
-        for (size_t i = tid; i < n16; i += nth) d4[i] = s4[i];
+// Last kernel of a pipeline step: the packets and -- for the streams whose frame became a keyframe -- the
+// rectified image pair (part of the output StereoFrame, include/kimera-vio/frontend/StereoFrame.h:71-87) go
+// into the mapped host buffers the I/O block names; the last CTA to finish fences and publishes the step's
+// sequence number, which is all the dispatcher polls.  CTA 0: packets (only the entries in use), 16-byte
+// stores by 128 threads.  CTAs 1..: rectified images, one warp each, bulk copies through the same ring as the
+// fetch (HBM -> shared -> host).
+__global__ void __launch_bounds__(128) publish_io_kernel(DevCfg dc, DevBuf db, StepIO* io, unsigned int* counter) {
+  __shared__ __align__(128) BulkRing ring;
+  if (blockIdx.x == 0) {
+    if (io->dst_packets) {
+      // header, then of every array only the entries in use (a packet's capacity is ~2.3x its typical content)
+      const unsigned sz[KVFE_PACKET_ARRAYS] = {4, 4, 8, 4, 8, 24, 4, 4, 4, 4, 4, 4, 8, 24, 4, 4, 8, 8, 8, 8, 24};
+      for (int b = 0; b < dc.B; ++b) {
+        const unsigned char* src = db.packets + (size_t)b * db.packet_bytes;
+        unsigned char* dst = io->dst_packets + (size_t)b * db.packet_bytes;
+        const kvfe_packet_header* h = reinterpret_cast<const kvfe_packet_header*>(src);
+        const int n = h->n, ns = h->n_smart, nt = h->n_mesh_triangles;
+        for (int a = -1; a < KVFE_PACKET_ARRAYS; ++a) {
+          const size_t off = a < 0 ? 0 : db.pk_off[a];
+          const size_t bytes = a < 0 ? sizeof(kvfe_packet_header) : (size_t)sz[a] * (size_t)(a == 20 ? nt : a >= 16 ? ns : n);
+          const size_t n16 = (bytes + 15) / 16;       // arrays start 16-byte aligned and are padded to 16 bytes
+          const uint4* s4 = reinterpret_cast<const uint4*>(src + off);
+          uint4* d4 = reinterpret_cast<uint4*>(dst + off);
+          for (size_t i = threadIdx.x; i < n16; i += blockDim.x) d4[i] = s4[i];
+        }
       }
     }
-  }
-  if (io->dst_rectL && io->dst_rectR) {
+  } else if (io->dst_rectL && io->dst_rectR) {
     const size_t img = (size_t)dc.W * dc.H;
+    const int part = blockIdx.x - 1, nparts = gridDim.x - 1;
+    unsigned int uses[FETCH_STAGES] = {0};
+    if (threadIdx.x == 0) bulk_ring_init(ring);
     for (int b = 0; b < dc.B; ++b) {
       const int mode = db.st[b].mode;
       if (!(mode == 0 || mode == 2)) continue;
       for (int cam = 0; cam < 2; ++cam) {
         const unsigned char* src = (cam ? db.rectR : db.rectL) + (size_t)b * dc.img_stride;
         unsigned char* dst = (cam ? io->dst_rectR : io->dst_rectL) + (size_t)b * img;
-        if (dc.pitch == dc.W && (((size_t)dst) & 15) == 0) {
-          const size_t n16 = img / 16;
-          for (size_t i = tid; i < n16; i += nth) reinterpret_cast<uint4*>(dst)[i] = reinterpret_cast<const uint4*>(src)[i];
-          for (size_t i = n16 * 16 + tid; i < img; i += nth) dst[i] = src[i];
+        if (dc.pitch == dc.W && ((((size_t)dst | (size_t)src) | img) & 15) == 0) {
+          if (threadIdx.x == 0) bulk_stream_copy(ring, uses, dst, src, img, part, nparts);
         } else {
-          for (size_t i = tid; i < img; i += nth) { const size_t y = i / dc.W, x = i - y * dc.W; dst[i] = src[y * dc.pitch + x]; }
+          for (size_t i = (size_t)part * blockDim.x + threadIdx.x; i < img; i += (size_t)nparts * blockDim.x) {
+            const size_t y = i / dc.W, x = i - y * dc.W;
+            dst[i] = src[y * dc.pitch + x];
+          }
         }
       }
     }
@@ -544,7 +601,7 @@ __global__ void __launch_bounds__(256) publish_io_kernel(DevCfg dc, DevBuf db, S
   }
 }
 int launch_publish_io(const DevCfg& dc, const DevBuf& db, StepIO* io, unsigned int* counter, cudaStream_t s) {
-  publish_io_kernel<<<16, 256, 0, s>>>(dc, db, io, counter);
+  publish_io_kernel<<<1 + bulk_grid(dc), 128, 0, s>>>(dc, db, io, counter);
   return 1;
 }
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {

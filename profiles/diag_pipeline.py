@@ -9,6 +9,8 @@ import time
 
 import numpy as np
 
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 import bench as B  # noqa: E402
@@ -35,7 +37,9 @@ def main():
     frame_of = np.array([B.pass_frame(t, NF) for t in range(n_pass)], np.int64)
     rot_tab = np.stack([np.stack([B.pass_rotation(fwd, bwd, s, t, NF).reshape(9) for t in range(n_pass)]) for s in range(PS)])
 
-    def run_variant(name, streams, batch, workers, in_flight, rect, chk):
+    pL, pR = torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory()
+
+    def run_variant(name, streams, batch, workers, in_flight, rect, chk, host=False):
         kcfg = kl.make_config(p, W, H, batch=batch, sobel_cpu_tail_start=tail)
         pipe = kl.Pipeline(kcfg, rig.to_c(), n_streams=streams, n_workers=workers, queue_depth=n_pass + 8, output_slots=4,
                            want_rectified=rect, rotation_mode=1, checksum_outputs=chk, max_in_flight=in_flight)
@@ -46,8 +50,8 @@ def main():
         tt = np.repeat(np.arange(n_pass, dtype=np.int64), streams)
         ss = sidx.astype(np.int64) % PS
         off = (ss * NF + frame_of[tt]) * img
-        lp = (dL.data_ptr() + off).astype(np.uint64)
-        rp = (dR.data_ptr() + off).astype(np.uint64)
+        lp = ((pL if host else dL).data_ptr() + off).astype(np.uint64)
+        rp = ((pR if host else dR).data_ptr() + off).astype(np.uint64)
         ts = (B.T0_NS + (tt + np.where(tt >= 1, np.tile(np.arange(streams) % 4, n_pass), 0)) * B.DT_NS).astype(np.int64)
         Rm = np.ascontiguousarray(rot_tab[ss, tt])
         tags = tt.astype(np.uint64)
@@ -80,6 +84,10 @@ def main():
         ("32x1 w4 if1 norect nochk", 32, 1, 4, 1, False, False),
         ("16x1 w4 if2 norect nochk", 16, 1, 4, 2, False, False),
         ("8x1 w4 if2 norect nochk", 8, 1, 4, 2, False, False),
+        ("HOST 32x1 w4 if2 rect chk (bench e2e)", 32, 1, 4, 2, True, True, True),
+        ("HOST 32x1 w4 if2 rect nochk", 32, 1, 4, 2, True, False, True),
+        ("HOST 32x1 w4 if2 norect nochk", 32, 1, 4, 2, False, False, True),
+        ("HOST 32x1 w8 if2 rect chk", 32, 1, 8, 2, True, True, True),
     ]
     want = set(args.variants.split(",")) if args.variants else None
     for i, v in enumerate(V):
