@@ -11,6 +11,8 @@
 #include <random>
 #include <vector>
 
+#include <cuda.h>           // CUtensorMap types only: the encoder is resolved through the runtime, libcuda is not linked
+
 #include "kvfe_internal.h"
 
 static thread_local char g_create_err[512] = "";
@@ -150,6 +152,41 @@ static std::vector<int> circle_half_widths(int r) {
       return KVFE_ERR_CUDA;                                                                     \
     }                                                                                           \
   } while (0)
+// Tensor maps of the pyramid levels for the LK patch boxes (lk.cu, lk_kernel_tma): per pyramid slot and level
+// one 3-D u8 tensor (x: level width, y: level height, z: stream) with row pitch lvl_pitch and stream pitch
+// pyr_stride, box 48 x 28 x 1, no swizzle, zero fill outside.  cuTensorMapEncodeTiled is a driver entry point:
+// it is looked up through cudaGetDriverEntryPoint.  On failure the maps stay null and LK runs lk_kernel_col.
+static const void* build_lk_tensor_maps(const DevCfg& dc, unsigned char* const pyr[2]) {
+  typedef CUresult (*EncodeTiled)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+  void* fn = nullptr;
+  cudaDriverEntryPointQueryResult qres;
+  if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &fn, cudaEnableDefault, &qres) != cudaSuccess || !fn ||
+      qres != cudaDriverEntryPointSuccess) {
+    cudaGetLastError();
+    return nullptr;
+  }
+  EncodeTiled encode = reinterpret_cast<EncodeTiled>(fn);
+  std::vector<CUtensorMap> maps(2 * KVFE_MAX_LEVELS);
+  memset(maps.data(), 0, maps.size() * sizeof(CUtensorMap));
+  for (int slot = 0; slot < 2; ++slot)
+    for (int l = 0; l < dc.n_levels; ++l) {
+      const cuuint64_t dims[3] = {(cuuint64_t)dc.lvl_w[l], (cuuint64_t)dc.lvl_h[l], (cuuint64_t)dc.B};
+      const cuuint64_t strides[2] = {(cuuint64_t)dc.lvl_pitch[l], (cuuint64_t)dc.pyr_stride};
+      const cuuint32_t box[3] = {48, 28, 1}, estr[3] = {1, 1, 1};   // LKT_BOXW x LKT_BOXH of lk.cu
+      CUresult r = encode(&maps[slot * KVFE_MAX_LEVELS + l], CU_TENSOR_MAP_DATA_TYPE_UINT8, 3, pyr[slot] + dc.lvl_off[l], dims,
+                          strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                          CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+      if (r != CUDA_SUCCESS) return nullptr;
+    }
+  // handed to the kernel as a __grid_constant__ parameter (the documented way to give a tensor map to the TMA
+  // unit); the host copy lives as long as the context
+  void* h = aligned_alloc(128, maps.size() * sizeof(CUtensorMap));
+  if (h) memcpy(h, maps.data(), maps.size() * sizeof(CUtensorMap));
+  return h;
+}
+
 extern "C" void kvfe_destroy(kvfe_ctx* ctx);
 extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx** out) {
   kvfe_ctx* ctx = nullptr;
@@ -256,6 +293,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CUC(dmalloc(&ctx->d_cam, 2));
   CUC(cudaMemcpy(ctx->d_cam, ctx->cam, sizeof(CamModel) * 2, cudaMemcpyHostToDevice));
   for (int k = 0; k < 2; ++k) CUC(dmalloc(&db.pyr[k], B * dc.pyr_stride));
+  static_assert(sizeof(CUtensorMap) == 128, "lk_kernel_tma indexes the tensor maps with a 128-byte stride");
+  db.lk_tmaps = build_lk_tensor_maps(dc, db.pyr);
   CUC(dmalloc(&db.right_raw, B * dc.img_stride));
   // fixed-point remap tables (cv::convertMaps-style: integer source pixel + 5+5 fractional bits),
   // computed once per rig from the in-register f64 map model
@@ -396,6 +435,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
     if (ctx->pipe_graph_ready[i]) cudaGraphExecDestroy(ctx->pipe_graph[i]);
     if (ctx->pio[i]) cudaFreeHost(ctx->pio[i]);
   }
+  free(const_cast<void*>(db.lk_tmaps));
   void* ptrs[] = {db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
                   db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,

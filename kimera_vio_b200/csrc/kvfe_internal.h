@@ -163,6 +163,9 @@ struct DevBuf {
   size_t packet_bytes;
   size_t pk_off[32];
   int* mesh_ws;                // quad-edge workspace of the mesh kernel when it does not fit shared memory
+  const void* lk_tmaps;        // HOST pointer (never dereferenced on the device): CUtensorMap[2 pyramid slots][KVFE_MAX_LEVELS],
+                               // (x, y, stream) u8 tensors of the pyramid levels, box 48 x 28 x 1 -- launch_lk passes them
+                               // to lk_kernel_tma as a __grid_constant__ parameter; null when they could not be built
 };
 
 struct kvfe_ctx {
