@@ -379,6 +379,10 @@ typedef struct {
   int32_t checksum_outputs; /* the dispatcher reads every delivered byte (packet, rectified images) and
                                returns a 64-bit checksum with the output */
   int32_t max_in_flight;    /* steps in flight per stream on the GPU, 1 or 2 (0 = default 2) */
+  int32_t prefetch;         /* > 0: when a stream's NEXT frame is already queued at launch time (dense rows, 16-byte
+                               aligned, device or pinned memory), its images are pulled into a staging slot by a side
+                               branch of the current step's graph.  Off by default: with 32 streams on one B200 the
+                               forked graphs measured slower than the plain chain (see pipeline.cu) */
 } kvfe_pipeline_config;
 typedef struct {
   int32_t stream, slot;     /* slot: pass back to kvfe_pipeline_release */

@@ -417,7 +417,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
     ctx->use_cond = (c && c[0] == '1');
   }
   CUC(dmalloc(&ctx->d_kf_steps, 1));
-  CUC(dmalloc(&ctx->d_pub_count, 1));
+  CUC(dmalloc(&ctx->d_pub_count, 2));
+  CUC(cudaMemset(ctx->d_pub_count, 0, 2 * sizeof(unsigned int)));
   for (int i = 0; i < 2; ++i) {
     const size_t bytes = KVFE_STEPIO_ARRAYS + B * (sizeof(long long) + 9 * sizeof(double));
     CUC(cudaMallocHost((void**)&ctx->pio[i], bytes));
@@ -436,7 +437,10 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
     if (ctx->pio[i]) cudaFreeHost(ctx->pio[i]);
   }
   free(const_cast<void*>(db.lk_tmaps));
-  void* ptrs[] = {db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
+  if (ctx->side) cudaStreamDestroy(ctx->side);
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
+  void* ptrs[] = {db.stage_img[0], db.stage_img[1], db.stage_seq, db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
                   db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,

@@ -505,11 +505,17 @@ __device__ __forceinline__ void bulk_stream_copy(BulkRing& r, unsigned int (&use
   asm volatile("fence.proxy.async;" ::: "memory");
 }
 
+// Head of the step graph: the frame's images go to pyramid level 0 / the right raw image -- from the staging slot
+// when the previous step's prefetch branch already pulled them (stage_seq == this step's sequence number: an
+// HBM -> HBM copy), else straight from the source the I/O block names.
 __global__ void __launch_bounds__(32) fetch_io_kernel(DevCfg dc, const StepIO* __restrict__ io, unsigned char* __restrict__ dstL,
-                                                      unsigned char* __restrict__ dstR) {
+                                                      unsigned char* __restrict__ dstR, const unsigned char* __restrict__ stage,
+                                                      const unsigned long long* __restrict__ stage_seq) {
   __shared__ __align__(128) BulkRing ring;
-  const size_t sp = (size_t)io->src_pitch;
-  const unsigned char* src = (blockIdx.z ? io->srcR : io->srcL) + (size_t)blockIdx.y * sp * dc.H;
+  const bool staged = stage != nullptr && *stage_seq == io->seq;
+  const size_t sp = staged ? (size_t)dc.W : (size_t)io->src_pitch;
+  const unsigned char* src = staged ? stage + ((size_t)blockIdx.z * dc.B + blockIdx.y) * dc.img_stride
+                                    : (blockIdx.z ? io->srcR : io->srcL) + (size_t)blockIdx.y * sp * dc.H;
   unsigned char* dst = blockIdx.z ? dstR + (size_t)blockIdx.y * dc.img_stride : dstL + (size_t)blockIdx.y * dc.pyr_stride;
   const size_t img = (size_t)dc.W * dc.H;
   if (sp == (size_t)dc.W && dc.pitch == dc.W && ((((size_t)src | (size_t)dst) | img) & 15) == 0) {
@@ -526,6 +532,31 @@ __global__ void __launch_bounds__(32) fetch_io_kernel(DevCfg dc, const StepIO* _
     }
   }
 }
+// Side branch of the step graph (runs beside the step's kernels): the NEXT frame's images, when that frame is
+// already queued, are pulled over the host link into the other staging slot; the last CTA publishes the
+// sequence number the next step's head looks for.  next_src* are dense and 16-byte aligned (the host checks).
+__global__ void __launch_bounds__(32) prefetch_io_kernel(DevCfg dc, const StepIO* __restrict__ io, unsigned char* __restrict__ stage,
+                                                         unsigned long long* __restrict__ stage_seq, unsigned int* counter) {
+  __shared__ __align__(128) BulkRing ring;
+  const unsigned char* sL = io->next_srcL;
+  const unsigned char* sR = io->next_srcR;
+  if (!sL || !sR) return;                          // grid-uniform: nobody touches the counter
+  const size_t img = (size_t)dc.W * dc.H;
+  const unsigned char* src = (blockIdx.z ? sR : sL) + (size_t)blockIdx.y * img;
+  unsigned char* dst = stage + ((size_t)blockIdx.z * dc.B + blockIdx.y) * dc.img_stride;
+  if (threadIdx.x == 0) {
+    unsigned int uses[FETCH_STAGES] = {0};
+    bulk_ring_init(ring);
+    bulk_stream_copy(ring, uses, dst, src, img, blockIdx.x, gridDim.x);
+    __threadfence();
+    const unsigned int total = gridDim.x * gridDim.y * gridDim.z;
+    if (atomicAdd(counter, 1u) == total - 1) {
+      *counter = 0;
+      __threadfence();
+      *stage_seq = io->seq + 1;
+    }
+  }
+}
 static int bulk_grid(const DevCfg& dc) {
   const int nchunks = (int)(((size_t)dc.W * dc.H + FETCH_CHUNK - 1) / FETCH_CHUNK);
   static const int env_ctas = getenv("KVFE_FETCH_CTAS") ? atoi(getenv("KVFE_FETCH_CTAS")) : 0;   // diagnostic
@@ -535,7 +566,12 @@ static int bulk_grid(const DevCfg& dc) {
   return g < 2 ? 2 : (g > 16 ? 16 : g);
 }
 int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s) {
-  fetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, 2), 32, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw);
+  fetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, 2), 32, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw,
+                                                              db.stage_img[cur_slot], db.stage_seq ? db.stage_seq + cur_slot : nullptr);
+  return 1;
+}
+int launch_prefetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, unsigned int* counter, cudaStream_t s) {
+  prefetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, 2), 32, 0, s>>>(dc, io, db.stage_img[cur_slot ^ 1], db.stage_seq + (cur_slot ^ 1), counter);
   return 1;
 }
 

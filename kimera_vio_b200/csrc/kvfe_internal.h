@@ -83,7 +83,9 @@ struct StepIO {
   unsigned long long seq;        // echoed into done_seq by the last kernel of the step
   int rot_mode;                  // 0: R = lkf_R_cur (StereoVisionImuFrontend.cpp:149-150); 1: R = km1_R_cur
   int pad0;
-  unsigned long long pad1[8];
+  const unsigned char* next_srcL;   // images of the stream's NEXT frame when it is already queued (dense rows, 16-byte
+  const unsigned char* next_srcR;   // aligned), else null: pulled into the staging slot while this step computes
+  unsigned long long pad1[6];
   volatile unsigned long long done_seq;   // device -> host, own 64-byte line
 };
 static_assert(sizeof(StepIO) <= KVFE_STEPIO_ARRAYS, "StepIO header must fit before the arrays");
@@ -163,6 +165,8 @@ struct DevBuf {
   size_t packet_bytes;
   size_t pk_off[32];
   int* mesh_ws;                // quad-edge workspace of the mesh kernel when it does not fit shared memory
+  unsigned char* stage_img[2]; // pipeline prefetch staging, per pyramid slot: [cam][B] dense images, img_stride apart (or null)
+  unsigned long long* stage_seq; // [2]: sequence number of the frame held by stage_img[slot] (0: none)
   const void* lk_tmaps;        // HOST pointer (never dereferenced on the device): CUtensorMap[2 pyramid slots][KVFE_MAX_LEVELS],
                                // (x, y, stream) u8 tensors of the pyramid levels, box 48 x 28 x 1 -- launch_lk passes them
                                // to lk_kernel_tma as a __grid_constant__ parameter; null when they could not be built
@@ -205,7 +209,9 @@ struct kvfe_ctx {
   // pipeline step (pipeline.cu): I/O blocks in mapped pinned memory, one graph per pyramid slot
   unsigned char* pio[2];
   cudaGraphExec_t pipe_graph[2]; int pipe_graph_ready[2]; long long pipe_graph_launches;
-  unsigned int* d_pub_count;   // last-block-done counter of publish_io_kernel
+  unsigned int* d_pub_count;   // last-block-done counters: [0] publish_io_kernel, [1] prefetch_io_kernel
+  cudaStream_t side;           // capture-time fork of the pipeline step graph (prefetch branch); no work is ever queued on it
+  cudaEvent_t ev_fork, ev_join;
 };
 
 // ---- launchers (each returns the number of kernels it launched) ------------------------------
@@ -250,6 +256,7 @@ int launch_ransac_3pt_raw(const DevCfg& dc, const DevBuf& db, const double* p_re
 int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const long long* ts,
                 const double* Rin, const StepIO* io, cudaStream_t s);
 int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s);
+int launch_prefetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, unsigned int* counter, cudaStream_t s);
 int launch_publish_io(const DevCfg& dc, const DevBuf& db, StepIO* io, unsigned int* counter, cudaStream_t s);
 int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_track_post(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, cudaStream_t s);

@@ -90,10 +90,18 @@ static int build_pipe_graph(kvfe_ctx* ctx, int slot) {
   cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
   if (e != cudaSuccess) return kvfe_set_err(ctx, KVFE_ERR_CUDA, "pipeline graph capture: %s", cudaGetErrorString(e));
   long long k = 0;
+  if (ctx->db.stage_img[0]) {
+    // fork: the prefetch of the next frame's images runs beside the whole step and joins at its end
+    cudaEventRecord(ctx->ev_fork, ctx->stream);
+    cudaStreamWaitEvent(ctx->side, ctx->ev_fork, 0);
+    n += launch_prefetch_io(ctx->dc, ctx->db, io, slot, ctx->d_pub_count + 1, ctx->side);
+    cudaEventRecord(ctx->ev_join, ctx->side);
+  }
   n += launch_fetch_io(ctx->dc, ctx->db, io, slot, ctx->stream);
   int rc = kvfe_enqueue_step_kernels(ctx, io, &k);
   n += k;
   n += launch_publish_io(ctx->dc, ctx->db, io, ctx->d_pub_count, ctx->stream);
+  if (ctx->db.stage_img[0]) cudaStreamWaitEvent(ctx->stream, ctx->ev_join, 0);
   e = cudaStreamEndCapture(ctx->stream, &g);
   if (rc != KVFE_OK) { if (g) cudaGraphDestroy(g); return rc; }
   if (e != cudaSuccess) return kvfe_set_err(ctx, KVFE_ERR_CUDA, "pipeline graph capture: %s", cudaGetErrorString(e));
@@ -174,6 +182,15 @@ static const unsigned char* resolve_src(kvfe_pipeline* p, PipeStream* s, int io_
   return d;
 }
 
+// device-visible address of a buffer the SMs can read in place (device memory, or pinned mapped host memory); null otherwise
+static const unsigned char* direct_src(const unsigned char* ptr) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, ptr) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  if (a.type == cudaMemoryTypeDevice || a.type == cudaMemoryTypeManaged) return ptr;
+  if (a.type == cudaMemoryTypeHost && a.devicePointer) return static_cast<const unsigned char*>(a.devicePointer);
+  return nullptr;
+}
+
 static void worker_main(kvfe_pipeline* p, int widx) {
   cudaSetDevice(p->device);
   std::vector<int> mine;
@@ -198,12 +215,14 @@ static void worker_main(kvfe_pipeline* p, int widx) {
       }
       // launches
       while ((int)s->fl.size() < depth) {
-        PipeIn in; int oslot = -1;
+        PipeIn in, nxt; int oslot = -1;
+        bool have_next = false;
         {
           std::lock_guard<std::mutex> g(s->mu);
           if (s->in.empty() || s->free_out.empty()) break;
           in = s->in.front(); s->in.pop_front();
           oslot = s->free_out.back(); s->free_out.pop_back();
+          if (p->pc.prefetch != 0 && !s->in.empty()) { nxt = s->in.front(); have_next = true; }
         }
         const double t0 = now_s();
         const int io_slot = ctx->cur_slot;
@@ -217,6 +236,12 @@ static void worker_main(kvfe_pipeline* p, int widx) {
         }
         if (!L || !R || pl != pr) { pipe_fail(p, KVFE_ERR_CUDA, "pipeline: cannot stage the input images"); break; }
         io->srcL = L; io->srcR = R; io->src_pitch = pl;
+        io->next_srcL = nullptr; io->next_srcR = nullptr;
+        if (have_next) {
+          const unsigned char* nl = direct_src(nxt.L);
+          const unsigned char* nr = direct_src(nxt.R);
+          if (nl && nr && nxt.pitch == (size_t)p->W && ((((size_t)nl | (size_t)nr) | p->img) & 15) == 0) { io->next_srcL = nl; io->next_srcR = nr; }
+        }
         io->dst_packets = s->out[oslot].packet;
         io->dst_rectL = p->pc.want_rectified ? s->out[oslot].rectL : nullptr;
         io->dst_rectR = p->pc.want_rectified ? s->out[oslot].rectR : nullptr;
@@ -290,6 +315,10 @@ extern "C" int kvfe_pipeline_create(const kvfe_config* cfg, const kvfe_rig* rig,
   if (p->pc.queue_depth <= 0) p->pc.queue_depth = 4;
   if (p->pc.output_slots < 2) p->pc.output_slots = 4;
   if (p->pc.max_in_flight <= 0 || p->pc.max_in_flight > 2) p->pc.max_in_flight = 2;
+  // opt-in: measured SLOWER on B200 with 32 streams (device-resident 0.63 -> 0.75 ms per pass, host buffers 0.81 ->
+  // 0.87): a step graph with a parallel branch costs twice the launch time on the host and the branches of 32
+  // graphs compete for the 32 hardware work queues; the overlap across streams already hides the transfer
+  p->pc.prefetch = pc->prefetch > 0 ? 1 : 0;
   p->W = cfg->width; p->H = cfg->height; p->img = (size_t)cfg->width * cfg->height;
   kvfe_config c1 = *cfg;
   c1.batch = 1;
@@ -301,6 +330,22 @@ extern "C" int kvfe_pipeline_create(const kvfe_config* cfg, const kvfe_rig* rig,
       pipe_fail(nullptr, rc, kvfe_last_error(nullptr));
       kvfe_pipeline_destroy(p);
       return rc;
+    }
+    if (p->pc.prefetch != 0) {
+      // staging of the next frame's images (two slots, like the pyramid) + the fork stream / events of the capture
+      kvfe_ctx* c = s->ctx;
+      bool ok = true;
+      for (int k = 0; k < 2 && ok; ++k) ok = cudaMalloc((void**)&c->db.stage_img[k], 2 * (size_t)c->dc.B * c->dc.img_stride) == cudaSuccess;
+      ok = ok && cudaMalloc((void**)&c->db.stage_seq, 2 * sizeof(unsigned long long)) == cudaSuccess;
+      ok = ok && cudaMemset(c->db.stage_seq, 0, 2 * sizeof(unsigned long long)) == cudaSuccess;
+      ok = ok && cudaStreamCreateWithFlags(&c->side, cudaStreamNonBlocking) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&c->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+      ok = ok && cudaEventCreateWithFlags(&c->ev_join, cudaEventDisableTiming) == cudaSuccess;
+      if (!ok) {
+        pipe_fail(nullptr, KVFE_ERR_CUDA, "pipeline: prefetch staging allocation failed");
+        kvfe_pipeline_destroy(p);
+        return KVFE_ERR_CUDA;
+      }
     }
     for (int slot = 1; slot >= 0; --slot) {      // slot 0 last: cur_slot ends at 0
       rc = build_pipe_graph(s->ctx, slot);

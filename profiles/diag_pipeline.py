@@ -39,10 +39,10 @@ def main():
 
     pL, pR = torch.from_numpy(left).pin_memory(), torch.from_numpy(right).pin_memory()
 
-    def run_variant(name, streams, batch, workers, in_flight, rect, chk, host=False):
+    def run_variant(name, streams, batch, workers, in_flight, rect, chk, host=False, prefetch=0):
         kcfg = kl.make_config(p, W, H, batch=batch, sobel_cpu_tail_start=tail)
         pipe = kl.Pipeline(kcfg, rig.to_c(), n_streams=streams, n_workers=workers, queue_depth=n_pass + 8, output_slots=4,
-                           want_rectified=rect, rotation_mode=1, checksum_outputs=chk, max_in_flight=in_flight)
+                           want_rectified=rect, rotation_mode=1, checksum_outputs=chk, max_in_flight=in_flight, prefetch=prefetch)
         lib, ph = pipe.lib, pipe.h
         OUTS = (kl.PipelineOutput * 1024)()
         n = n_pass * streams
@@ -88,6 +88,8 @@ def main():
         ("HOST 32x1 w4 if2 rect nochk", 32, 1, 4, 2, True, False, True),
         ("HOST 32x1 w4 if2 norect nochk", 32, 1, 4, 2, False, False, True),
         ("HOST 32x1 w8 if2 rect chk", 32, 1, 8, 2, True, True, True),
+        ("HOST 32x1 w4 if2 rect chk PREFETCH", 32, 1, 4, 2, True, True, True, 1),
+        ("32x1 w4 if2 rect chk PREFETCH", 32, 1, 4, 2, True, True, False, 1),
     ]
     want = set(args.variants.split(",")) if args.variants else None
     for i, v in enumerate(V):

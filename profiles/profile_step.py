@@ -1,4 +1,5 @@
-"""Small driver for ncu: N steps of the device-resident batch step (batch 32, Euroc 752x480)."""
+"""Small driver for ncu: N device-resident batch steps (one context, batch 32, BASELINE configs[1] by default).
+  KVFE_NO_GRAPH=1 KVFE_STEPS=10 ncu ... python profiles/profile_step.py [config]"""
 import os, sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
@@ -6,28 +7,30 @@ import numpy as np
 import torch
 import bench
 from kimera_vio_b200 import lib as kl
-from kimera_vio_b200.params import CameraParams, FrontendParams
-from kimera_vio_b200.rig import StereoRigSetup
 
-B = int(os.environ.get("KVFE_BATCH", "32"))
+name = sys.argv[1] if len(sys.argv) > 1 else "c2"
+cfg = bench.CONFIGS[name]
+W, H, PS, NF = cfg["W"], cfg["H"], cfg["pool_streams"], cfg["pool_frames"]
+B = int(os.environ.get("KVFE_BATCH", str(cfg["batch"])))
 N = int(os.environ.get("KVFE_STEPS", "10"))
-rig = StereoRigSetup(CameraParams.euroc_left(), CameraParams.euroc_right())
-left, right, rot = bench.frame_pool(20, rig)
-ctx = kl.Context(kl.make_config(FrontendParams.euroc(), bench.W, bench.H, batch=B), rig.to_c())
-dL = torch.empty((N, B, bench.H, bench.W), dtype=torch.uint8, device="cuda")
-dR = torch.empty_like(dL)
+left, right, fwd, bwd = bench.frame_pool(name)
+lcam, rcam, rig = bench.config_rig(cfg)
+p = bench.config_params(cfg)
+ctx = kl.Context(kl.make_config(p, W, H, batch=B, sobel_cpu_tail_start=bench.sobel_cpu_tail_start(W)), rig.to_c())
+dL, dR = torch.from_numpy(left).cuda(), torch.from_numpy(right).cuda()
+idx = torch.tensor([b % PS for b in range(B)], device="cuda")
+acc = [np.eye(3) for _ in range(B)]
 for k in range(N):
-    for b in range(B):
-        dL[k, b].copy_(torch.from_numpy(left[b % bench.POOL_STREAMS, k]))
-        dR[k, b].copy_(torch.from_numpy(right[b % bench.POOL_STREAMS, k]))
-torch.cuda.synchronize()
-lkf = np.zeros(B, np.int64)
-for k in range(N):
+    f = bench.pass_frame(k, NF)
+    bl, br = dL[idx, f].contiguous(), dR[idx, f].contiguous()
     ts = np.array([bench.slot_timestamp(b, k) for b in range(B)], np.int64)
-    R = np.stack([rot[b % bench.POOL_STREAMS, lkf[b], k].reshape(9) for b in range(B)])
-    ctx.step_dev(dL[k].data_ptr(), dR[k].data_ptr(), bench.W, ts, R)
+    R = np.zeros((B, 9))
+    for b in range(B):
+        acc[b] = bench.mat3(acc[b], bench.pass_rotation(fwd, bwd, b % PS, k, NF))
+        R[b] = acc[b].reshape(9)
+    ctx.step_dev(bl.data_ptr(), br.data_ptr(), W, ts, np.ascontiguousarray(R))
     pk = ctx.read_packets()
     for b in range(B):
         if pk[b]["is_keyframe"]:
-            lkf[b] = k
-print("modes of last step:", [p["mode"] for p in pk])
+            acc[b] = np.eye(3)
+print("keyframes in the last step:", sum(int(q["is_keyframe"]) for q in pk), "of", B)
