@@ -13,6 +13,8 @@
 //
 // HBM traffic per keyframe image: image 1 B/px (L2 hits for the 3-row window), mask 1 B/px write
 // + read, response 4 B/px write + 9 reads served by L1/L2.  Non-compulsory.
+#include <cstdlib>
+
 #include "common.cuh"
 
 // ------------------------------------------------------------------------------------------------
@@ -182,6 +184,193 @@ __global__ void __launch_bounds__(128) mineig_kernel(DevCfg dc, DevBuf db, const
       rm1_0 = r0; rm1_1 = r1; rm1_2 = r2;
     }
     __syncwarp();
+  }
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(KVFE_FULL_MASK, vmax, o));
+  if (lane == 0 && vmax > -INFINITY) atomicMax(&db.eig_max[b], f2ord(vmax));
+}
+
+// ------------------------------------------------------------------------------------------------
+// Response map, warp-specialised: the same arithmetic as mineig_kernel, with the row-parallel part (Sobel,
+// products, f64 row sums) taken off the serial column scan.  One CTA per stripe of 30 output columns:
+//   warps 0..2  producers: chunks of 8 rows (chunk c -> warp c % 3); per row the three f64 row sums R(p) of the
+//               stripe go into a 32-row shared-memory ring;
+//   warp 3      scanner: the history-dependent running column sums (2 dependent f64 adds per sum and row) and
+//               nothing else; the sums of every output row go into a second ring as floats;
+//   warps 4..7  finishers (chunk k -> warp k % 4): min-eigenvalue formula, store, masked maximum.
+// The warp that carries the serial chain executes ~20 instructions per row instead of ~120 interleaved with the
+// image loads.  Hand-over through shared-memory sequence numbers per 8-row chunk (ready / scanned / finished).
+// ------------------------------------------------------------------------------------------------
+#define ME_RING 32
+#define ME_CHUNK 8
+#define ME_PRODUCERS 3
+#define ME_FINISHERS 4
+#define ME_SLOTS (ME_RING / ME_CHUNK)
+struct MeRing {
+  double r0[ME_RING][32], r1[ME_RING][32], r2[ME_RING][32];   // producers -> scanner: f64 row sums R(p)
+  float s0[ME_RING][32], s1[ME_RING][32], s2[ME_RING][32];    // scanner -> finishers: (float) column sums of output row y
+  int ready[ME_SLOTS];                // chunk index + 1 once the chunk's R rows are in the ring
+  int scanned[ME_SLOTS];              // chunk index + 1 once the chunk's column sums are in the ring
+  int finished[ME_SLOTS];             // chunk index + 1 once a finisher is done with the chunk's column sums
+  int cons_row;                       // R rows the scanner is done with
+};
+
+__global__ void __launch_bounds__(32 * (ME_PRODUCERS + 1 + ME_FINISHERS))
+mineig_pipe_kernel(DevCfg dc, DevBuf db, const unsigned char* __restrict__ imgs, size_t img_stride, int mode_mask, int use_mask) {
+  __shared__ MeRing ring;
+  const int b = blockIdx.y;
+  if (!mode_on(db.st[b].mode, mode_mask)) return;
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int x0 = blockIdx.x * 30;
+  const int W = dc.W, H = dc.H;
+  if (x0 >= W) return;
+  const unsigned char* img = imgs + (size_t)b * img_stride;
+  const int cx = x0 - 1 + lane;                 // lanes 0 and 31 are halo
+  int c = reflect101(cx, W);
+  c = clampi(c, 0, W - 1);                      // lanes beyond the reflected border are inactive
+  const int pitch = dc.pitch;
+  if (threadIdx.x < ME_SLOTS) { ring.ready[threadIdx.x] = 0; ring.scanned[threadIdx.x] = 0; ring.finished[threadIdx.x] = 0; }
+  if (threadIdx.x == 0) ring.cons_row = 0;
+  __syncthreads();
+  volatile int* ready = ring.ready;
+  volatile int* scanned = ring.scanned;
+  volatile int* finished = ring.finished;
+  volatile int* cons_row = &ring.cons_row;
+
+  if (warp < ME_PRODUCERS) {
+    // ---- producers: Sobel, products, f64 row sums of chunk rows p0 .. p0 + 7
+    const int cm = reflect101(c - 1, W), cp = reflect101(c + 1, W);
+    const float s = (float)(1.0 / 3060.0), s2 = 2.0f * s;
+    const bool tail = dc.sobel_tail_start >= 0 && c >= dc.sobel_tail_start;
+    for (int p0 = warp * ME_CHUNK; p0 < H; p0 += ME_PRODUCERS * ME_CHUNK) {
+      // image rows p0 - 1 .. p0 + ME_CHUNK (reflected), three columns each: independent loads, issued up front
+      float im[ME_CHUNK + 2], i0[ME_CHUNK + 2], ip[ME_CHUNK + 2];
+#pragma unroll
+      for (int u = 0; u < ME_CHUNK + 2; ++u) {
+        const int y = reflect101(min(p0 - 1 + u, H), H);
+        const unsigned char* row = img + (size_t)y * pitch;
+        im[u] = (float)row[cm]; i0[u] = (float)row[c]; ip[u] = (float)row[cp];
+      }
+      RT rt[ME_CHUNK + 2];
+#pragma unroll
+      for (int u = 0; u < ME_CHUNK + 2; ++u) rt[u] = rt_from(im[u], i0[u], ip[u], s, s2, tail);
+      // the ring slots of this chunk are free once the scanner is past row p0 + ME_CHUNK - 1 - ME_RING
+      while (*cons_row <= p0 + ME_CHUNK - 1 - ME_RING) __nanosleep(64);
+      __threadfence_block();
+#pragma unroll
+      for (int u = 0; u < ME_CHUNK; ++u) {
+        const int p = p0 + u;
+        if (p < H) {
+          // cv::Sobel column pass: Dx = fma(r(y-1) + r(y+1), s, (2s) * r(y)); Dy = t(y+1) - t(y-1)
+          const float dx = fmaf(rt[u].r + rt[u + 2].r, s, s2 * rt[u + 1].r);
+          const float dy = rt[u + 2].t - rt[u].t;
+          const float pxx = dx * dx, pxy = dx * dy, pyy = dy * dy;
+          // RowSum<float,double>, ksize 3: (S[x-1] + S[x]) + S[x+1]
+          const float l0 = __shfl_up_sync(KVFE_FULL_MASK, pxx, 1), g0 = __shfl_down_sync(KVFE_FULL_MASK, pxx, 1);
+          const float l1 = __shfl_up_sync(KVFE_FULL_MASK, pxy, 1), g1 = __shfl_down_sync(KVFE_FULL_MASK, pxy, 1);
+          const float l2 = __shfl_up_sync(KVFE_FULL_MASK, pyy, 1), g2 = __shfl_down_sync(KVFE_FULL_MASK, pyy, 1);
+          const int slot = p & (ME_RING - 1);
+          ring.r0[slot][lane] = ((double)l0 + (double)pxx) + (double)g0;
+          ring.r1[slot][lane] = ((double)l1 + (double)pxy) + (double)g1;
+          ring.r2[slot][lane] = ((double)l2 + (double)pyy) + (double)g2;
+        }
+      }
+      __syncwarp();
+      __threadfence_block();
+      if (lane == 0) ready[(p0 / ME_CHUNK) & (ME_SLOTS - 1)] = p0 / ME_CHUNK + 1;
+    }
+    return;
+  }
+
+  if (warp == ME_PRODUCERS) {
+    // ---- scanner: the history-dependent running column sums, nothing else.  Iteration p consumes R(p) and emits the
+    // sums of output row y = p - 1 into ring slot y % ME_RING; output chunk k = rows 8k .. 8k + 7.
+    double sum0 = 0, sum1 = 0, sum2 = 0;             // running column sums (xx, xy, yy)
+    double rm2_0 = 0, rm2_1 = 0, rm2_2 = 0;          // R(p-2)
+    double rm1_0 = 0, rm1_1 = 0, rm1_2 = 0;          // R(p-1)
+    for (int p0 = 0; p0 <= H; p0 += ME_CHUNK) {
+      if (p0 < H) {                                      // one wait per chunk: its 8 rows then pipeline freely
+        while (ready[(p0 / ME_CHUNK) & (ME_SLOTS - 1)] != p0 / ME_CHUNK + 1) __nanosleep(32);
+        // output rows p0 .. p0 + 7 reuse the slots of rows p0 - 32 ..: their finisher must be done
+        if (p0 >= ME_RING) while (finished[(p0 / ME_CHUNK) & (ME_SLOTS - 1)] != p0 / ME_CHUNK - ME_SLOTS + 1) __nanosleep(32);
+        __threadfence_block();
+      }
+      double q0[ME_CHUNK], q1[ME_CHUNK], q2[ME_CHUNK];
+#pragma unroll
+      for (int u = 0; u < ME_CHUNK; ++u) {
+        const int slot = (p0 + u) & (ME_RING - 1);
+        q0[u] = ring.r0[slot][lane]; q1[u] = ring.r1[slot][lane]; q2[u] = ring.r2[slot][lane];
+      }
+#pragma unroll
+      for (int u = 0; u < ME_CHUNK; ++u) {
+        const int p = p0 + u;
+        if (p > H) break;
+        double r0, r1, r2;
+        if (p < H) {
+          r0 = q0[u]; r1 = q1[u]; r2 = q2[u];
+        } else {
+          r0 = rm2_0; r1 = rm2_1; r2 = rm2_2;            // R(H) = R(H-2) (reflect)
+        }
+        if (p == 1) {                                    // ColumnSum init: SUM = (0 + R(-1)) + R(0), R(-1) = R(1)
+          sum0 = (0.0 + r0) + rm1_0;
+          sum1 = (0.0 + r1) + rm1_1;
+          sum2 = (0.0 + r2) + rm1_2;
+        }
+        if (p >= 1) {
+          const int y = p - 1;
+          // s0 = SUM + R(y+1); out = (float)s0; SUM = s0 - R(y-1)   (R(-1) = R(1))
+          const double s0 = sum0 + r0, s1 = sum1 + r1, s2d = sum2 + r2;
+          const double o0 = (y == 0) ? r0 : rm2_0, o1 = (y == 0) ? r1 : rm2_1, o2 = (y == 0) ? r2 : rm2_2;
+          sum0 = s0 - o0; sum1 = s1 - o1; sum2 = s2d - o2;
+          const int slot = y & (ME_RING - 1);
+          ring.s0[slot][lane] = (float)s0; ring.s1[slot][lane] = (float)s1; ring.s2[slot][lane] = (float)s2d;
+          if ((y & (ME_CHUNK - 1)) == ME_CHUNK - 1 || y == H - 1) {     // output chunk complete (warp-uniform)
+            __syncwarp();
+            __threadfence_block();
+            if (lane == 0) scanned[(y / ME_CHUNK) & (ME_SLOTS - 1)] = y / ME_CHUNK + 1;
+          }
+        }
+        rm2_0 = rm1_0; rm2_1 = rm1_1; rm2_2 = rm1_2;
+        rm1_0 = r0; rm1_1 = r1; rm1_2 = r2;
+      }
+      __syncwarp();
+      if (lane == 0) *cons_row = min(p0 + ME_CHUNK, H);   // every lane has read the R rows below this
+    }
+    return;
+  }
+
+  // ---- finishers: min-eigenvalue formula, store, masked maximum of output chunk k (rows 8k .. 8k + 7)
+  const int fw = warp - ME_PRODUCERS - 1;
+  const unsigned char* msk = db.mask + (size_t)b * dc.img_stride;
+  float* eig = db.eig + (size_t)b * W * H;
+  const bool writer = lane >= 1 && lane <= 30 && cx < W;
+  const int cxw = clampi(cx, 0, W - 1);
+  float vmax = -INFINITY;
+  for (int k = fw; k * ME_CHUNK < H; k += ME_FINISHERS) {
+    const int y0 = k * ME_CHUNK;
+    unsigned char mk[ME_CHUNK];
+#pragma unroll
+    for (int u = 0; u < ME_CHUNK; ++u) mk[u] = use_mask ? msk[(size_t)min(y0 + u, H - 1) * pitch + cxw] : (unsigned char)255;
+    while (scanned[k & (ME_SLOTS - 1)] != k + 1) __nanosleep(64);
+    __threadfence_block();
+    float a0[ME_CHUNK], a1[ME_CHUNK], a2[ME_CHUNK];
+#pragma unroll
+    for (int u = 0; u < ME_CHUNK; ++u) {
+      const int slot = (y0 + u) & (ME_RING - 1);
+      a0[u] = ring.s0[slot][lane]; a1[u] = ring.s1[slot][lane]; a2[u] = ring.s2[slot][lane];
+    }
+    __syncwarp();
+    if (lane == 0) finished[k & (ME_SLOTS - 1)] = k + 1;       // every lane holds the chunk in registers
+#pragma unroll
+    for (int u = 0; u < ME_CHUNK; ++u) {
+      const int y = y0 + u;
+      if (writer && y < H) {
+        const float A = a0[u] * 0.5f, Bv = a1[u], C = a2[u] * 0.5f;
+        const float e = (A + C) - sqrtf((A - C) * (A - C) + Bv * Bv);
+        eig[(size_t)y * W + cx] = e;
+        if (mk[u]) vmax = fmaxf(vmax, e);
+      }
+    }
   }
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) vmax = fmaxf(vmax, __shfl_xor_sync(KVFE_FULL_MASK, vmax, o));
@@ -456,13 +645,20 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   (void)H;
 }
 
+static int launch_mineig_any(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride, int mode_mask,
+                             int use_mask, cudaStream_t s) {
+  static const int mode = getenv("KVFE_MINEIG") ? atoi(getenv("KVFE_MINEIG")) : 2;      // diagnostic: 1 = mineig_kernel
+  const int groups = (dc.W + 29) / 30;
+  if (mode == 2) mineig_pipe_kernel<<<dim3(groups, dc.B), 32 * (ME_PRODUCERS + 1 + ME_FINISHERS), 0, s>>>(dc, db, img, img_stride, mode_mask, use_mask);
+  else mineig_kernel<<<dim3((groups + 3) / 4, dc.B), 128, 0, s>>>(dc, db, img, img_stride, mode_mask, use_mask);
+  return 1;
+}
+
 int launch_min_eig(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
                    int mode_mask, cudaStream_t s) {
   int n = 0;
   gftt_init_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, mode_mask); ++n;
-  int groups = (dc.W + 29) / 30;
-  dim3 grid((groups + 3) / 4, dc.B);
-  mineig_kernel<<<grid, 128, 0, s>>>(dc, db, img, img_stride, mode_mask, 0); ++n;
+  n += launch_mineig_any(dc, db, img, img_stride, mode_mask, 0, s);
   return n;
 }
 
@@ -472,8 +668,7 @@ int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, si
   gftt_init_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, mode_mask); ++n;
   mask_fill_kernel<<<dim3(64, dc.B), 256, 0, s>>>(dc, db.mask, db.st, mode_mask); ++n;
   mask_circles_kernel<<<dim3((dc.cap + 7) / 8, dc.B), 256, 0, s>>>(dc, db, circle_hw, circle_r, mode_mask); ++n;
-  int groups = (dc.W + 29) / 30;
-  mineig_kernel<<<dim3((groups + 3) / 4, dc.B), 128, 0, s>>>(dc, db, img, img_stride, mode_mask, 1); ++n;
+  n += launch_mineig_any(dc, db, img, img_stride, mode_mask, 1, s);
   cand_kernel<<<dim3((dc.W + 31) / 32, (dc.H + 63) / 64, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;
   int smem_keys = 16384;
   const int smem_bytes = (smem_keys + GREEDY_ACC_MAX) * 8 + 3 * GREEDY_SMEM_CELLS * 4 + smem_keys;
