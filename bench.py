@@ -50,13 +50,13 @@ T0_NS = 1403715273262142976
 
 # BASELINE.json configs[1..3]; B_alg of SURVEY 8(d) is computed from the measured keyframe ratio
 CONFIGS = {
-    "c2": dict(W=752, H=480, feats=300, batch=32, pool_streams=4, pool_frames=48,
+    "c2": dict(W=752, H=480, feats=300, batch=32, pool_streams=4, pool_frames=48, cpu_pairs=600,
                workload="Euroc stereo 752x480, 300 feats, 1xB200 batch=32 frame-pairs (BASELINE.json configs[1])"),
-    "c3": dict(W=1280, H=720, feats=500, batch=16, pool_streams=2, pool_frames=24,
+    "c3": dict(W=1280, H=720, feats=500, batch=16, pool_streams=2, pool_frames=24, cpu_pairs=200,
                workload="uHumans2-shaped 720p stereo 1280x720, 500 feats, 1xB200, 16 streams (BASELINE.json configs[2], without the Mesher)"),
-    "c4": dict(W=1920, H=1080, feats=1000, batch=1, pool_streams=1, pool_frames=24,
+    "c4": dict(W=1920, H=1080, feats=1000, batch=1, pool_streams=1, pool_frames=24, cpu_pairs=80,
                workload="Synthetic 1080p stereo 1920x1080, 1000 feats, one independent stream per B200 (BASELINE.json configs[3])"),
-    "c5": dict(W=3840, H=2160, feats=2000, batch=1, pool_streams=1, pool_frames=10,
+    "c5": dict(W=3840, H=2160, feats=2000, batch=1, pool_streams=1, pool_frames=10, cpu_pairs=24,
                workload="4K stereo 3840x2160, 2000 feats, one stream on ONE B200 (the single-GPU side of BASELINE.json configs[4])"),
 }
 
@@ -506,7 +506,7 @@ def run_gpu(args):
         # parity self-check: the first passes of slot 0 against the oracle fed the same frames and rotations
         parity, cpu = None, None
         if world == 1 and not args.no_cpu_baseline:
-            cpu, rec = cpu_baseline_single(name, 8, args.cpu_pairs, N_PAR)
+            cpu, rec = cpu_baseline_single(name, 8, args.cpu_pairs or cfg["cpu_pairs"], N_PAR)
             kept = res["e2e"]["warm"][3]
             bad = []
             for t, (okf, okp, olm) in enumerate(rec):
@@ -576,7 +576,7 @@ def main():
     ap.add_argument("--batch", type=int, default=0, help="streams per GPU (0: the config's)")
     ap.add_argument("--workers", type=int, default=0, help="dispatcher threads (0: library default)")
     ap.add_argument("--in-flight", type=int, default=0, help="steps in flight per stream, 1 or 2 (0: library default)")
-    ap.add_argument("--cpu-pairs", type=int, default=300, help="timed frame-pairs of the CPU baseline sample")
+    ap.add_argument("--cpu-pairs", type=int, default=0, help="timed frame-pairs of the CPU baseline sample (0: the config's, ~10-30 s of CPU work)")
     ap.add_argument("--impl", default="kvfe", choices=["kvfe", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pin", action="store_true", help="do not pin the rank to the GPU's NUMA node")

@@ -311,6 +311,10 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CUC(dmalloc(&db.eig_max, B));
   CUC(dmalloc(&db.cand, B * (size_t)dc.cand_cap));
   CUC(dmalloc(&db.cand_n, B));
+  CUC(dmalloc(&db.cand_hist, B * 2048));
+  CUC(dmalloc(&db.cand_sel, B * 16384));
+  CUC(dmalloc(&db.cand_sel_n, B));
+  CUC(dmalloc(&db.greedy_redo, B));
   CUC(dmalloc(&db.corner_idx, B * (size_t)dc.max_before_anms));
   CUC(dmalloc(&db.corner_n, B));
   CUC(dmalloc(&db.new_x, B * cap)); CUC(dmalloc(&db.new_y, B * cap)); CUC(dmalloc(&db.new_n, B));
@@ -440,7 +444,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  void* ptrs[] = {db.stage_img[0], db.stage_img[1], db.stage_seq, db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
+  void* ptrs[] = {db.cand_hist, db.cand_sel, db.cand_sel_n, db.greedy_redo, db.stage_img[0], db.stage_img[1], db.stage_seq, db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
                   db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,

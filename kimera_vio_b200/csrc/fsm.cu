@@ -242,7 +242,7 @@ __global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db, cudaG
   }
   int* m_ref = db.m_ref + (size_t)b * dc.cap;
   int* m_cur = db.m_cur + (size_t)b * dc.cap;
-  const int nm = block_find_matches(dc, db, fl, fk, false, m_ref, m_cur);
+  const int nm = block_find_matches(dc, db, fl, fk, false, m_ref, m_cur, db.scratch_i + (size_t)b * db.scratch_stride);
   double* tmp = db.rs_d + (size_t)b * db.rs_stride;
   double med = block_median_disparity(dc, db, fl, fk, m_ref, m_cur, nullptr, nm, tmp);
   // nr valid keypoints of frame k

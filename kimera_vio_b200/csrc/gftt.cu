@@ -13,9 +13,14 @@
 //
 // HBM traffic per keyframe image: image 1 B/px (L2 hits for the 3-row window), mask 1 B/px write
 // + read, response 4 B/px write + 9 reads served by L1/L2.  Non-compulsory.
+#include <cstdio>
 #include <cstdlib>
 
 #include "common.cuh"
+
+#define GREEDY_TOPK 12288        // candidates the first selection pass looks at (top-K prefilter)
+#define GREEDY_SEL_CAP 16384
+#define CAND_HIST_BINS 2048
 
 // ------------------------------------------------------------------------------------------------
 // mask
@@ -377,13 +382,18 @@ mineig_pipe_kernel(DevCfg dc, DevBuf db, const unsigned char* __restrict__ imgs,
   if (lane == 0 && vmax > -INFINITY) atomicMax(&db.eig_max[b], f2ord(vmax));
 }
 
+// grid B, block 256
 __global__ void gftt_init_kernel(DevCfg dc, DevBuf db, int mode_mask) {
-  int b = blockIdx.x * blockDim.x + threadIdx.x;
-  if (b >= dc.B) return;
+  const int b = blockIdx.x;
   if (!mode_on(db.st[b].mode, mode_mask)) return;
-  db.eig_max[b] = f2ord(-INFINITY);
-  db.cand_n[b] = 0;
-  db.corner_n[b] = 0;
+  if (threadIdx.x == 0) {
+    db.eig_max[b] = f2ord(-INFINITY);
+    db.cand_n[b] = 0;
+    db.corner_n[b] = 0;
+    db.cand_sel_n[b] = 0;
+    db.greedy_redo[b] = 0;
+  }
+  for (int i = threadIdx.x; i < CAND_HIST_BINS; i += blockDim.x) db.cand_hist[(size_t)b * CAND_HIST_BINS + i] = 0;
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -412,7 +422,80 @@ __global__ void __launch_bounds__(256) cand_kernel(DevCfg dc, DevBuf db, int mod
     int slot = atomicAdd(&db.cand_n[b], 1);
     if (slot < dc.cand_cap)
       db.cand[(size_t)b * dc.cand_cap + slot] =
-          ((unsigned long long)__float_as_uint(v) << 32) | (unsigned int)(y * W + x);
+          ((unsigned long long)__float_as_uint(v) << 32) | ((unsigned int)y << 16) | (unsigned int)x;   // (y, x) orders like y * W + x
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Top-K prefilter of the candidate list.  cv::goodFeaturesToTrack walks the candidates in descending order and
+// stops after maxCorners acceptances, and a candidate's fate depends only on BETTER candidates: the greedy
+// selection over the best K candidates decides them exactly as the full run would, and when it already yields
+// maxCorners corners the rest of the list is never looked at.  A 4K keyframe has > 10^5 candidates at
+// quality_level 0.001 but needs 2000 corners: the single-CTA selection over all of them took 18.7 ms; over the
+// best ~12 k it runs out of shared memory like the 752 x 480 case.  When the prefix does NOT reach maxCorners
+// the selection is repeated over the full list (second launch, exits at entry otherwise): always exact.
+//   cand_hist_kernel     histogram of the candidates' float bits relative to the maximum (128 bins per binade)
+//   cand_compact_kernel  threshold bin for >= GREEDY_TOPK candidates, compaction into cand_sel
+// ------------------------------------------------------------------------------------------------
+
+__device__ __forceinline__ int cand_bin(unsigned long long key, unsigned int maxbits) {
+  const int d = (int)(maxbits >> 16) - (int)((unsigned int)(key >> 32) >> 16);
+  return d < 0 ? 0 : (d > CAND_HIST_BINS - 1 ? CAND_HIST_BINS - 1 : d);
+}
+
+// grid (x, B)
+__global__ void __launch_bounds__(256) cand_hist_kernel(DevCfg dc, DevBuf db, int mode_mask) {
+  __shared__ int h[CAND_HIST_BINS];
+  const int b = blockIdx.y;
+  if (!mode_on(db.st[b].mode, mode_mask)) return;
+  const int n = min(db.cand_n[b], dc.cand_cap);
+  if (n <= GREEDY_TOPK) return;                     // small list: the selection reads it as it is
+  for (int i = threadIdx.x; i < CAND_HIST_BINS; i += blockDim.x) h[i] = 0;
+  __syncthreads();
+  const unsigned long long* gk = db.cand + (size_t)b * dc.cand_cap;
+  const unsigned int maxbits = __float_as_uint(ord2f(db.eig_max[b]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) atomicAdd(&h[cand_bin(gk[i], maxbits)], 1);
+  __syncthreads();
+  int* gh = db.cand_hist + (size_t)b * CAND_HIST_BINS;
+  for (int i = threadIdx.x; i < CAND_HIST_BINS; i += blockDim.x) if (h[i]) atomicAdd(&gh[i], h[i]);
+}
+
+// grid (x, B): every CTA finds the threshold bin from the finished histogram, then compacts its slice
+__global__ void __launch_bounds__(256) cand_compact_kernel(DevCfg dc, DevBuf db, int mode_mask) {
+  __shared__ int s_t;
+  const int b = blockIdx.y;
+  if (!mode_on(db.st[b].mode, mode_mask)) return;
+  const int n = min(db.cand_n[b], dc.cand_cap);
+  if (n <= GREEDY_TOPK) return;
+  const int* gh = db.cand_hist + (size_t)b * CAND_HIST_BINS;
+  if (threadIdx.x < 32) {                           // smallest t with count(bin <= t) >= GREEDY_TOPK
+    int carry = 0, t = CAND_HIST_BINS - 1;
+    bool found = false;
+    for (int base = 0; base < CAND_HIST_BINS && !found; base += 32) {
+      const int v = gh[base + threadIdx.x];
+      int incl = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int u = __shfl_up_sync(KVFE_FULL_MASK, incl, o);
+        if ((int)threadIdx.x >= o) incl += u;
+      }
+      const unsigned hit = __ballot_sync(KVFE_FULL_MASK, carry + incl >= GREEDY_TOPK);
+      if (hit) { t = base + __ffs(hit) - 1; found = true; }
+      carry += __shfl_sync(KVFE_FULL_MASK, incl, 31);
+    }
+    if (threadIdx.x == 0) s_t = t;
+  }
+  __syncthreads();
+  const int t = s_t;
+  const unsigned long long* gk = db.cand + (size_t)b * dc.cand_cap;
+  unsigned long long* sel = db.cand_sel + (size_t)b * GREEDY_SEL_CAP;
+  const unsigned int maxbits = __float_as_uint(ord2f(db.eig_max[b]));
+  for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+    const unsigned long long key = gk[i];
+    if (cand_bin(key, maxbits) <= t) {
+      const int pos = atomicAdd(&db.cand_sel_n[b], 1);
+      if (pos < GREEDY_SEL_CAP) sel[pos] = key;
+    }
   }
 }
 
@@ -440,19 +523,26 @@ __device__ void bitonic_desc(unsigned long long* k, int P) {
   }
 }
 
+__device__ int getenv_dbg = 0;
 #define GREEDY_ACC_MAX 2048
 #define GREEDY_SMEM_CELLS 4096
 
 // Layout of the dynamic shared memory: skey[smem_keys] (candidates ordered by (cell, key desc)),
 // then acc[GREEDY_ACC_MAX].  When the candidates do not fit, skey lives in the global candidate
 // buffer instead (same code path, slower).
-__global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf db, int mode_mask, int smem_keys) {
+// pass 0: the top-K prefix when the prefilter produced one (else the full list); pass 1: the full list, only for the
+// streams whose prefix did not reach maxCorners (greedy_redo)
+__global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf db, int mode_mask, int smem_keys, int pass) {
   extern __shared__ unsigned long long skeys[];
   const int b = blockIdx.x;
   if (!mode_on(db.st[b].mode, mode_mask)) return;
   const int W = dc.W, H = dc.H;
-  const int n = min(db.cand_n[b], dc.cand_cap);
-  unsigned long long* gk = db.cand + (size_t)b * dc.cand_cap;
+  const int n_all = min(db.cand_n[b], dc.cand_cap);
+  const int n_sel = db.cand_sel_n[b];
+  const bool prefix = pass == 0 && n_all > GREEDY_TOPK && n_sel <= GREEDY_SEL_CAP;
+  if (pass == 1 && !db.greedy_redo[b]) return;
+  const int n = prefix ? n_sel : n_all;
+  unsigned long long* gk = prefix ? db.cand_sel + (size_t)b * GREEDY_SEL_CAP : db.cand + (size_t)b * dc.cand_cap;
   int* corner = db.corner_idx + (size_t)b * dc.max_before_anms;
   __shared__ int s_total, s_chunk, wsum[32];
   const int md = dc.min_distance;
@@ -466,13 +556,16 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
     __syncthreads();
     bitonic_desc(k, P);
     int m = min(n, dc.max_before_anms);
-    for (int i = tid; i < m; i += blockDim.x) corner[i] = (int)(k[i] & 0xffffffffu);
+    for (int i = tid; i < m; i += blockDim.x) { const unsigned int lo = (unsigned int)(k[i] & 0xffffffffu); corner[i] = (int)(lo >> 16) * W + (int)(lo & 0xffffu); }
     if (tid == 0) db.corner_n[b] = m;
     return;
   }
 
   int* sc = db.scratch_i + (size_t)b * db.scratch_stride;
-  const int cell = md;                      // cvRound(minDistance), minDistance is an int parameter
+  // cells of k * minDistance (any cell >= minDistance keeps every conflict inside the 3x3 neighbourhood): the
+  // smallest k whose grid fits the shared-memory bookkeeping -- 1 at 752x480 / 20 px, 3 at 3840x2160
+  int cell = md;                            // cvRound(minDistance), minDistance is an int parameter
+  while ((long long)((W + cell - 1) / cell) * ((H + cell - 1) / cell) + 1 > GREEDY_SMEM_CELLS && cell < 64 * md) cell += md;
   const int gw = (W + cell - 1) / cell, gh = (H + cell - 1) / cell;
   const int ncells = gw * gh;
   // bookkeeping arrays: shared memory when the grid and the candidate list fit, else global scratch
@@ -493,8 +586,8 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   for (int i = tid; i <= ncells; i += blockDim.x) cstart[i] = 0;
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) {
-    int idx = (int)(gk[i] & 0xffffffffu);
-    int y = idx / W, x = idx - y * W;
+    const unsigned int lo = (unsigned int)(gk[i] & 0xffffffffu);
+    int y = (int)(lo >> 16), x = (int)(lo & 0xffffu);
     atomicAdd(&cstart[(y / cell) * gw + (x / cell) + 1], 1);
   }
   __syncthreads();
@@ -515,8 +608,8 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   __syncthreads();
   for (int i = tid; i < n; i += blockDim.x) {        // cstart[c+1] = cursor of cell c
     unsigned long long key = gk[i];
-    int idx = (int)(key & 0xffffffffu);
-    int y = idx / W, x = idx - y * W;
+    const unsigned int lo = (unsigned int)(key & 0xffffffffu);
+    int y = (int)(lo >> 16), x = (int)(lo & 0xffffu);
     int pos = atomicAdd(&cstart[(y / cell) * gw + (x / cell) + 1], 1);
     tmp[pos] = key;
   }
@@ -525,8 +618,8 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   // ---- 2. order every cell by key descending (rank by counting inside the cell)
   for (int i = tid; i < n; i += blockDim.x) {
     unsigned long long key = tmp[i];
-    int idx = (int)(key & 0xffffffffu);
-    int y = idx / W, x = idx - y * W;
+    const unsigned int lo = (unsigned int)(key & 0xffffffffu);
+    int y = (int)(lo >> 16), x = (int)(lo & 0xffffu);
     int c = (y / cell) * gw + (x / cell);
     int a0 = cstart[c], a1 = cstart[c + 1], rank = 0;
     for (int q = a0; q < a1; ++q) rank += tmp[q] > key;
@@ -539,61 +632,73 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   const int md2 = md * md;
   volatile unsigned char* vst = state;
   volatile int* vhead = head;
-  // Asynchronous relaxation: a cell thread keeps deciding its successive heads without waiting
-  // for a block-wide barrier; an accepted head immediately rejects the undecided candidates around
-  // it.  States only move 0 -> 1/2, readers of a stale 0 merely wait, and two conflicting heads can
-  // never both be accepted (the worse one always sees the better one as undecided or accepted).
+  // Asynchronous relaxation, one WARP per cell: the warps draw cells from a shared counter and decide a cell's
+  // successive heads; the 32 lanes test the candidates of the three neighbouring cell rows in parallel (a row's
+  // three cells are contiguous in the cell-ordered array).  An accepted head immediately rejects the undecided
+  // candidates within minDistance.  States only move 0 -> 1/2, readers of a stale 0 merely wait, and two
+  // conflicting heads can never both be accepted (the worse one always sees the better one as undecided or
+  // accepted; "rejected" wins over "wait": an accepted better neighbour within minDistance is final).
+  // (Round 1 gave every cell to one THREAD: the critical path was the busiest thread's serial scan -- 49 % of
+  // the samples sat in the barrier behind it, profiles/r02_ncu_kf.txt.)
+  __shared__ int s_next_cell;
+  const int lane = tid & 31;
   for (int round = 0; round < 100000; ++round) {
     int active = 0;
-    for (int c = tid; c < ncells; c += blockDim.x) {
+    if (tid == 0) s_next_cell = 0;
+    __syncthreads();
+    for (;;) {
+      int c = 0;
+      if (lane == 0) c = atomicAdd(&s_next_cell, 1);
+      c = __shfl_sync(KVFE_FULL_MASK, c, 0);
+      if (c >= ncells) break;
       const int e = cstart[c + 1];
+      int h = vhead[c];
+      if (h >= e) continue;
       const int cxl = c % gw, cyl = c / gw;
       const int x1 = max(cxl - 1, 0), x2 = min(cxl + 1, gw - 1), y1 = max(cyl - 1, 0), y2 = min(cyl + 1, gh - 1);
-      int h = vhead[c];
       for (int attempt = 0; attempt < 64; ++attempt) {
-        while (h < e && vst[h] != 0) ++h;              // skip decided entries
+        while (h < e && vst[h] != 0) ++h;              // skip decided entries (warp-uniform)
         if (h >= e) break;
         const unsigned long long kh = sk[h];
-        const int idx = (int)(kh & 0xffffffffu);
-        const int y = idx / W, x = idx - y * W;
-        int verdict = 1;                                // 1 accept, 0 wait, 2 reject
-        for (int yy = y1; yy <= y2 && verdict == 1; ++yy)
-          for (int xx = x1; xx <= x2 && verdict == 1; ++xx) {
-            const int d = yy * gw + xx;
-            if (d == c) continue;
-            const int de = cstart[d + 1];
-            for (int q = cstart[d]; q < de; ++q) {      // better candidates form a prefix of the cell
-              const unsigned long long kq = sk[q];
-              if (kq < kh) break;
-              const int sq = vst[q];
-              if (sq == 2) continue;
-              const int jdx = (int)(kq & 0xffffffffu);
-              const int jy = jdx / W, jx = jdx - jy * W;
-              const int ddx = x - jx, ddy = y - jy;
-              if (ddx * ddx + ddy * ddy < md2) { verdict = (sq == 1) ? 2 : 0; break; }
-            }
+        const unsigned int lo = (unsigned int)(kh & 0xffffffffu);
+        const int y = (int)(lo >> 16), x = (int)(lo & 0xffffu);
+        bool rej = false, wait = false;
+        for (int yy = y1; yy <= y2; ++yy) {
+          const int qa = cstart[yy * gw + x1], qb = cstart[yy * gw + x2 + 1];
+          for (int q = qa + lane; q < qb; q += 32) {
+            const unsigned long long kq = sk[q];
+            if (kq <= kh) continue;                       // only better candidates matter (kq == kh: the head itself)
+            const int sq = vst[q];
+            if (sq == 2) continue;
+            const unsigned int jlo = (unsigned int)(kq & 0xffffffffu);
+            const int ddx = x - (int)(jlo & 0xffffu), ddy = y - (int)(jlo >> 16);
+            if (ddx * ddx + ddy * ddy < md2) { if (sq == 1) rej = true; else wait = true; }
           }
-        if (verdict == 0) { active = 1; break; }        // blocked by an undecided better neighbour
-        vst[h] = (unsigned char)verdict;
-        if (verdict == 1) {
+        }
+        rej = __any_sync(KVFE_FULL_MASK, rej);
+        wait = __any_sync(KVFE_FULL_MASK, wait);
+        if (!rej && wait) { active = 1; break; }        // blocked by an undecided better neighbour
+        if (lane == 0) vst[h] = rej ? (unsigned char)2 : (unsigned char)1;
+        __syncwarp();
+        if (!rej) {
           __threadfence_block();
           for (int yy = y1; yy <= y2; ++yy) {           // reject the undecided candidates within minDistance
             const int qa = cstart[yy * gw + x1], qb = cstart[yy * gw + x2 + 1];
-            for (int q = qa; q < qb; ++q) {
+            for (int q = qa + lane; q < qb; q += 32) {
               if (vst[q] != 0) continue;
-              const int jdx = (int)(sk[q] & 0xffffffffu);
-              const int jy = jdx / W, jx = jdx - jy * W;
-              const int ddx = x - jx, ddy = y - jy;
+              const unsigned int jlo = (unsigned int)(sk[q] & 0xffffffffu);
+              const int ddx = x - (int)(jlo & 0xffffu), ddy = y - (int)(jlo >> 16);
               if (ddx * ddx + ddy * ddy < md2) vst[q] = 2;
             }
           }
+          __syncwarp();
         }
       }
       while (h < e && vst[h] != 0) ++h;
-      vhead[c] = h;
+      if (lane == 0) vhead[c] = h;
       if (h < e) active = 1;
     }
-    if (!__syncthreads_or(active)) break;
+    if (!__syncthreads_or(active)) { if (tid == 0 && getenv_dbg) printf("greedy b=%d pass=%d n=%d ncells=%d cell=%d rounds=%d\n", b, pass, n, ncells, cell, round + 1); break; }
   }
   __syncthreads();
   // ---- 4. gather accepted keys, sort them descending, emit the first maxCorners
@@ -640,8 +745,13 @@ __global__ void __launch_bounds__(1024, 1) sort_greedy_kernel(DevCfg dc, DevBuf 
   __syncthreads();
   bitonic_desc(acc, P);
   const int m = min(na, dc.max_before_anms);
-  for (int i = tid; i < m; i += blockDim.x) corner[i] = (int)(acc[i] & 0xffffffffu);
-  if (tid == 0) db.corner_n[b] = m;
+  if (prefix && na < dc.max_before_anms) {
+    // the best-K prefix does not fill maxCorners: the full list decides (pass 1)
+    if (tid == 0) db.greedy_redo[b] = 1;
+    return;
+  }
+  for (int i = tid; i < m; i += blockDim.x) { const unsigned int lo = (unsigned int)(acc[i] & 0xffffffffu); corner[i] = (int)(lo >> 16) * W + (int)(lo & 0xffffu); }
+  if (tid == 0) { db.corner_n[b] = m; db.greedy_redo[b] = 0; }
   (void)H;
 }
 
@@ -657,7 +767,7 @@ static int launch_mineig_any(const DevCfg& dc, const DevBuf& db, const unsigned 
 int launch_min_eig(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
                    int mode_mask, cudaStream_t s) {
   int n = 0;
-  gftt_init_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, mode_mask); ++n;
+  gftt_init_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask); ++n;
   n += launch_mineig_any(dc, db, img, img_stride, mode_mask, 0, s);
   return n;
 }
@@ -665,7 +775,7 @@ int launch_min_eig(const DevCfg& dc, const DevBuf& db, const unsigned char* img,
 int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
                 const int* circle_hw, int circle_r, int mode_mask, cudaStream_t s) {
   int n = 0;
-  gftt_init_kernel<<<(dc.B + 63) / 64, 64, 0, s>>>(dc, db, mode_mask); ++n;
+  gftt_init_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask); ++n;
   mask_fill_kernel<<<dim3(64, dc.B), 256, 0, s>>>(dc, db.mask, db.st, mode_mask); ++n;
   mask_circles_kernel<<<dim3((dc.cap + 7) / 8, dc.B), 256, 0, s>>>(dc, db, circle_hw, circle_r, mode_mask); ++n;
   n += launch_mineig_any(dc, db, img, img_stride, mode_mask, 1, s);
@@ -677,6 +787,10 @@ int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, si
     cudaFuncSetAttribute(sort_greedy_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, smem_bytes);
     attr_set = true;
   }
-  sort_greedy_kernel<<<dc.B, 1024, smem_bytes, s>>>(dc, db, mode_mask, smem_keys); ++n;
+  { static int once = 0; if (!once) { once = 1; if (getenv("KVFE_GREEDY_DEBUG")) { int one = 1; cudaMemcpyToSymbol(getenv_dbg, &one, sizeof(int)); } } }
+  cand_hist_kernel<<<dim3(32, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;
+  cand_compact_kernel<<<dim3(32, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;
+  sort_greedy_kernel<<<dc.B, 1024, smem_bytes, s>>>(dc, db, mode_mask, smem_keys, 0); ++n;
+  sort_greedy_kernel<<<dc.B, 1024, smem_bytes, s>>>(dc, db, mode_mask, smem_keys, 1); ++n;
   return n;
 }

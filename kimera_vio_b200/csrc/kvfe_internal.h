@@ -135,6 +135,10 @@ struct DevBuf {
   unsigned int* eig_max;       // B (ordered-int encoded float)
   unsigned long long* cand;    // B * cand_cap  (float bits << 32 | pixel index)
   int* cand_n;                 // B
+  int* cand_hist;              // B * 2048: histogram of the candidates' float bits below the maximum (top-K prefilter)
+  unsigned long long* cand_sel;  // B * 16384: the best candidates, compacted (unordered)
+  int* cand_sel_n;             // B
+  int* greedy_redo;            // B: the prefix did not reach maxCorners, the full list decides
   int* corner_idx;             // B * max_before_anms: accepted GFTT corners (pixel index), in order
   int* corner_n;               // B
   float *new_x, *new_y;        // B * cap: corners after NMS / subpix

@@ -305,7 +305,7 @@ __device__ void mono_ransac_body(const DevCfg& dc, const DevBuf& db, const int b
   int* inl = db.inl + (size_t)b * dc.cap;
   __shared__ double R12[9];
   __shared__ double model[12];
-  const int n = block_find_matches(dc, db, fs_ref, fs_cur, false, m_ref, m_cur);
+  const int n = block_find_matches(dc, db, fs_ref, fs_cur, false, m_ref, m_cur, db.scratch_i + (size_t)b * db.scratch_stride);
   if (threadIdx.x == 0) { s.nr_mono_put = n; s.nr_mono_inl = 0; }
   if (n == 0) {                       // Tracker.cpp:336-340
     if (threadIdx.x == 0) s.mono_status = KVFE_TRK_INVALID;
@@ -503,7 +503,7 @@ __global__ void __launch_bounds__(RS_THREADS) stereo_ransac_kernel(DevCfg dc, De
   int* inl = db.inl + (size_t)b * dc.cap;
   __shared__ double pose[12], info[9];
   __shared__ int s_ninl;
-  const int n = block_find_matches(dc, db, fs_ref, fs_cur, true, m_ref, m_cur);
+  const int n = block_find_matches(dc, db, fs_ref, fs_cur, true, m_ref, m_cur, db.scratch_i + (size_t)b * db.scratch_stride);
   const bool one_pt = dc.use_1pt && s.given_rot;
   int status;
   if (one_pt) {
