@@ -9,7 +9,9 @@ import pytest
 
 import helpers as H
 import scenes
+from kimera_vio_b200 import lib as kl
 from kimera_vio_b200.params import CameraParams, FrontendParams
+from kimera_vio_b200.rig import StereoRigSetup
 from oracle import frontend as ofe
 from oracle import ransac as ors
 from oracle.rig import StereoRig
@@ -380,6 +382,58 @@ def test_ransac_5pt_nister():
             t = gpose[:, 3] / np.linalg.norm(gpose[:, 3])
             assert np.allclose(t, T, atol=1e-3)
     ctx.close()
+
+
+@pytest.mark.parametrize("order", ["gcc", "clang"])
+def test_ransac_reference_seeded_scenes(order):
+    """The four RANSAC kernels on the scenes of the reference's own tests regenerated from the reference's RNG streams
+    (tests/golden/tracker_scenes.npz): inlier lists equal to the oracle's, which satisfy the reference's assertions
+    (tests/test_oracle_ransac.py::test_reference_seeded_scenes)."""
+    import dataclasses
+    from test_oracle_ransac import seeded_scenes
+    z, left, right = seeded_scenes()
+    rig = StereoRigSetup(left, right)
+
+    def make(**kw):
+        p = dataclasses.replace(FrontendParams.euroc(), **kw)
+        cfg = kl.make_config(p, rig.W, rig.H, batch=1, sobel_cpu_tail_start=H.sobel_cpu_tail_start(rig.W))
+        return kl.Context(cfg, rig.to_c())
+    bad = []
+    ctx = make(ransac_use_2point_mono=False, ransac_use_1point_stereo=False, ransac_max_iterations=1000)
+    for ci in range(3):
+        pre = "%s/5pt/%d/" % (order, ci)
+        st, gpose, ginl = ctx.ransac_mono(z[pre + "f_ref"], z[pre + "f_cur"], None)
+        want = [int(v) for v in z[pre + "oracle_inliers"]]
+        if not (st == ors.VALID and ginl == want and np.allclose(gpose[:, :3], z["R_5pt"], atol=1e-3)):
+            bad.append((pre, st, len(ginl), len(want)))
+    ctx.close()
+    ctx = make(ransac_threshold_stereo=0.3)
+    for ci in range(3):
+        pre = "%s/2pt/%d/" % (order, ci)
+        st, gpose, ginl = ctx.ransac_mono(z[pre + "f_ref"], z[pre + "f_cur"], np.eye(3))
+        want = [int(v) for v in z[pre + "oracle_inliers"]]
+        if not (st == ors.VALID and ginl == want and np.abs(gpose - z[pre + "oracle_pose"]).max() < 1e-9):
+            bad.append((pre, st, len(ginl), len(want)))
+    for ci in range(4):
+        pre = "%s/3pt/%d/" % (order, ci)
+        st, gpose, ginl = ctx.ransac_stereo_3pt(z[pre + "p_ref"], z[pre + "p_cur"])
+        want = [int(v) for v in z[pre + "oracle_inliers"]]
+        if not (ginl == want and st == (ors.VALID if len(want) >= 5 else ors.FEW_MATCHES) and np.abs(gpose - z[pre + "oracle_pose"]).max() < 1e-6):
+            bad.append((pre, st, len(ginl), len(want)))
+    ctx.close()
+    ctx = make()
+    R1 = np.asarray(z["R1"])
+    for ci in range(4):
+        pre = "%s/1pt/%d/" % (order, ci)
+        p_ref, p_cur = (R1 @ z[pre + "p_ref"].T).T, (R1 @ z[pre + "p_cur"].T).T
+        st, gpose, ginl, ginfo = ctx.ransac_stereo_1pt(z[pre + "ref_left"], z[pre + "ref_right"], z[pre + "cur_left"],
+                                                       z[pre + "cur_right"], p_ref, p_cur, R1 @ z["R_stereo"] @ R1.T)
+        want = [int(v) for v in z[pre + "oracle_inliers"]]
+        if not (ginl == want and st == int(z[pre + "oracle_status"]) and np.abs(gpose - z[pre + "oracle_pose"]).max() < 1e-6):
+            bad.append((pre, st, len(ginl), len(want)))
+    ctx.close()
+    H.diag("ransac_seeded", order=order, bad=bad)
+    assert not bad, bad
 
 
 @pytest.mark.parametrize("variant", ["no_nms", "topn", "binning_mask", "min_distance_8", "min_distance_3", "min_distance_1", "quality_1e-10"])

@@ -136,3 +136,80 @@ def test_voting_mahalanobis_formula_equivalence():
         above = rs.voting_1pt(rel, cov, np.float32(ref * (1 - 1e-3) - 1e-2))
         below = rs.voting_1pt(rel, cov, np.float32(ref * (1 + 1e-3) + 1e-2))
         assert above[0] == 1 and below[0] == 2, (ref, above[0], below[0])
+
+
+# ----------------------------------------------------------------------------------------------
+# The reference's tests on the reference's OWN seeded scenes (tests/golden/tracker_scenes.npz, built by
+# tests/golden/make_tracker_scenes.py from glibc srand(3)/rand() and libstdc++ normal_distribution streams)
+# ----------------------------------------------------------------------------------------------
+SCENES = os.path.join(ROOT, "tests", "golden", "tracker_scenes.npz")
+
+
+def seeded_scenes():
+    import json
+    z = np.load(SCENES)
+    cams = json.loads(str(z["cams_json"]))
+
+    def cam(d):
+        d = dict(d)
+        d["T_BS"] = np.asarray(d["T_BS"], np.float64)
+        return CameraParams(**d)
+    return z, cam(cams["left"]), cam(cams["right"])
+
+
+@pytest.mark.parametrize("order", ["gcc", "clang"])
+def test_reference_seeded_scenes(order):
+    """What tests/testTracker.cpp asserts -- every synthesized inlier kept, every outlier removed, VALID status,
+    translation / point tolerances -- must hold for the oracle on the scenes the reference's RNG streams produce;
+    and the oracle's inlier lists, iteration counts and number of RNG draws must equal the recorded ones."""
+    z, left, right = seeded_scenes()
+    rig = StereoRig(left, right)
+    R5, Rs = z["R_5pt"], z["R_stereo"]
+    # geometricOutlierRejection2d2d, testTracker.cpp:704-801 (ransac_max_iterations 1000)
+    for ci in range(3):
+        pre = "%s/5pt/%d/" % (order, ci)
+        planar, n_in, n_out = [int(v) for v in z[pre + "meta"]]
+        prob = rs.Problem2d2dNister(z[pre + "f_ref"], z[pre + "f_cur"], rs.rnd_table(16384))
+        ok, model, inl, its = rs.sac_ransac(prob, 1e-6, 1000, 0.995)
+        assert ok and inl == list(range(n_in))                       # :784-797
+        assert inl == [int(v) for v in z[pre + "oracle_inliers"]]
+        assert its == int(z[pre + "oracle_iterations"]) and prob._rnd_pos == int(z[pre + "oracle_draws"])
+        assert np.allclose(model, z[pre + "oracle_pose"], atol=1e-9)
+    # geometricOutlierRejection2d2dGivenRotation, testTracker.cpp:804-895
+    for ci in range(3):
+        pre = "%s/2pt/%d/" % (order, ci)
+        planar, n_in, n_out = [int(v) for v in z[pre + "meta"]]
+        prob = rs.Problem2d2dGivenRot(z[pre + "f_ref"], z[pre + "f_cur"], np.eye(3), rs.rnd_table(4096))
+        ok, model, inl, its = rs.sac_ransac(prob, 1e-6, 100, 0.995)
+        assert ok and inl == list(range(n_in))                       # :879-891
+        assert its == int(z[pre + "oracle_iterations"]) and prob._rnd_pos == int(z[pre + "oracle_draws"])
+        assert np.allclose(model[:, 3], [1.0, 0, 0], atol=1e-3)
+    # geometricOutlierRejection3d3d, testTracker.cpp:898-1039 (ransac_threshold_stereo 0.3)
+    T = np.array([rig.baseline, 0, 0])
+    for ci in range(4):
+        pre = "%s/3pt/%d/" % (order, ci)
+        planar, n_in, n_out = [int(v) for v in z[pre + "meta"]]
+        p_ref, p_cur = z[pre + "p_ref"], z[pre + "p_cur"]
+        prob = rs.Problem3d3d(p_ref, p_cur, rs.rnd_table(4096))
+        ok, pose, inl = rs.run_ransac(prob, 0.3, 100, 0.995)
+        assert ok and inl == list(range(n_in))                       # :985-1014
+        assert inl == [int(v) for v in z[pre + "oracle_inliers"]]
+        tol = 1e-3 if ci < 2 else 1e-1
+        if ci < 2:
+            assert np.allclose(pose[:, 3], T, atol=tol)              # :1019-1024
+        for i in range(n_in):                                        # :1029-1036
+            exp = pose[:, :3].T @ p_ref[i] - pose[:, :3].T @ pose[:, 3]
+            assert np.linalg.norm(exp - p_cur[i]) < tol
+    # geometricOutlierRejection3d3dGivenRotation, testTracker.cpp:1042-1185
+    calib = (rig.fx, rig.fy, rig.cx, rig.cy, rig.baseline)
+    for ci in range(4):
+        pre = "%s/1pt/%d/" % (order, ci)
+        planar, n_in, n_out = [int(v) for v in z[pre + "meta"]]
+        p_ref = (rig.R1 @ z[pre + "p_ref"].T).T
+        p_cur = (rig.R1 @ z[pre + "p_cur"].T).T
+        n = len(p_ref)
+        status, pose, inl, info = rs.outlier_rejection_3d3d_given_rotation(
+            z[pre + "ref_left"], z[pre + "ref_right"], z[pre + "cur_left"], z[pre + "cur_right"], p_ref, p_cur, calib,
+            [(i, i) for i in range(n)], rig.R1 @ Rs @ rig.R1.T, 1.0, 5)
+        assert inl == list(range(n_in))                              # :1133-1161
+        assert inl == [int(v) for v in z[pre + "oracle_inliers"]] and status == int(z[pre + "oracle_status"])
