@@ -110,6 +110,13 @@ typedef struct {
   int32_t mesh_2d;                      /* 0 off (default), 1 on */
   float subdiv_bounding_factor;         /* cv::Subdiv2D::initDelaunay: outer triangle at factor * max(w, h);
                                            0 = 6 (OpenCV 4.13, this repo's oracle); OpenCV <= 4.5 used 3 */
+  /* keys the reference parses that change the results when set: carried so that they are REJECTED or honoured,
+   * never silently ignored */
+  int32_t optimize_2d2d_pose_from_inliers;  /* VisionImuTrackerParams.cpp:119-122: nonlinear refinement of the RANSAC */
+  int32_t optimize_3d3d_pose_from_inliers;  /* pose (opengv optimize_nonlinear); must be 0: KVFE_ERR_INVALID_ARG otherwise */
+  int32_t equalize_image;               /* StereoMatchingParams.cpp:80-90 "equalizeImage": cv::equalizeHist on both raw
+                                           images (UtilsOpenCV::ReadAndConvertToGrayScale, UtilsOpenCV.cpp:390-403),
+                                           done on the device as the first kernels of a step */
 } kvfe_config;
 
 /* Stereo rig after cv::stereoRectify -- what StereoCamera::StereoCamera hands to its two
@@ -197,6 +204,54 @@ int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint8_t* right,
                        const float* kp_x, const float* kp_y, const double* versors, int n,
                        kvfe_stereo_out* out, uint8_t* left_rect, uint8_t* right_rect,
                        size_t rect_pitch);
+
+/* ---- the remaining public methods of the replaced classes, one call each (stage level) ------------------------- */
+/* UndistorterRectifier::checkUndistortedRectifiedLeftKeypoints (include/kimera-vio/frontend/UndistorterRectifier.h:106,
+ * src/frontend/UndistorterRectifier.cpp:138-211): crop the undistorted-rectified keypoint to the image, look the
+ * rectification maps up at its rounded position and compare with the distorted keypoint; status VALID or NO_LEFT_RECT,
+ * out = the cropped rectified keypoint.  cam: 0 left maps, 1 right maps.  The reference's default tolerance is 2.0. */
+int kvfe_check_rectified_keypoints(kvfe_ctx* ctx, int cam, const float* distorted_x, const float* distorted_y,
+                                   const float* rectified_x, const float* rectified_y, int n, float pixel_tolerance,
+                                   int32_t* status, float* out_x, float* out_y);
+/* UndistorterRectifier::distortUnrectifyKeypoints (UndistorterRectifier.h:113, .cpp:213-228) /
+ * StereoCamera::distortUnrectifyRightKeypoints (StereoCamera.cpp:262-267, cam = 1): maps at the rounded rectified
+ * position for VALID keypoints, (0, 0) otherwise. */
+int kvfe_distort_unrectify_keypoints(kvfe_ctx* ctx, int cam, const int32_t* status, const float* x, const float* y,
+                                     int n, float* out_x, float* out_y);
+/* StereoCamera::undistortRectifyLeftKeypoints (StereoCamera.cpp:236-260): cv::undistortPoints(K, D, R1, P1) followed
+ * by the check above with the default tolerance. */
+int kvfe_undistort_rectify_left_keypoints(kvfe_ctx* ctx, const float* x, const float* y, int n, int32_t* status,
+                                          float* rect_x, float* rect_y);
+/* StereoMatcher::getRightKeypointsRectified (include/kimera-vio/frontend/StereoMatcher.h:81, .cpp:196-281): the
+ * epipolar template search of every VALID rectified left keypoint on an already rectified image pair. */
+int kvfe_right_keypoints_rectified(kvfe_ctx* ctx, const uint8_t* left_rectified, const uint8_t* right_rectified, size_t pitch,
+                                   const int32_t* left_status, const float* left_x, const float* left_y, int n,
+                                   int32_t* right_status, float* right_x, float* right_y);
+/* StereoMatcher::getDepthFromRectifiedMatches (StereoMatcher.h:89, .cpp:425-483): depth = fx * baseline / disparity
+ * inside [minPointDist, maxPointDist]; right_status is updated in place (NO_DEPTH, or the left status). */
+int kvfe_depth_from_rectified_matches(kvfe_ctx* ctx, const int32_t* left_status, const float* left_x, int32_t* right_status,
+                                      const float* right_x, int n, double* depth);
+/* Tracker::computeMedianDisparity (include/kimera-vio/frontend/Tracker.h:215, .cpp:991-1018): *ok = 0 and nothing
+ * computed when there is no match. */
+int kvfe_compute_median_disparity(kvfe_ctx* ctx, const float* ref_x, const float* ref_y, int n_ref, const float* cur_x,
+                                  const float* cur_y, int n_cur, const int32_t* match_ref, const int32_t* match_cur,
+                                  int n_matches, double* median, int* ok);
+/* Tracker::getPoint3AndCovariance (Tracker.h:221, .cpp:772-818) for n rectified stereo points at once, with
+ * stereo_point_covariance = identity (what its caller passes, Tracker.cpp:560-563): out_points = R * p (p when R is
+ * NULL), out_cov = (R J)(R J)^T with J the Jacobian of gtsam::StereoCamera::backproject2 at (uL, uR, v). */
+int kvfe_point3_and_covariance(kvfe_ctx* ctx, const float* left_x, const float* right_x, const float* left_y,
+                               const double* points_3d, int n, const double* R, double* out_points, double* out_cov);
+/* Tracker::findOutliers / removeOutliersMono / removeOutliersStereo (Tracker.h:150-172, .cpp:836-917): pure
+ * bookkeeping on the caller's vectors (host logic, no device work -- the frame-level path does the same on the GPU). */
+int kvfe_find_outliers(int n_matches, const int32_t* inliers, int n_inliers, int32_t* outliers, int* n_outliers);
+int kvfe_remove_outliers_mono(const int32_t* inliers, int n_inliers, int64_t* ref_landmarks, int n_ref, int64_t* cur_landmarks,
+                              int n_cur, int32_t* match_ref, int32_t* match_cur, int* n_matches);
+int kvfe_remove_outliers_stereo(const int32_t* inliers, int n_inliers, int32_t* ref_right_status, double* ref_depth,
+                                double* ref_points_3d, int n_ref, int32_t* cur_right_status, double* cur_depth,
+                                double* cur_points_3d, int n_cur, int32_t* match_ref, int32_t* match_cur, int* n_matches);
+
+/* cv::equalizeHist as UtilsOpenCV::ReadAndConvertToGrayScale applies it (src/utils/UtilsOpenCV.cpp:390-403), one image. */
+int kvfe_equalize_hist(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* out, size_t out_pitch);
 
 /* Mesher::createMesh2dImpl (src/mesh/Mesher.cpp:1712-1817): cv::Subdiv2D(rect(0, 0, width, height)), insert the
  * keypoints that lie inside the image, getTriangleList, keep the triangles with all vertices inside.  triangles:

@@ -80,6 +80,7 @@ extern "C" void kvfe_config_default(kvfe_config* c) {
   c->min_number_features = 0; c->use_stereo_tracking = 1; c->use_ransac = 1;
   c->max_disparity_since_lkf = 1000.0;
   c->mesh_2d = 0; c->subdiv_bounding_factor = 0.f;
+  c->optimize_2d2d_pose_from_inliers = 0; c->optimize_3d3d_pose_from_inliers = 0; c->equalize_image = 0;
 }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -214,6 +215,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   if (c.pose_2d2d_algorithm != 1) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "pose_2d2d_algorithm must be 1 (NISTER)");
   if (c.klt_max_level < 0 || c.klt_max_level >= KVFE_MAX_LEVELS) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "klt_max_level must be in [0,%d]", KVFE_MAX_LEVELS - 1);
   if (c.min_distance < 0) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "min_distance must be >= 0");
+  if (c.optimize_2d2d_pose_from_inliers || c.optimize_3d3d_pose_from_inliers)
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "optimize_{2d2d,3d3d}_pose_from_inliers (nonlinear refinement of the RANSAC pose) is not implemented");
 
   ctx = new kvfe_ctx();
   memset(ctx, 0, sizeof(*ctx));
@@ -390,6 +393,7 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   }
   CUC(dmalloc(&db.st, B));
   dc.mesh_on = c.mesh_2d ? 1 : 0;
+  dc.equalize = c.equalize_image ? 1 : 0;
   dc.subdiv_factor = c.subdiv_bounding_factor > 0.f ? c.subdiv_bounding_factor : 6.f;
   packet_layout(cap, dc.mesh_on != 0, db.pk_off, &db.packet_bytes);
   launch_mesh_init(dc);
@@ -783,6 +787,260 @@ extern "C" int kvfe_sparse_stereo(kvfe_ctx* ctx, const uint8_t* left, const uint
   return KVFE_OK;
 }
 
+// ---- boundary completion: the remaining public methods of UndistorterRectifier / StereoCamera / StereoMatcher /
+// Tracker as stage-level calls (host buffers, synchronous, stream 0 of the context as scratch) -------------
+namespace {
+// n floats / ints of several host arrays through one device allocation
+struct StageScratch {
+  unsigned char* p = nullptr;
+  cudaError_t alloc(size_t bytes) { return cudaMalloc((void**)&p, bytes ? bytes : 16); }
+  ~StageScratch() { if (p) cudaFree(p); }
+};
+}  // namespace
+
+extern "C" int kvfe_check_rectified_keypoints(kvfe_ctx* ctx, int cam, const float* distorted_x, const float* distorted_y,
+                                              const float* rectified_x, const float* rectified_y, int n, float pixel_tolerance,
+                                              int32_t* status, float* out_x, float* out_y) {
+  if (!ctx || !distorted_x || !distorted_y || !rectified_x || !rectified_y || !status || !out_x || !out_y || cam < 0 || cam > 1)
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "bad argument");
+  if (n <= 0) return KVFE_OK;
+  StageScratch d;
+  CU(d.alloc(7 * (size_t)n * 4));
+  float* f = reinterpret_cast<float*>(d.p);
+  const float* src[4] = {distorted_x, distorted_y, rectified_x, rectified_y};
+  for (int k = 0; k < 4; ++k) CU(cudaMemcpyAsync(f + (size_t)k * n, src[k], n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  int* dst = reinterpret_cast<int*>(f + 4 * (size_t)n);
+  ctx->launches += launch_check_rect_raw(ctx->dc, ctx->d_cam, cam, f, f + n, f + 2 * (size_t)n, f + 3 * (size_t)n, n, pixel_tolerance, dst,
+                                         f + 5 * (size_t)n, f + 6 * (size_t)n, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(status, dst, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_x, f + 5 * (size_t)n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_y, f + 6 * (size_t)n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_distort_unrectify_keypoints(kvfe_ctx* ctx, int cam, const int32_t* status, const float* x, const float* y,
+                                                int n, float* out_x, float* out_y) {
+  if (!ctx || !status || !x || !y || !out_x || !out_y || cam < 0 || cam > 1) return set_err(ctx, KVFE_ERR_INVALID_ARG, "bad argument");
+  if (n <= 0) return KVFE_OK;
+  StageScratch d;
+  CU(d.alloc(5 * (size_t)n * 4));
+  float* f = reinterpret_cast<float*>(d.p);
+  int* ds = reinterpret_cast<int*>(f + 4 * (size_t)n);
+  CU(cudaMemcpyAsync(f, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f + n, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(ds, status, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_distort_unrectify_raw(ctx->dc, ctx->d_cam, cam, ds, f, f + n, n, f + 2 * (size_t)n, f + 3 * (size_t)n, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(out_x, f + 2 * (size_t)n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_y, f + 3 * (size_t)n, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+// the frame-level stereo kernels work on frame slot 0 of stream 0: a stage call fills the fields a kernel reads
+static int stage_frame_begin(kvfe_ctx* ctx, int n) {
+  if (n > ctx->dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, ctx->dc.cap);
+  if (ctx->n_submitted != ctx->n_waited) return set_err(ctx, KVFE_ERR_STATE, "stage call with frame-level steps in flight");
+  RET(park_other_streams(ctx));
+  return set_stage_state(ctx, 2, 0, n);
+}
+
+extern "C" int kvfe_undistort_rectify_left_keypoints(kvfe_ctx* ctx, const float* x, const float* y, int n, int32_t* status,
+                                                     float* rect_x, float* rect_y) {
+  if (!ctx || !x || !y || !status || !rect_x || !rect_y) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (n <= 0) return KVFE_OK;
+  RET(stage_frame_begin(ctx, n));
+  const FrameSoA& f = ctx->db.fr;
+  CU(cudaMemcpyAsync(f.kx, x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.ky, y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_sparse_stereo_part(ctx->dc, ctx->db, ctx->d_cam, 1 << 2, 0, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(status, f.lstat, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(rect_x, f.lrx, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(rect_y, f.lry, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_right_keypoints_rectified(kvfe_ctx* ctx, const uint8_t* left_rectified, const uint8_t* right_rectified, size_t pitch,
+                                              const int32_t* left_status, const float* left_x, const float* left_y, int n,
+                                              int32_t* right_status, float* right_x, float* right_y) {
+  if (!ctx || !left_rectified || !right_rectified || !left_status || !left_x || !left_y || !right_status || !right_x || !right_y)
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (n <= 0) return KVFE_OK;
+  RET(stage_frame_begin(ctx, n));
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  const FrameSoA& f = db.fr;
+  RET(upload_image(ctx, db.rectL, dc.pitch, left_rectified, pitch));
+  RET(upload_image(ctx, db.rectR, dc.pitch, right_rectified, pitch));
+  CU(cudaMemcpyAsync(f.lstat, left_status, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.lrx, left_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.lry, left_y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_sparse_stereo_part(dc, db, ctx->d_cam, 1 << 2, 1, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(right_status, f.rstat, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(right_x, f.rrx, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(right_y, f.rry, n * sizeof(float), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_depth_from_rectified_matches(kvfe_ctx* ctx, const int32_t* left_status, const float* left_x,
+                                                 int32_t* right_status, const float* right_x, int n, double* depth) {
+  if (!ctx || !left_status || !left_x || !right_status || !right_x || !depth) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (n <= 0) return KVFE_OK;
+  RET(stage_frame_begin(ctx, n));
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  const FrameSoA& f = db.fr;
+  CU(cudaMemcpyAsync(f.lstat, left_status, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.lrx, left_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.rstat, right_status, n * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.rrx, right_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemsetAsync(f.rry, 0, n * sizeof(float), ctx->stream));
+  CU(cudaMemsetAsync(f.versor, 0, 3 * (size_t)n * sizeof(double), ctx->stream));
+  ctx->launches += launch_sparse_stereo_part(dc, db, ctx->d_cam, 1 << 2, 2, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(right_status, f.rstat, n * sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(depth, f.depth, n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_compute_median_disparity(kvfe_ctx* ctx, const float* ref_x, const float* ref_y, int n_ref, const float* cur_x,
+                                             const float* cur_y, int n_cur, const int32_t* match_ref, const int32_t* match_cur,
+                                             int n_matches, double* median, int* ok) {
+  if (!ctx || !ref_x || !ref_y || !cur_x || !cur_y || !median || !ok || (n_matches > 0 && (!match_ref || !match_cur)))
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  if (n_ref > dc.cap || n_cur > dc.cap || n_matches > dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "more keypoints than capacity %d", dc.cap);
+  for (int i = 0; i < n_matches; ++i)
+    if (match_ref[i] < 0 || match_ref[i] >= n_ref || match_cur[i] < 0 || match_cur[i] >= n_cur) return set_err(ctx, KVFE_ERR_INVALID_ARG, "match index out of range");
+  *median = 0.0; *ok = 0;
+  if (n_matches <= 0) return KVFE_OK;                 // Tracker.cpp:995-999: false, nothing computed
+  RET(stage_frame_begin(ctx, n_cur));
+  const FrameSoA& f = db.fr;
+  CU(cudaMemcpyAsync(f.kx, cur_x, n_cur * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));                   // slot 0 = cur
+  CU(cudaMemcpyAsync(f.ky, cur_y, n_cur * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f.kx + dc.cap, ref_x, n_ref * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));          // slot 1 = ref
+  CU(cudaMemcpyAsync(f.ky + dc.cap, ref_y, n_ref * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(db.m_ref, match_ref, n_matches * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(db.m_cur, match_cur, n_matches * sizeof(int), cudaMemcpyHostToDevice, ctx->stream));
+  StageScratch d;
+  CU(d.alloc(2 * sizeof(double)));
+  ctx->launches += launch_median_disparity_raw(dc, db, n_matches, reinterpret_cast<double*>(d.p), ctx->stream);
+  CHECK_LAUNCH();
+  double h[2] = {0, 0};
+  CU(cudaMemcpyAsync(h, d.p, sizeof(h), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  *median = h[0]; *ok = h[1] != 0.0;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_point3_and_covariance(kvfe_ctx* ctx, const float* left_x, const float* right_x, const float* left_y,
+                                          const double* points_3d, int n, const double* R, double* out_points, double* out_cov) {
+  if (!ctx || !left_x || !right_x || !left_y || !points_3d || !out_points || !out_cov) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (n <= 0) return KVFE_OK;
+  StageScratch d;
+  const size_t fbytes = 3 * (size_t)n * sizeof(float), pbytes = 3 * (size_t)n * sizeof(double);
+  const size_t off_p = (fbytes + 15) & ~(size_t)15, off_R = off_p + pbytes, off_op = off_R + 16 * sizeof(double), off_cov = off_op + pbytes;
+  CU(d.alloc(off_cov + 9 * (size_t)n * sizeof(double)));
+  float* f = reinterpret_cast<float*>(d.p);
+  double* dp = reinterpret_cast<double*>(d.p + off_p);
+  double* dR = reinterpret_cast<double*>(d.p + off_R);
+  double* dop = reinterpret_cast<double*>(d.p + off_op);
+  double* dcov = reinterpret_cast<double*>(d.p + off_cov);
+  CU(cudaMemcpyAsync(f, left_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f + n, right_x, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(f + 2 * (size_t)n, left_y, n * sizeof(float), cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaMemcpyAsync(dp, points_3d, pbytes, cudaMemcpyHostToDevice, ctx->stream));
+  if (R) CU(cudaMemcpyAsync(dR, R, 9 * sizeof(double), cudaMemcpyHostToDevice, ctx->stream));
+  ctx->launches += launch_point3_cov_raw(ctx->dc, f, f + n, f + 2 * (size_t)n, dp, n, R ? dR : nullptr, dop, dcov, ctx->stream);
+  CHECK_LAUNCH();
+  CU(cudaMemcpyAsync(out_points, dop, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaMemcpyAsync(out_cov, dcov, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+// Tracker::findOutliers (Tracker.cpp:836-853): the match indices that are not in the (sorted or unsorted) inlier list,
+// ascending.  Host logic: the reference's own implementation is a std::set_difference on the host.
+extern "C" int kvfe_find_outliers(int n_matches, const int32_t* inliers, int n_inliers, int32_t* outliers, int* n_outliers) {
+  if (n_matches < 0 || n_inliers < 0 || (n_inliers > 0 && !inliers) || !outliers || !n_outliers) return KVFE_ERR_INVALID_ARG;
+  std::vector<char> in(n_matches, 0);
+  for (int i = 0; i < n_inliers; ++i) if (inliers[i] >= 0 && inliers[i] < n_matches) in[inliers[i]] = 1;
+  int m = 0;
+  for (int i = 0; i < n_matches; ++i) if (!in[i]) outliers[m++] = i;
+  *n_outliers = m;
+  return KVFE_OK;
+}
+// Tracker::removeOutliersMono (Tracker.cpp:856-882): landmarks of the outlier matches become -1 in both frames and the
+// match list is reduced to the inliers (in inlier-list order).
+extern "C" int kvfe_remove_outliers_mono(const int32_t* inliers, int n_inliers, int64_t* ref_landmarks, int n_ref,
+                                         int64_t* cur_landmarks, int n_cur, int32_t* match_ref, int32_t* match_cur, int* n_matches) {
+  if (!ref_landmarks || !cur_landmarks || !match_ref || !match_cur || !n_matches || (n_inliers > 0 && !inliers)) return KVFE_ERR_INVALID_ARG;
+  const int nm = *n_matches;
+  std::vector<int32_t> out(nm > 0 ? nm : 1);
+  int no = 0;
+  int rc = kvfe_find_outliers(nm, inliers, n_inliers, out.data(), &no);
+  if (rc != KVFE_OK) return rc;
+  for (int k = 0; k < no; ++k) {
+    const int ir = match_ref[out[k]], ic = match_cur[out[k]];
+    if (ir < 0 || ir >= n_ref || ic < 0 || ic >= n_cur) return KVFE_ERR_INVALID_ARG;
+    ref_landmarks[ir] = -1; cur_landmarks[ic] = -1;
+  }
+  std::vector<int32_t> mr(n_inliers > 0 ? n_inliers : 1), mc(n_inliers > 0 ? n_inliers : 1);
+  for (int k = 0; k < n_inliers; ++k) {
+    if (inliers[k] < 0 || inliers[k] >= nm) return KVFE_ERR_INVALID_ARG;
+    mr[k] = match_ref[inliers[k]]; mc[k] = match_cur[inliers[k]];
+  }
+  for (int k = 0; k < n_inliers; ++k) { match_ref[k] = mr[k]; match_cur[k] = mc[k]; }
+  *n_matches = n_inliers;
+  return KVFE_OK;
+}
+// Tracker::removeOutliersStereo (Tracker.cpp:884-917): outlier matches get right status FAILED_ARUN, depth 0 and a
+// zero 3-D point in both frames; the match list is reduced to the inliers.
+extern "C" int kvfe_remove_outliers_stereo(const int32_t* inliers, int n_inliers, int32_t* ref_right_status, double* ref_depth,
+                                           double* ref_points_3d, int n_ref, int32_t* cur_right_status, double* cur_depth,
+                                           double* cur_points_3d, int n_cur, int32_t* match_ref, int32_t* match_cur, int* n_matches) {
+  if (!ref_right_status || !ref_depth || !ref_points_3d || !cur_right_status || !cur_depth || !cur_points_3d || !match_ref || !match_cur ||
+      !n_matches || (n_inliers > 0 && !inliers)) return KVFE_ERR_INVALID_ARG;
+  const int nm = *n_matches;
+  std::vector<int32_t> out(nm > 0 ? nm : 1);
+  int no = 0;
+  int rc = kvfe_find_outliers(nm, inliers, n_inliers, out.data(), &no);
+  if (rc != KVFE_OK) return rc;
+  for (int k = 0; k < no; ++k) {
+    const int ir = match_ref[out[k]], ic = match_cur[out[k]];
+    if (ir < 0 || ir >= n_ref || ic < 0 || ic >= n_cur) return KVFE_ERR_INVALID_ARG;
+    ref_right_status[ir] = KVFE_KP_FAILED_ARUN; ref_depth[ir] = 0.0;
+    cur_right_status[ic] = KVFE_KP_FAILED_ARUN; cur_depth[ic] = 0.0;
+    for (int a = 0; a < 3; ++a) { ref_points_3d[3 * (size_t)ir + a] = 0.0; cur_points_3d[3 * (size_t)ic + a] = 0.0; }
+  }
+  std::vector<int32_t> mr(n_inliers > 0 ? n_inliers : 1), mc(n_inliers > 0 ? n_inliers : 1);
+  for (int k = 0; k < n_inliers; ++k) {
+    if (inliers[k] < 0 || inliers[k] >= nm) return KVFE_ERR_INVALID_ARG;
+    mr[k] = match_ref[inliers[k]]; mc[k] = match_cur[inliers[k]];
+  }
+  for (int k = 0; k < n_inliers; ++k) { match_ref[k] = mr[k]; match_cur[k] = mc[k]; }
+  *n_matches = n_inliers;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_equalize_hist(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* out, size_t out_pitch) {
+  if (!ctx || !img || !out) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (ctx->n_submitted != ctx->n_waited) return set_err(ctx, KVFE_ERR_STATE, "stage call with frame-level steps in flight");
+  const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
+  unsigned char* L = db.pyr[0] + dc.lvl_off[0];
+  RET(upload_image(ctx, L, dc.pitch, img, pitch));
+  ctx->launches += launch_equalize(dc, L, dc.pyr_stride, 1, nullptr, 0, ctx->stream);
+  CHECK_LAUNCH();
+  RET(download_image(ctx, out, out_pitch, L, dc.pitch));
+  CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
 extern "C" int kvfe_mesh_2d(kvfe_ctx* ctx, const float* kp_x, const float* kp_y, int n, float* triangles, int max_triangles,
                             int* n_triangles) {
   if (!ctx || !kp_x || !kp_y || !triangles || !n_triangles || max_triangles < 0) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
@@ -921,6 +1179,10 @@ static int enqueue_part_track(kvfe_ctx* ctx, unsigned long long cond, long long*
   const int cur = ctx->cur_slot, prev = cur ^ 1;
   long long n = 0;
   n += launch_prep(dc, db, ctx->d_cam, ctx->in_ts ? ctx->in_ts : ctx->d_ts, ctx->in_R ? ctx->in_R : ctx->d_Rin, io, s);
+  if (dc.equalize) {       // what the reference's data provider does at load time (UtilsOpenCV.cpp:390-403)
+    n += launch_equalize(dc, db.pyr[cur] + dc.lvl_off[0], dc.pyr_stride, dc.B, nullptr, 0, s);
+    n += launch_equalize(dc, db.right_raw, dc.img_stride, dc.B, nullptr, 0, s);
+  }
   n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
   n += launch_track_pre(dc, db, s);
   n += launch_lk(dc, db, prev, cur, s);
@@ -1381,6 +1643,10 @@ extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_d
   long long n = 0;
   CU(cudaEventRecord(ev[0], s));
   n += launch_prep(dc, db, ctx->d_cam, ctx->d_ts, ctx->d_Rin, nullptr, s);
+  if (dc.equalize) {
+    n += launch_equalize(dc, db.pyr[cur] + dc.lvl_off[0], dc.pyr_stride, dc.B, nullptr, 0, s);
+    n += launch_equalize(dc, db.right_raw, dc.img_stride, dc.B, nullptr, 0, s);
+  }
   n += launch_pyramid(dc, db.pyr[cur], dc.B, s);
   CU(cudaEventRecord(ev[1], s));
   n += launch_track_pre(dc, db, s);

@@ -122,6 +122,8 @@ struct DevCfg {          // passed by value to kernels
   double fx, fy, cxr, cyr, baseline;
   // mesher
   int mesh_on; float subdiv_factor;
+  // ingest
+  int equalize;          // cv::equalizeHist on both raw images before anything else (stereo_matching_params.equalize_image)
 };
 
 struct DevBuf {
@@ -244,7 +246,15 @@ int launch_undistort(const DevCfg& dc, const CamModel* d_cam, int cam, int use_R
                      const float* x, const float* y, int n, float* ox, float* oy, cudaStream_t s);
 int launch_bearing(const DevCfg& dc, const CamModel* d_cam, const float* x, const float* y, int n,
                    double* versors, cudaStream_t s);
+int launch_check_rect_raw(const DevCfg& dc, const CamModel* d_cam, int cam, const float* dx, const float* dy, const float* ux,
+                          const float* uy, int n, float tol, int* status, float* ox, float* oy, cudaStream_t s);
+int launch_distort_unrectify_raw(const DevCfg& dc, const CamModel* d_cam, int cam, const int* status, const float* x,
+                                 const float* y, int n, float* ox, float* oy, cudaStream_t s);
+int launch_sparse_stereo_part(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, int mode_mask, int which, cudaStream_t s);
 // ransac.cu
+int launch_median_disparity_raw(const DevCfg& dc, const DevBuf& db, int m, double* out, cudaStream_t s);
+int launch_point3_cov_raw(const DevCfg& dc, const float* ul, const float* ur, const float* v, const double* p3d, int n,
+                          const double* Rm, double* op, double* ocov, cudaStream_t s);
 int launch_ransac_mono(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s);
 int launch_ransac_stereo(const DevCfg& dc, const DevBuf& db, int mode_mask, cudaStream_t s);
 int launch_ransac_mono_raw(const DevCfg& dc, const DevBuf& db, const double* f_ref, const double* f_cur,
@@ -271,6 +281,9 @@ int launch_decide(const DevCfg& dc, const DevBuf& db, unsigned long long cond, c
 int launch_detect_pre(const DevCfg& dc, const DevBuf& db, int mode_mask, int* kf_counter, cudaStream_t s);
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
+// ingest.cu
+int launch_equalize(const DevCfg& dc, unsigned char* imgs, size_t img_stride, int nimg, const StreamState* st, int mode_mask,
+                    cudaStream_t s);
 // mesh.cu
 bool mesh_fits_smem(const DevCfg& dc);
 size_t mesh_global_ws_ints(const DevCfg& dc);

@@ -648,3 +648,36 @@ int launch_ransac_1pt_raw(const DevCfg& dc, const DevBuf& db, const float* rl, c
                                            status);
   return 1;
 }
+
+
+// ---- stage-level statics of the Tracker (include/kvfe.h, "boundary completion") -------------------------
+// Tracker::computeMedianDisparity (Tracker.cpp:991-1018) over frame slots 1 (ref) / 0 (cur) of stream 0 and the
+// match list in m_ref / m_cur; out[0] = median, out[1] = 1 when there is at least one match
+__global__ void __launch_bounds__(256) median_disparity_raw_kernel(DevCfg dc, DevBuf db, int m, double* out) {
+  const double med = block_median_disparity(dc, db, 1, 0, db.m_ref, db.m_cur, nullptr, m, db.rs_d);
+  if (threadIdx.x == 0) { out[0] = med < 0.0 ? 0.0 : med; out[1] = med < 0.0 ? 0.0 : 1.0; }
+}
+// Tracker::getPoint3AndCovariance (Tracker.cpp:772-818) with stereo_point_covariance = I (its only caller,
+// Tracker.cpp:560-563): p' = R p, cov = (R J)(R J)^T, J = d backproject2 / d (uL, uR, v)
+__global__ void __launch_bounds__(128) point3_cov_raw_kernel(DevCfg dc, const float* __restrict__ ul, const float* __restrict__ ur,
+                                                             const float* __restrict__ v, const double* __restrict__ p3d, int n,
+                                                             const double* __restrict__ Rm, double* __restrict__ op,
+                                                             double* __restrict__ ocov) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  double c[9];
+  point_cov(dc, ul[i], ur[i], v[i], Rm, c);
+  for (int k = 0; k < 9; ++k) ocov[9 * (size_t)i + k] = c[k];
+  double p[3] = {p3d[3 * (size_t)i], p3d[3 * (size_t)i + 1], p3d[3 * (size_t)i + 2]};
+  if (Rm) { double q[3]; matvec3(Rm, p, q); p[0] = q[0]; p[1] = q[1]; p[2] = q[2]; }
+  for (int k = 0; k < 3; ++k) op[3 * (size_t)i + k] = p[k];
+}
+int launch_median_disparity_raw(const DevCfg& dc, const DevBuf& db, int m, double* out, cudaStream_t s) {
+  median_disparity_raw_kernel<<<1, 256, 0, s>>>(dc, db, m, out);
+  return 1;
+}
+int launch_point3_cov_raw(const DevCfg& dc, const float* ul, const float* ur, const float* v, const double* p3d, int n,
+                          const double* Rm, double* op, double* ocov, cudaStream_t s) {
+  point3_cov_raw_kernel<<<(n + 127) / 128, 128, 0, s>>>(dc, ul, ur, v, p3d, n, Rm, op, ocov);
+  return 1;
+}

@@ -363,3 +363,61 @@ int launch_bearing(const DevCfg& dc, const CamModel* d_cam, const float* x, cons
   (void)dc;
   return 1;
 }
+
+
+// ---- stage-level pieces of the sparse stereo path (include/kvfe.h, "boundary completion") ----------------
+// UndistorterRectifier::checkUndistortedRectifiedLeftKeypoints (UndistorterRectifier.cpp:138-211) with the
+// caller's undistorted keypoints and pixel tolerance; cam selects the maps (0: left, 1: right).
+__global__ void __launch_bounds__(128) check_rect_raw_kernel(DevCfg dc, const CamModel* __restrict__ cams, int cam,
+                                                             const float* __restrict__ dx, const float* __restrict__ dy,
+                                                             const float* __restrict__ ux_in, const float* __restrict__ uy_in, int n,
+                                                             float tol, int* __restrict__ status, float* __restrict__ ox,
+                                                             float* __restrict__ oy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float ux = ux_in[i], uy = uy_in[i];
+  bool cropped = false;                              // UtilsOpenCV::cropToSize
+  const float mw = (float)(dc.W - 1), mh = (float)(dc.H - 1);
+  if (ux > mw) { ux = mw; cropped = true; } else if (ux < 0.0f) { ux = 0.0f; cropped = true; }
+  if (uy > mh) { uy = mh; cropped = true; } else if (uy < 0.0f) { uy = 0.0f; cropped = true; }
+  const int rx = clampi((int)roundf(ux), 0, dc.W - 1), ry = clampi((int)roundf(uy), 0, dc.H - 1);
+  float ex, ey;
+  rect_map_at(cams[cam], rx, ry, &ex, &ey);
+  int st = KVFE_KP_VALID;
+  if (cropped || fabsf(dx[i] - ex) > tol || fabsf(dy[i] - ey) > tol) st = KVFE_KP_NO_LEFT_RECT;
+  status[i] = st; ox[i] = ux; oy[i] = uy;
+}
+// UndistorterRectifier::distortUnrectifyKeypoints (UndistorterRectifier.cpp:213-228)
+__global__ void __launch_bounds__(128) distort_unrectify_raw_kernel(DevCfg dc, const CamModel* __restrict__ cams, int cam,
+                                                                    const int* __restrict__ status, const float* __restrict__ x,
+                                                                    const float* __restrict__ y, int n, float* __restrict__ ox,
+                                                                    float* __restrict__ oy) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  float rx = 0.f, ry = 0.f;
+  if (status[i] == KVFE_KP_VALID) {
+    const int xx = clampi((int)roundf(x[i]), 0, dc.W - 1), yy = clampi((int)roundf(y[i]), 0, dc.H - 1);
+    rect_map_at(cams[cam], xx, yy, &rx, &ry);
+  }
+  ox[i] = rx; oy[i] = ry;
+}
+int launch_check_rect_raw(const DevCfg& dc, const CamModel* d_cam, int cam, const float* dx, const float* dy, const float* ux,
+                          const float* uy, int n, float tol, int* status, float* ox, float* oy, cudaStream_t s) {
+  check_rect_raw_kernel<<<(n + 127) / 128, 128, 0, s>>>(dc, d_cam, cam, dx, dy, ux, uy, n, tol, status, ox, oy);
+  return 1;
+}
+int launch_distort_unrectify_raw(const DevCfg& dc, const CamModel* d_cam, int cam, const int* status, const float* x,
+                                 const float* y, int n, float* ox, float* oy, cudaStream_t s) {
+  distort_unrectify_raw_kernel<<<(n + 127) / 128, 128, 0, s>>>(dc, d_cam, cam, status, x, y, n, ox, oy);
+  return 1;
+}
+// the three kernels of launch_sparse_stereo one at a time (which: 0 left_rect, 1 match, 2 depth), stage state in stream 0
+int launch_sparse_stereo_part(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, int mode_mask, int which, cudaStream_t s) {
+  if (which == 0) { left_rect_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); return 1; }
+  if (which == 2) { depth_kernel<<<dim3((dc.cap + 127) / 128, dc.B), 128, 0, s>>>(dc, db, d_cam, mode_mask); return 1; }
+  size_t sm = match_geom(dc.templ_cols, dc.templ_rows, dc.stripe_cols, dc.stripe_rows).bytes;
+  if (sm < (size_t)SUBPIX_PATCH * 4) sm = (size_t)SUBPIX_PATCH * 4;
+  if (sm > 48 * 1024) cudaFuncSetAttribute(match_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm);
+  match_kernel<<<dim3((dc.cap + MATCH_KP_PER_CTA - 1) / MATCH_KP_PER_CTA, dc.B), MATCH_THREADS, sm, s>>>(dc, db, mode_mask, 0);
+  return 1;
+}

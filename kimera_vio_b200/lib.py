@@ -59,6 +59,8 @@ class Config(C.Structure):
         ("use_stereo_tracking", C.c_int32), ("use_ransac", C.c_int32),
         ("max_disparity_since_lkf", C.c_double),
         ("mesh_2d", C.c_int32), ("subdiv_bounding_factor", C.c_float),
+        ("optimize_2d2d_pose_from_inliers", C.c_int32), ("optimize_3d3d_pose_from_inliers", C.c_int32),
+        ("equalize_image", C.c_int32),
     ]
 
 
@@ -173,6 +175,9 @@ def make_config(p: FrontendParams, width: int, height: int, batch: int = 1, max_
     c.use_stereo_tracking, c.use_ransac = int(p.use_stereo_tracking), int(p.use_ransac)
     c.max_disparity_since_lkf = p.max_disparity_since_lkf
     c.mesh_2d = int(mesh_2d)
+    c.optimize_2d2d_pose_from_inliers = int(getattr(p, "optimize_2d2d_pose_from_inliers", 0))
+    c.optimize_3d3d_pose_from_inliers = int(getattr(p, "optimize_3d3d_pose_from_inliers", 0))
+    c.equalize_image = int(p.equalize_image)
     return c
 
 
@@ -329,6 +334,77 @@ class Context:
                                               _p(vs), n, C.byref(so), _p(rl), _p(rr), C.c_size_t(rl.strides[0])))
         res["left_rect"], res["right_rect"] = rl, rr
         return res
+
+    # ---- boundary completion (include/kvfe.h) ----
+    def check_rectified_keypoints(self, cam: int, distorted_xy, rectified_xy, tol: float = 2.0):
+        d, u = np.ascontiguousarray(distorted_xy, np.float32).reshape(-1, 2), np.ascontiguousarray(rectified_xy, np.float32).reshape(-1, 2)
+        n = len(d)
+        st, ox, oy = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        dx, dy, ux, uy = (np.ascontiguousarray(a) for a in (d[:, 0], d[:, 1], u[:, 0], u[:, 1]))
+        self._chk(self.lib.kvfe_check_rectified_keypoints(self.h, cam, _p(dx), _p(dy), _p(ux), _p(uy), n, C.c_float(tol), _p(st), _p(ox), _p(oy)))
+        return st, np.stack([ox, oy], 1)
+
+    def distort_unrectify_keypoints(self, cam: int, status, xy):
+        st = np.ascontiguousarray(status, np.int32)
+        a = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        n = len(st)
+        x, y = np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
+        ox, oy = np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._chk(self.lib.kvfe_distort_unrectify_keypoints(self.h, cam, _p(st), _p(x), _p(y), n, _p(ox), _p(oy)))
+        return np.stack([ox, oy], 1)
+
+    def undistort_rectify_left_keypoints(self, xy):
+        a = np.ascontiguousarray(xy, np.float32).reshape(-1, 2)
+        n = len(a)
+        x, y = np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
+        st, ox, oy = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._chk(self.lib.kvfe_undistort_rectify_left_keypoints(self.h, _p(x), _p(y), n, _p(st), _p(ox), _p(oy)))
+        return st, np.stack([ox, oy], 1)
+
+    def right_keypoints_rectified(self, left_rect: np.ndarray, right_rect: np.ndarray, left_status, left_xy):
+        L, R = np.ascontiguousarray(left_rect, np.uint8), np.ascontiguousarray(right_rect, np.uint8)
+        ls = np.ascontiguousarray(left_status, np.int32)
+        a = np.ascontiguousarray(left_xy, np.float32).reshape(-1, 2)
+        n = len(ls)
+        x, y = np.ascontiguousarray(a[:, 0]), np.ascontiguousarray(a[:, 1])
+        rs, rx, ry = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._chk(self.lib.kvfe_right_keypoints_rectified(self.h, _p(L), _p(R), C.c_size_t(L.shape[1]), _p(ls), _p(x), _p(y), n,
+                                                          _p(rs), _p(rx), _p(ry)))
+        return rs, np.stack([rx, ry], 1)
+
+    def depth_from_rectified_matches(self, left_status, left_x, right_status, right_x):
+        ls, rs = np.ascontiguousarray(left_status, np.int32), np.array(right_status, np.int32)
+        lx, rx = np.ascontiguousarray(left_x, np.float32), np.ascontiguousarray(right_x, np.float32)
+        n = len(ls)
+        depth = np.zeros(n, np.float64)
+        self._chk(self.lib.kvfe_depth_from_rectified_matches(self.h, _p(ls), _p(lx), _p(rs), _p(rx), n, _p(depth)))
+        return rs, depth
+
+    def compute_median_disparity(self, ref_xy, cur_xy, matches):
+        r, c = np.ascontiguousarray(ref_xy, np.float32).reshape(-1, 2), np.ascontiguousarray(cur_xy, np.float32).reshape(-1, 2)
+        m = np.ascontiguousarray(matches, np.int32).reshape(-1, 2)
+        mr, mc = np.ascontiguousarray(m[:, 0]), np.ascontiguousarray(m[:, 1])
+        rx, ry, cx, cy = (np.ascontiguousarray(a) for a in (r[:, 0], r[:, 1], c[:, 0], c[:, 1]))
+        med, ok = C.c_double(), C.c_int()
+        self._chk(self.lib.kvfe_compute_median_disparity(self.h, _p(rx), _p(ry), len(r), _p(cx), _p(cy), len(c), _p(mr), _p(mc), len(m),
+                                                         C.byref(med), C.byref(ok)))
+        return bool(ok.value), med.value
+
+    def point3_and_covariance(self, left_xy, right_xy, points_3d, R=None):
+        l, r = np.ascontiguousarray(left_xy, np.float32).reshape(-1, 2), np.ascontiguousarray(right_xy, np.float32).reshape(-1, 2)
+        p = np.ascontiguousarray(points_3d, np.float64).reshape(-1, 3)
+        n = len(p)
+        lx, rx, ly = np.ascontiguousarray(l[:, 0]), np.ascontiguousarray(r[:, 0]), np.ascontiguousarray(l[:, 1])
+        Rm = None if R is None else np.ascontiguousarray(R, np.float64).reshape(9)
+        op, oc = np.zeros((n, 3)), np.zeros((n, 3, 3))
+        self._chk(self.lib.kvfe_point3_and_covariance(self.h, _p(lx), _p(rx), _p(ly), _p(p), n, _p(Rm), _p(op), _p(oc)))
+        return op, oc
+
+    def equalize_hist(self, img: np.ndarray) -> np.ndarray:
+        a = np.ascontiguousarray(img, np.uint8)
+        out = np.empty_like(a)
+        self._chk(self.lib.kvfe_equalize_hist(self.h, _p(a), C.c_size_t(a.shape[1]), _p(out), C.c_size_t(a.shape[1])))
+        return out
 
     def mesh_2d(self, kps_xy):
         xy = np.asarray(kps_xy, np.float32).reshape(-1, 2)

@@ -89,6 +89,8 @@ class FrontendParams:
     bidirectional_matching: bool = False
     subpixel_refinement_stereo: bool = False
     equalize_image: bool = False
+    optimize_2d2d_pose_from_inliers: bool = False     # VisionImuTrackerParams.cpp:119-122 (rejected by kvfe_create when set)
+    optimize_3d3d_pose_from_inliers: bool = False
     # --- front-end FSM (VisionImuFrontendParams.h)
     min_intra_keyframe_time_ns: int = int(0.2 * 10e6)   # sic: the reference's units slip (SURVEY B-11)
     max_intra_keyframe_time_ns: int = int(10.0 * 10e6)
@@ -166,6 +168,8 @@ class FrontendParams:
         get("bidirectionalMatching", "bidirectional_matching", b)
         get("subpixelRefinementStereo", "subpixel_refinement_stereo", b)
         get("equalizeImage", "equalize_image", b)
+        get("optimize_2d2d_pose_from_inliers", "optimize_2d2d_pose_from_inliers", b)
+        get("optimize_3d3d_pose_from_inliers", "optimize_3d3d_pose_from_inliers", b)
         if "min_intra_keyframe_time" in y:
             p.min_intra_keyframe_time_ns = int(float(y["min_intra_keyframe_time"]) * 1e9)
         if "max_intra_keyframe_time" in y:

@@ -148,3 +148,48 @@ def test_delaunay_restatement_matches_subdiv2d():
         ref = create_mesh_2d_impl((w, h), [tuple(p) for p in pts])
         assert tri[:m].shape == ref.shape and np.array_equal(tri[:m], ref), (trial, kind, n)
         assert nq.value <= 3 * n + 16
+
+
+def test_find_and_remove_outliers_host_logic():
+    """kvfe_find_outliers / kvfe_remove_outliers_{mono,stereo} (Tracker.cpp:836-917): pure host bookkeeping, no GPU."""
+    import ctypes as C
+    from kimera_vio_b200 import build as kb
+    from oracle import ransac as ors
+    lib = C.CDLL(kb.build())
+    rng = np.random.default_rng(2)
+    for n_matches, n_inl in ((40, 25), (7, 0), (5, 5), (0, 0)):
+        inl = rng.permutation(n_matches)[:n_inl].astype(np.int32)          # unsorted on purpose
+        out = np.zeros(max(n_matches, 1), np.int32)
+        no = C.c_int()
+        assert lib.kvfe_find_outliers(n_matches, inl.ctypes.data_as(C.c_void_p), n_inl, out.ctypes.data_as(C.c_void_p), C.byref(no)) == 0
+        assert list(out[:no.value]) == ors.find_outliers(n_matches, sorted(int(v) for v in inl))
+        # mono
+        n_ref, n_cur = n_matches + 5, n_matches + 3
+        mr = rng.permutation(n_ref)[:n_matches].astype(np.int32)
+        mc = rng.permutation(n_cur)[:n_matches].astype(np.int32)
+        lr = np.arange(100, 100 + n_ref, dtype=np.int64)
+        lc = np.arange(500, 500 + n_cur, dtype=np.int64)
+        elr, elc = lr.copy(), lc.copy()
+        for o in ors.find_outliers(n_matches, sorted(int(v) for v in inl)):
+            elr[mr[o]] = -1
+            elc[mc[o]] = -1
+        emr, emc = mr[inl].copy(), mc[inl].copy()
+        mr2, mc2 = mr.copy(), mc.copy()
+        nm = C.c_int(n_matches)
+        vp = lambda a: a.ctypes.data_as(C.c_void_p)
+        assert lib.kvfe_remove_outliers_mono(vp(inl), n_inl, vp(lr), n_ref, vp(lc), n_cur, vp(mr2), vp(mc2), C.byref(nm)) == 0
+        assert nm.value == n_inl and np.array_equal(lr, elr) and np.array_equal(lc, elc)
+        assert np.array_equal(mr2[:n_inl], emr) and np.array_equal(mc2[:n_inl], emc)
+        # stereo
+        rs, cs = np.zeros(n_ref, np.int32), np.zeros(n_cur, np.int32)
+        rd, cd = np.ones(n_ref), np.ones(n_cur)
+        rp, cp = np.ones((n_ref, 3)), np.ones((n_cur, 3))
+        mr3, mc3 = mr.copy(), mc.copy()
+        nm = C.c_int(n_matches)
+        assert lib.kvfe_remove_outliers_stereo(vp(inl), n_inl, vp(rs), vp(rd), vp(rp), n_ref, vp(cs), vp(cd), vp(cp), n_cur,
+                                               vp(mr3), vp(mc3), C.byref(nm)) == 0
+        outl = ors.find_outliers(n_matches, sorted(int(v) for v in inl))
+        assert sorted(np.nonzero(rs == 4)[0]) == sorted(int(mr[o]) for o in outl)
+        assert sorted(np.nonzero(cd == 0)[0]) == sorted(int(mc[o]) for o in outl)
+        assert all((rp[mr[o]] == 0).all() and (cp[mc[o]] == 0).all() for o in outl)
+        assert nm.value == n_inl and np.array_equal(mr3[:n_inl], emr)
