@@ -169,6 +169,11 @@ int kvfe_min_eigen_response(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, flo
 int kvfe_detect(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* existing_x,
                 const float* existing_y, const int64_t* existing_lmk, int n_existing, int need,
                 float* out_x, float* out_y, int* n_out);
+/* Same with a caller-supplied Frame::detection_mask_ (FeatureDetector.cpp:186-189; the RGB-D front-end fills it):
+ * 255 = consider, 0 = do not; the circles around the tracked keypoints are drawn into it like the reference does. */
+int kvfe_detect_masked(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const uint8_t* detection_mask, size_t mask_pitch,
+                       const float* existing_x, const float* existing_y, const int64_t* existing_lmk, int n_existing,
+                       int need, float* out_x, float* out_y, int* n_out);
 /* Same, but stops after cv::GFTTDetector::detect (FeatureDetector::rawFeatureDetection,
  * FeatureDetector.cpp:165-172): corners in descending-response order. */
 int kvfe_detect_raw(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* existing_x,
@@ -313,6 +318,9 @@ size_t kvfe_packet_bytes(const kvfe_ctx* ctx);
 int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries);
 
 int kvfe_frontend_reset(kvfe_ctx* ctx);
+/* Frame::isKeyframe_ (include/kimera-vio/frontend/Frame.h:172): flags[b] != 0 makes the NEXT step's frame of stream b a
+ * keyframe whatever the other criteria say (VisionImuFrontend::shouldBeKeyframe, VisionImuFrontend.cpp:207-209). */
+int kvfe_frontend_force_keyframe(kvfe_ctx* ctx, const int32_t* flags /* batch */);
 
 /* Host-buffer step: copies the batch's images H2D, runs the step, copies the packets (and, when
  * rect_left/right are non-NULL, the rectified images of keyframes) D2H.  left/right: `batch`
@@ -468,6 +476,8 @@ int kvfe_pipeline_push(kvfe_pipeline* p, int stream, const uint8_t* left, const 
 int kvfe_pipeline_push_many(kvfe_pipeline* p, int n, const int32_t* streams, const uint8_t* const* left,
                             const uint8_t* const* right, size_t pitch, const int64_t* timestamps,
                             const double* R, const uint64_t* tags);
+/* Frame::isKeyframe_ = true (user-enforced keyframe, VisionImuFrontend.cpp:207-209) for the next frame pushed on `stream`. */
+int kvfe_pipeline_force_keyframe(kvfe_pipeline* p, int stream);
 /* Up to max_n finished frames; blocks up to timeout_ms (0: poll) while none is ready.  Returns the count. */
 int kvfe_pipeline_pop(kvfe_pipeline* p, kvfe_pipeline_output* outs, int max_n, int timeout_ms);
 int kvfe_pipeline_release(kvfe_pipeline* p, const kvfe_pipeline_output* outs, int n);

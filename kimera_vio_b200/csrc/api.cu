@@ -318,6 +318,7 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CUC(dmalloc(&db.cand_sel, B * 16384));
   CUC(dmalloc(&db.cand_sel_n, B));
   CUC(dmalloc(&db.greedy_redo, B));
+  CUC(dmalloc(&db.force_kf, B));
   CUC(dmalloc(&db.corner_idx, B * (size_t)dc.max_before_anms));
   CUC(dmalloc(&db.corner_n, B));
   CUC(dmalloc(&db.new_x, B * cap)); CUC(dmalloc(&db.new_y, B * cap)); CUC(dmalloc(&db.new_n, B));
@@ -448,7 +449,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   if (ctx->side) cudaStreamDestroy(ctx->side);
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   if (ctx->ev_join) cudaEventDestroy(ctx->ev_join);
-  void* ptrs[] = {db.cand_hist, db.cand_sel, db.cand_sel_n, db.greedy_redo, db.stage_img[0], db.stage_img[1], db.stage_seq, db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
+  void* ptrs[] = {db.force_kf, db.cand_hist, db.cand_sel, db.cand_sel_n, db.greedy_redo, db.stage_img[0], db.stage_img[1], db.stage_seq, db.mesh_ws, ctx->d_pub_count, ctx->d_kf_steps, ctx->d_cam, db.pyr[0], db.pyr[1], db.right_raw, db.rmap[0], db.rmap[1], db.rectL, db.rectR, db.mask, db.eig, db.eig_max,
                   db.cand, db.cand_n, db.corner_idx, db.corner_n, db.new_x, db.new_y, db.new_n, db.scratch_i,
                   db.sort_perm, db.rnd_table, db.subpix_mask, db.subpix_mask_stereo, ctx->circle_hw, db.lk_px,
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
@@ -617,14 +618,15 @@ static int load_existing(kvfe_ctx* ctx, const float* x, const float* y, const in
 }
 
 static int detect_common(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const float* ex, const float* ey,
-                         const int64_t* el, int n_existing, int need, bool raw) {
+                         const int64_t* el, int n_existing, int need, bool raw, const uint8_t* mask = nullptr, size_t mask_pitch = 0) {
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db;
   RET(park_other_streams(ctx));
   RET(set_stage_state(ctx, 2, need, n_existing));
   RET(load_existing(ctx, ex, ey, el, n_existing));
   unsigned char* I = db.pyr[0] + dc.lvl_off[0];
   RET(upload_image(ctx, I, dc.pitch, img, pitch));
-  ctx->launches += launch_gftt(dc, db, I, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, 1 << 2, ctx->stream);
+  if (mask) RET(upload_image(ctx, db.mask, dc.pitch, mask, mask_pitch));      // Frame::detection_mask_
+  ctx->launches += launch_gftt(dc, db, I, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, 1 << 2, ctx->stream, mask ? 1 : 0);
   if (!raw) ctx->launches += launch_select(dc, db, I, dc.pyr_stride, ctx->d_cam, 1 << 2, 0, ctx->stream);
   CHECK_LAUNCH();
   return KVFE_OK;
@@ -635,6 +637,22 @@ extern "C" int kvfe_detect(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, cons
                            float* out_x, float* out_y, int* n_out) {
   if (!ctx || !img || !out_x || !out_y || !n_out) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
   RET(detect_common(ctx, img, pitch, existing_x, existing_y, existing_lmk, n_existing, need, false));
+  int n = 0;
+  CU(cudaMemcpyAsync(&n, ctx->db.new_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (n > 0) {
+    CU(cudaMemcpy(out_x, ctx->db.new_x, n * sizeof(float), cudaMemcpyDeviceToHost));
+    CU(cudaMemcpy(out_y, ctx->db.new_y, n * sizeof(float), cudaMemcpyDeviceToHost));
+  }
+  *n_out = n;
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_detect_masked(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, const uint8_t* detection_mask, size_t mask_pitch,
+                                  const float* existing_x, const float* existing_y, const int64_t* existing_lmk, int n_existing,
+                                  int need, float* out_x, float* out_y, int* n_out) {
+  if (!ctx || !img || !detection_mask || !out_x || !out_y || !n_out) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  RET(detect_common(ctx, img, pitch, existing_x, existing_y, existing_lmk, n_existing, need, false, detection_mask, mask_pitch));
   int n = 0;
   CU(cudaMemcpyAsync(&n, ctx->db.new_n, sizeof(int), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
@@ -1161,6 +1179,15 @@ extern "C" int kvfe_ransac_stereo_1pt(kvfe_ctx* ctx, const float* ref_left_xy, c
 }
 
 // ---- frame-level step ---------------------------------------------------------------------------
+extern "C" int kvfe_frontend_force_keyframe(kvfe_ctx* ctx, const int32_t* flags) {
+  if (!ctx || !flags) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  // consumed (and cleared) by the next step's keyframe decision; enqueued on the context's stream like the step itself
+  std::vector<int> h(flags, flags + ctx->dc.B);
+  for (int& v : h) v = v ? 1 : 0;
+  CU(cudaMemcpy(ctx->db.force_kf, h.data(), h.size() * sizeof(int), cudaMemcpyHostToDevice));
+  return KVFE_OK;
+}
+
 extern "C" int kvfe_frontend_reset(kvfe_ctx* ctx) {
   if (!ctx) return KVFE_ERR_INVALID_ARG;
   ctx->launches += launch_reset(ctx->dc, ctx->db, ctx->stream);

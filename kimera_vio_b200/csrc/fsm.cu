@@ -47,6 +47,7 @@ __global__ void prep_kernel(DevCfg dc, DevBuf db, const CamModel* __restrict__ c
     ts = reinterpret_cast<const long long*>(arr);
     Rin = reinterpret_cast<const double*>(arr + (size_t)dc.B * sizeof(long long));
     rot_mode = io->rot_mode;
+    if (io->force_kf) db.force_kf[b] = 1;
   }
   s.timestamp = ts[b];
   if (rot_mode == 1) {
@@ -231,13 +232,13 @@ __global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db, cudaG
   const int b = blockIdx.x;
   StreamState& s = db.st[b];
   if (s.mode == 0) {
-    if (threadIdx.x == 0 && cond) cudaGraphSetConditional(cond, 1);
+    if (threadIdx.x == 0) { db.force_kf[b] = 0; if (cond) cudaGraphSetConditional(cond, 1); }
     return;
   }
   const int fk = b * 3 + s.slot_k, fl = b * 3 + s.slot_lkf;
   const int nk = db.fr.n[fk];
   if (nk == 0) {                       // StereoVisionImuFrontend.cpp:312-323
-    if (threadIdx.x == 0) { s.mode = 3; if (cond) cudaGraphSetConditional(cond, 1); }
+    if (threadIdx.x == 0) { s.mode = 3; db.force_kf[b] = 0; if (cond) cudaGraphSetConditional(cond, 1); }
     return;
   }
   int* m_ref = db.m_ref + (size_t)b * dc.cap;
@@ -264,7 +265,9 @@ __global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db, cudaG
     bool enough = !is_low;
     bool max_disp = disparity > dc.max_disparity;
     bool flipped = (enough || low_first) && min_time;
-    bool kf = max_time || max_disp || flipped || nr_low;
+    const bool forced = db.force_kf[b] != 0;          // frame.isKeyframe_ (VisionImuFrontend.cpp:207-209), one shot
+    db.force_kf[b] = 0;
+    bool kf = max_time || max_disp || flipped || nr_low || forced;
     s.mode = kf ? 2 : 1;
     if (kf) {
       // StereoVisionImuFrontend.cpp:345-346, :402-404

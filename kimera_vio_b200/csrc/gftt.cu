@@ -773,10 +773,11 @@ int launch_min_eig(const DevCfg& dc, const DevBuf& db, const unsigned char* img,
 }
 
 int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
-                const int* circle_hw, int circle_r, int mode_mask, cudaStream_t s) {
+                const int* circle_hw, int circle_r, int mode_mask, cudaStream_t s, int keep_mask) {
   int n = 0;
   gftt_init_kernel<<<dc.B, 256, 0, s>>>(dc, db, mode_mask); ++n;
-  mask_fill_kernel<<<dim3(64, dc.B), 256, 0, s>>>(dc, db.mask, db.st, mode_mask); ++n;
+  // keep_mask: db.mask already holds the caller's Frame::detection_mask_ (FeatureDetector.cpp:186-189)
+  if (!keep_mask) { mask_fill_kernel<<<dim3(64, dc.B), 256, 0, s>>>(dc, db.mask, db.st, mode_mask); ++n; }
   mask_circles_kernel<<<dim3((dc.cap + 7) / 8, dc.B), 256, 0, s>>>(dc, db, circle_hw, circle_r, mode_mask); ++n;
   n += launch_mineig_any(dc, db, img, img_stride, mode_mask, 1, s);
   cand_kernel<<<dim3((dc.W + 31) / 32, (dc.H + 63) / 64, dc.B), 256, 0, s>>>(dc, db, mode_mask); ++n;

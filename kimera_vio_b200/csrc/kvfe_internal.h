@@ -82,7 +82,7 @@ struct StepIO {
   unsigned char* dst_rectR;
   unsigned long long seq;        // echoed into done_seq by the last kernel of the step
   int rot_mode;                  // 0: R = lkf_R_cur (StereoVisionImuFrontend.cpp:149-150); 1: R = km1_R_cur
-  int pad0;
+  int force_kf;                  // Frame::isKeyframe_ of this frame (user-enforced keyframe, VisionImuFrontend.cpp:209)
   const unsigned char* next_srcL;   // images of the stream's NEXT frame when it is already queued (dense rows, 16-byte
   const unsigned char* next_srcR;   // aligned), else null: pulled into the staging slot while this step computes
   unsigned long long pad1[6];
@@ -170,6 +170,7 @@ struct DevBuf {
   unsigned char* packets;      // B * packet_bytes
   size_t packet_bytes;
   size_t pk_off[32];
+  int* force_kf;               // B: user-enforced keyframe (Frame::isKeyframe_) for the next step, cleared by decide_kernel
   int* mesh_ws;                // quad-edge workspace of the mesh kernel when it does not fit shared memory
   unsigned char* stage_img[2]; // pipeline prefetch staging, per pyramid slot: [cam][B] dense images, img_stride apart (or null)
   unsigned long long* stage_seq; // [2]: sequence number of the frame held by stage_img[slot] (0: none)
@@ -233,7 +234,7 @@ int launch_pyramid(const DevCfg& dc, unsigned char* pyr, int nimg, cudaStream_t 
 int launch_lk(const DevCfg& dc, const DevBuf& db, int prev_slot, int cur_slot, cudaStream_t s);
 // gftt.cu
 int launch_gftt(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
-                const int* circle_hw, int circle_r, int mode_mask, cudaStream_t s);
+                const int* circle_hw, int circle_r, int mode_mask, cudaStream_t s, int keep_mask = 0);
 int launch_min_eig(const DevCfg& dc, const DevBuf& db, const unsigned char* img, size_t img_stride,
                    int mode_mask, cudaStream_t s);
 // select.cu (ANMS + subpix + append)

@@ -27,6 +27,7 @@ namespace {
 struct PipeIn {
   const unsigned char* L; const unsigned char* R; size_t pitch;
   long long ts; double Rm[9]; unsigned long long tag;
+  int force_kf;
 };
 struct PipeOutSlot { unsigned char* packet; unsigned char* rectL; unsigned char* rectR; };
 struct PipeFlight { int out_slot, io_slot; unsigned long long seq, tag; };
@@ -39,6 +40,7 @@ struct PipeStream {
   std::vector<PipeOutSlot> out;
   unsigned char* out_block = nullptr; // one pinned allocation behind `out`
   unsigned char* stage[2] = {nullptr, nullptr};   // pinned staging of pageable inputs, per I/O slot (lazy)
+  bool force_next = false;            // kvfe_pipeline_force_keyframe: Frame::isKeyframe_ of the next pushed frame (under mu)
   // dispatcher-private
   std::deque<PipeFlight> fl;
   unsigned long long seq = 0;
@@ -247,6 +249,7 @@ static void worker_main(kvfe_pipeline* p, int widx) {
         io->dst_rectR = p->pc.want_rectified ? s->out[oslot].rectR : nullptr;
         io->seq = ++s->seq;
         io->rot_mode = p->pc.rotation_mode;
+        io->force_kf = in.force_kf;
         unsigned char* arr = ctx->pio[io_slot] + KVFE_STEPIO_ARRAYS;
         memcpy(arr, &in.ts, sizeof(long long));
         memcpy(arr + sizeof(long long), in.Rm, 9 * sizeof(double));
@@ -388,11 +391,13 @@ static int push_one(kvfe_pipeline* p, int stream, const uint8_t* left, const uin
   if (int f = p->failed.load()) return f;
   PipeStream* s = p->streams[stream];
   PipeIn in;
-  in.L = left; in.R = right; in.pitch = pitch; in.ts = timestamp; in.tag = tag;
+  in.L = left; in.R = right; in.pitch = pitch; in.ts = timestamp; in.tag = tag; in.force_kf = 0;
   memcpy(in.Rm, R, sizeof(in.Rm));
   {
     std::lock_guard<std::mutex> g(s->mu);
     if ((int)s->in.size() >= p->pc.queue_depth) return KVFE_ERR_CAPACITY;
+    in.force_kf = s->force_next ? 1 : 0;
+    s->force_next = false;
     s->in.push_back(in);
   }
   p->n_pushed.fetch_add(1, std::memory_order_relaxed);
@@ -417,6 +422,14 @@ extern "C" int kvfe_pipeline_push_many(kvfe_pipeline* p, int n, const int32_t* s
   }
   p->wk_cv.notify_all();
   return i;
+}
+
+// Frame::isKeyframe_ (user-enforced keyframe, VisionImuFrontend.cpp:207-209) for the NEXT frame pushed on `stream`
+extern "C" int kvfe_pipeline_force_keyframe(kvfe_pipeline* p, int stream) {
+  if (!p || stream < 0 || stream >= (int)p->streams.size()) return KVFE_ERR_INVALID_ARG;
+  std::lock_guard<std::mutex> g(p->streams[stream]->mu);
+  p->streams[stream]->force_next = true;
+  return KVFE_OK;
 }
 
 extern "C" int kvfe_pipeline_pop(kvfe_pipeline* p, kvfe_pipeline_output* outs, int max_n, int timeout_ms) {

@@ -453,6 +453,20 @@ class Context:
     def reset(self):
         self._chk(self.lib.kvfe_frontend_reset(self.h))
 
+    def force_keyframe(self, flags):
+        f = np.ascontiguousarray(flags, np.int32)
+        assert f.size == self.B
+        self._chk(self.lib.kvfe_frontend_force_keyframe(self.h, _p(f)))
+
+    def detect_masked(self, img: np.ndarray, mask: np.ndarray, kps=(), lmks=(), need: int = 0):
+        a, m = np.ascontiguousarray(img, np.uint8), np.ascontiguousarray(mask, np.uint8)
+        ex, ey, el, ne = self._existing(kps, lmks)
+        ox, oy = np.zeros(self.cap, np.float32), np.zeros(self.cap, np.float32)
+        n = C.c_int()
+        self._chk(self.lib.kvfe_detect_masked(self.h, _p(a), C.c_size_t(a.shape[1]), _p(m), C.c_size_t(m.shape[1]), _p(ex), _p(ey), _p(el),
+                                              ne, need, _p(ox), _p(oy), C.byref(n)))
+        return np.stack([ox[:n.value], oy[:n.value]], 1)
+
     def step(self, lefts: Sequence[np.ndarray], rights: Sequence[np.ndarray], timestamps, kf_R_cur,
              want_rectified: bool = False):
         """Host-buffer step (kvfe_frontend_step).  Returns the parsed packets (list of dicts)."""
@@ -575,6 +589,7 @@ def _pipeline_protos(lib):
     lib.kvfe_pipeline_pop.argtypes = [C.c_void_p, C.POINTER(PipelineOutput), C.c_int, C.c_int]
     lib.kvfe_pipeline_release.argtypes = [C.c_void_p, C.POINTER(PipelineOutput), C.c_int]
     lib.kvfe_pipeline_reset.argtypes = [C.c_void_p]
+    lib.kvfe_pipeline_force_keyframe.argtypes = [C.c_void_p, C.c_int]
     lib.kvfe_pipeline_get_stats.argtypes = [C.c_void_p, C.POINTER(PipelineStats)]
     lib._kvfe_pipe_protos = True
 
@@ -652,6 +667,9 @@ class Pipeline:
 
     def reset(self):
         self._chk(self.lib.kvfe_pipeline_reset(self.h))
+
+    def force_keyframe(self, stream: int):
+        self._chk(self.lib.kvfe_pipeline_force_keyframe(self.h, stream))
 
     def stats(self) -> dict:
         st = PipelineStats()

@@ -86,8 +86,8 @@ def test_right_keypoints_and_depth(env):
     assert np.array_equal(d, np.array(depths))
 
 
-def test_median_disparity(env):
-    ctx = env["ctx"]
+def test_median_disparity():
+    p, rig, ctx = H.euroc_setup(batch=1, max_keypoints=2048)       # room for the > 1024-match (radix-select) path
     rng = np.random.default_rng(21)
     for n, m in ((50, 31), (400, 400), (1300, 1250), (10, 1)):       # > 1024 matches: the radix-select path
         ref = rng.uniform(0, 750, (n, 2)).astype(np.float32)
@@ -98,6 +98,7 @@ def test_median_disparity(env):
         gok, gmed = ctx.compute_median_disparity(ref, cur, matches)
         assert gok == ok and gmed == med, (n, m, gmed, med)
     assert ctx.compute_median_disparity(ref, cur, np.zeros((0, 2), np.int32)) == (False, 0.0)
+    ctx.close()
 
 
 def test_point3_and_covariance(env):
@@ -117,3 +118,65 @@ def test_point3_and_covariance(env):
             ep, ec = ors.get_point3_and_covariance(left[i], right[i], p3[i], calib, R)
             assert np.array_equal(gp[i], ep)
             assert np.abs(gc[i] - ec).max() <= 1e-12 * max(1.0, np.abs(ec).max())
+
+
+def test_detect_with_detection_mask(env):
+    """Frame::detection_mask_ (FeatureDetector.cpp:186-189): a caller-supplied mask replaces the all-255 one; the
+    circles around tracked keypoints are still drawn into it."""
+    p, o, ctx = env["p"], env["orig"], env["ctx"]
+    g, lefts, rights = H.golden()
+    L = lefts[0]
+    det = ofe.FeatureDetector(p)
+    mask = np.full(L.shape, 255, np.uint8)
+    mask[:, 300:520] = 0                   # a vertical band without detections
+    mask[100:180, :] = 0
+    fr = ofe.Frame(0, 0, L, o.left)
+    fr.keypoints = [(np.float32(100.0), np.float32(200.0)), (np.float32(600.5), np.float32(400.25))]
+    fr.landmarks = [5, -1]
+    fr.landmarks_age, fr.scores = [1, 1], [0.0, 0.0]
+
+    class MaskedDetector(ofe.FeatureDetector):
+        def build_mask(self, frame):
+            m = mask.copy()
+            for kp, lmk in zip(frame.keypoints, frame.landmarks):
+                if lmk != -1:
+                    c = (int(np.rint(np.float32(kp[0]))), int(np.rint(np.float32(kp[1]))))
+                    cv2.circle(m, c, self.p.min_distance, 0, cv2.FILLED)
+            return m
+    want = np.array(MaskedDetector(p).detect_corners(fr, 120), np.float32).reshape(-1, 2)
+    got = ctx.detect_masked(L, mask, fr.keypoints, fr.landmarks, need=120)
+    assert len(got) == len(want) and len(want) > 50
+    assert np.abs(got - want).max() <= 1e-3
+    assert not ((got[:, 0] > 300.5) & (got[:, 0] < 518.5)).any()
+
+
+def test_forced_keyframe_sequence():
+    """Frame::isKeyframe_ set by the caller (VisionImuFrontend.cpp:207-209): the forced frame becomes a keyframe in the
+    stream that asked for it and only there."""
+    from test_gpu_sequence import compare_packet, packet_ok
+    N, B = 8, 2
+    p, rig, ctx = H.euroc_setup(batch=B)
+    orig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    s, fr = H.synth_frames(N, seed=20240)
+    fes = [ofe.StereoFrontend(p, orig) for _ in range(B)]
+    lkf, ok, kf_flags = [0] * B, True, [[], []]
+    for k, f in enumerate(fr):
+        force = [1 if (b == 0 and k in (2, 3)) else 0 for b in range(B)]
+        if any(force):
+            ctx.force_keyframe(force)
+        Rs = [s.kf_rotation(lkf[b], k) for b in range(B)]
+        pks = ctx.step([f.left] * B, [f.right] * B, [f.timestamp] * B, np.array(Rs))
+        for b in range(B):
+            sf = ofe.StereoFrame.make(k, f.timestamp, f.left, f.right, orig)
+            sf.left_frame.is_keyframe = bool(force[b])
+            o = fes[b].spin(sf, Rs[b])
+            rec = compare_packet("forced/s%d/f%d" % (b, k), pks[b], o)
+            rec["ok"] = packet_ok(rec)
+            H.diag("sequence", **rec)
+            ok &= rec["ok"]
+            kf_flags[b].append(bool(pks[b]["is_keyframe"]))
+            if o.is_keyframe:
+                lkf[b] = k
+    ctx.close()
+    assert ok
+    assert kf_flags[0][2] and kf_flags[0][3] and not (kf_flags[1][2] and kf_flags[1][3])
