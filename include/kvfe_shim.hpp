@@ -66,6 +66,31 @@ class UndistorterRectifier {
                                       out.x.data(), out.y.data()), "UndistortRectifyKeypoints");
     return out;
   }
+  // StereoCamera::undistortRectifyLeftKeypoints (StereoCamera.cpp:236-260): statuses + rectified keypoints
+  std::vector<int32_t> undistortRectifyLeftKeypoints(const Keypoints& kps, Keypoints* rectified) const {
+    std::vector<int32_t> st(kps.size());
+    rectified->x.resize(kps.size()); rectified->y.resize(kps.size());
+    c_.check(kvfe_undistort_rectify_left_keypoints(c_.get(), kps.x.data(), kps.y.data(), (int)kps.size(), st.data(),
+                                                   rectified->x.data(), rectified->y.data()), "undistortRectifyLeftKeypoints");
+    return st;
+  }
+  // UndistorterRectifier.cpp:138-211
+  std::vector<int32_t> checkUndistortedRectifiedLeftKeypoints(const Keypoints& distorted, const Keypoints& undistorted,
+                                                              Keypoints* status_kps, float pixel_tol = 2.0f, int cam = 0) const {
+    std::vector<int32_t> st(distorted.size());
+    status_kps->x.resize(distorted.size()); status_kps->y.resize(distorted.size());
+    c_.check(kvfe_check_rectified_keypoints(c_.get(), cam, distorted.x.data(), distorted.y.data(), undistorted.x.data(),
+                                            undistorted.y.data(), (int)distorted.size(), pixel_tol, st.data(), status_kps->x.data(),
+                                            status_kps->y.data()), "checkUndistortedRectifiedLeftKeypoints");
+    return st;
+  }
+  // UndistorterRectifier.cpp:213-228 / StereoCamera::distortUnrectifyRightKeypoints (cam = 1)
+  Keypoints distortUnrectifyKeypoints(int cam, const std::vector<int32_t>& status, const Keypoints& rectified) const {
+    Keypoints out; out.x.resize(status.size()); out.y.resize(status.size());
+    c_.check(kvfe_distort_unrectify_keypoints(c_.get(), cam, status.data(), rectified.x.data(), rectified.y.data(), (int)status.size(),
+                                              out.x.data(), out.y.data()), "distortUnrectifyKeypoints");
+    return out;
+  }
   // UndistorterRectifier.cpp:73-113: unit bearing vectors (3 doubles per keypoint)
   std::vector<double> GetBearingVectors(const Keypoints& kps) const {
     std::vector<double> v(3 * kps.size());
@@ -89,6 +114,18 @@ class FeatureDetector {
     int n = 0;
     c_.check(kvfe_detect(c_.get(), img.data, img.pitch, existing.x.data(), existing.y.data(), landmarks.data(),
                          (int)existing.size(), need_n_corners, out.x.data(), out.y.data(), &n), "featureDetection");
+    out.x.resize(n); out.y.resize(n);
+    return out;
+  }
+  // the same with the frame's detection_mask_ (FeatureDetector.cpp:186-189)
+  Keypoints featureDetection(const ImageView& img, const ImageView& detection_mask, const Keypoints& existing,
+                             const std::vector<int64_t>& landmarks, int need_n_corners) const {
+    const int cap = kvfe_max_keypoints(c_.get());
+    Keypoints out; out.x.resize(cap); out.y.resize(cap);
+    int n = 0;
+    c_.check(kvfe_detect_masked(c_.get(), img.data, img.pitch, detection_mask.data, detection_mask.pitch, existing.x.data(),
+                                existing.y.data(), landmarks.data(), (int)existing.size(), need_n_corners, out.x.data(), out.y.data(), &n),
+             "featureDetection(mask)");
     out.x.resize(n); out.y.resize(n);
     return out;
   }
@@ -150,6 +187,40 @@ class Tracker {
     r.inliers.resize(ni);
     return r;
   }
+  // computeMedianDisparity :991-1018 (matches: ref index, cur index pairs); false when there is no match
+  bool computeMedianDisparity(const Keypoints& ref, const Keypoints& cur, const std::vector<int32_t>& match_ref,
+                              const std::vector<int32_t>& match_cur, double* median) const {
+    int ok = 0;
+    c_.check(kvfe_compute_median_disparity(c_.get(), ref.x.data(), ref.y.data(), (int)ref.size(), cur.x.data(), cur.y.data(),
+                                           (int)cur.size(), match_ref.data(), match_cur.data(), (int)match_ref.size(), median, &ok),
+             "computeMedianDisparity");
+    return ok != 0;
+  }
+  // getPoint3AndCovariance :772-818 for every rectified stereo point (stereo_point_covariance = identity)
+  void getPoint3AndCovariance(const Keypoints& left_rect, const Keypoints& right_rect, const std::vector<double>& points_3d,
+                              const double* Rmat, std::vector<double>* points, std::vector<double>* covariances) const {
+    const size_t n = left_rect.size();
+    points->resize(3 * n); covariances->resize(9 * n);
+    c_.check(kvfe_point3_and_covariance(c_.get(), left_rect.x.data(), right_rect.x.data(), left_rect.y.data(), points_3d.data(), (int)n,
+                                        Rmat, points->data(), covariances->data()), "getPoint3AndCovariance");
+  }
+  // findOutliers :836-853
+  static std::vector<int32_t> findOutliers(int n_matches, const std::vector<int32_t>& inliers) {
+    std::vector<int32_t> out(n_matches > 0 ? n_matches : 1);
+    int no = 0;
+    if (kvfe_find_outliers(n_matches, inliers.data(), (int)inliers.size(), out.data(), &no) != KVFE_OK) throw Error(KVFE_ERR_INVALID_ARG, "findOutliers");
+    out.resize(no);
+    return out;
+  }
+  // removeOutliersMono :856-882
+  static void removeOutliersMono(const std::vector<int32_t>& inliers, std::vector<int64_t>* ref_landmarks, std::vector<int64_t>* cur_landmarks,
+                                 std::vector<int32_t>* match_ref, std::vector<int32_t>* match_cur) {
+    int nm = (int)match_ref->size();
+    if (kvfe_remove_outliers_mono(inliers.data(), (int)inliers.size(), ref_landmarks->data(), (int)ref_landmarks->size(), cur_landmarks->data(),
+                                  (int)cur_landmarks->size(), match_ref->data(), match_cur->data(), &nm) != KVFE_OK)
+      throw Error(KVFE_ERR_INVALID_ARG, "removeOutliersMono");
+    match_ref->resize(nm); match_cur->resize(nm);
+  }
  private:
   Context c_;
 };
@@ -179,6 +250,25 @@ class StereoMatcher {
                                 (int)n, &o, left_rect ? left_rect->data : nullptr, right_rect ? right_rect->data : nullptr,
                                 left_rect ? left_rect->pitch : 0), "sparseStereoReconstruction");
     return r;
+  }
+  // getRightKeypointsRectified (StereoMatcher.cpp:196-281) on an already rectified pair
+  std::vector<int32_t> getRightKeypointsRectified(const ImageView& left_rectified, const ImageView& right_rectified,
+                                                  const std::vector<int32_t>& left_status, const Keypoints& left_rect,
+                                                  Keypoints* right_rect) const {
+    std::vector<int32_t> st(left_status.size());
+    right_rect->x.resize(st.size()); right_rect->y.resize(st.size());
+    c_.check(kvfe_right_keypoints_rectified(c_.get(), left_rectified.data, right_rectified.data, left_rectified.pitch, left_status.data(),
+                                            left_rect.x.data(), left_rect.y.data(), (int)st.size(), st.data(), right_rect->x.data(),
+                                            right_rect->y.data()), "getRightKeypointsRectified");
+    return st;
+  }
+  // getDepthFromRectifiedMatches (StereoMatcher.cpp:425-483); right_status is updated like the reference's list
+  std::vector<double> getDepthFromRectifiedMatches(const std::vector<int32_t>& left_status, const Keypoints& left_rect,
+                                                   std::vector<int32_t>* right_status, const Keypoints& right_rect) const {
+    std::vector<double> depth(left_status.size());
+    c_.check(kvfe_depth_from_rectified_matches(c_.get(), left_status.data(), left_rect.x.data(), right_status->data(), right_rect.x.data(),
+                                               (int)left_status.size(), depth.data()), "getDepthFromRectifiedMatches");
+    return depth;
   }
  private:
   Context c_;
