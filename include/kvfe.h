@@ -318,6 +318,10 @@ size_t kvfe_packet_bytes(const kvfe_ctx* ctx);
 int kvfe_packet_offsets(const kvfe_ctx* ctx, size_t* offsets, int max_entries);
 
 int kvfe_frontend_reset(kvfe_ctx* ctx);
+/* Multi-GPU (the optional gather of the keypoint packets to rank 0): the frame-level steps assemble their
+ * packets directly in `packets_dev` -- batch * kvfe_packet_bytes() bytes of caller-owned DEVICE memory, typically the
+ * send buffer of an NCCL gather -- so the collective needs no pack or copy kernel.  NULL restores the internal buffer. */
+int kvfe_frontend_bind_packets(kvfe_ctx* ctx, uint8_t* packets_dev);
 /* Frame::isKeyframe_ (include/kimera-vio/frontend/Frame.h:172): flags[b] != 0 makes the NEXT step's frame of stream b a
  * keyframe whatever the other criteria say (VisionImuFrontend::shouldBeKeyframe, VisionImuFrontend.cpp:207-209). */
 int kvfe_frontend_force_keyframe(kvfe_ctx* ctx, const int32_t* flags /* batch */);

@@ -455,7 +455,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
                   db.lk_py, db.lk_qx, db.lk_qy, db.lk_pred_x, db.lk_pred_y, db.lk_src, db.lk_status, db.m_ref,
                   db.m_cur, db.m_n, db.inl, db.inl_n, db.rs_d, db.fr.n, db.fr.timestamp, db.fr.frame_id, db.fr.kx,
                   db.fr.ky, db.fr.lmk, db.fr.age, db.fr.versor, db.fr.lstat, db.fr.lrx, db.fr.lry, db.fr.rstat, db.fr.mstat,
-                  db.fr.rrx, db.fr.rry, db.fr.depth, db.fr.p3d, db.fr.rkx, db.fr.rky, db.st, db.packets, ctx->d_in};
+                  db.fr.rrx, db.fr.rry, db.fr.depth, db.fr.p3d, db.fr.rkx, db.fr.rky, db.st, ctx->own_packets ? ctx->own_packets : db.packets, ctx->d_in};
   for (void* p : ptrs) if (p) cudaFree(p);
   if (ctx->h_stage) cudaFreeHost(ctx->h_stage);
   if (ctx->h_packets) cudaFreeHost(ctx->h_packets);
@@ -1179,6 +1179,23 @@ extern "C" int kvfe_ransac_stereo_1pt(kvfe_ctx* ctx, const float* ref_left_xy, c
 }
 
 // ---- frame-level step ---------------------------------------------------------------------------
+// The packets of the frame-level steps are assembled by finalize_kernel directly in `packets_dev` (batch *
+// kvfe_packet_bytes() bytes of device memory owned by the caller, e.g. the send buffer of an NCCL gather: the optional
+// gather of the keypoint packets to rank 0 then needs no pack / copy kernel).  NULL restores the internal buffer.
+// The captured step graphs hold the buffer address: they are rebuilt on the next step.
+extern "C" int kvfe_frontend_bind_packets(kvfe_ctx* ctx, uint8_t* packets_dev) {
+  if (!ctx) return KVFE_ERR_INVALID_ARG;
+  if (ctx->n_submitted != ctx->n_waited) return set_err(ctx, KVFE_ERR_STATE, "bind_packets with steps in flight");
+  CU(cudaStreamSynchronize(ctx->stream));
+  if (!ctx->own_packets) ctx->own_packets = ctx->db.packets;
+  ctx->db.packets = packets_dev ? packets_dev : ctx->own_packets;
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->graph_ready[i]) { cudaGraphExecDestroy(ctx->step_graph[i]); ctx->graph_ready[i] = 0; }
+    if (ctx->host_graph_ready[i]) { cudaGraphExecDestroy(ctx->host_graph[i]); ctx->host_graph_ready[i] = 0; }
+  }
+  return KVFE_OK;
+}
+
 extern "C" int kvfe_frontend_force_keyframe(kvfe_ctx* ctx, const int32_t* flags) {
   if (!ctx || !flags) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
   // consumed (and cleared) by the next step's keyframe decision; enqueued on the context's stream like the step itself

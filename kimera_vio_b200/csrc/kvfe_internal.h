@@ -217,6 +217,7 @@ struct kvfe_ctx {
   unsigned char* pio[2];
   cudaGraphExec_t pipe_graph[2]; int pipe_graph_ready[2]; long long pipe_graph_launches;
   unsigned int* d_pub_count;   // last-block-done counters: [0] publish_io_kernel, [1] prefetch_io_kernel
+  unsigned char* own_packets;  // the internal packet buffer while kvfe_frontend_bind_packets points db.packets elsewhere
   cudaStream_t side;           // capture-time fork of the pipeline step graph (prefetch branch); no work is ever queued on it
   cudaEvent_t ev_fork, ev_join;
 };

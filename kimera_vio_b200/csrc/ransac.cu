@@ -412,17 +412,19 @@ __device__ int voting_1pt(const DevCfg& dc, int n, const double* rel, double* co
   const float thr = (float)dc.thr_stereo;
   for (int i = threadIdx.x; i < n; i += blockDim.x) sizes[i] = 1;    // coherent with itself
   __syncthreads();
-  // every unordered pair once (the reference evaluates (i, j), i < j, and credits both sets)
-  const long long npairs = (long long)n * (n - 1) / 2;
-  for (long long q = threadIdx.x; q < npairs; q += blockDim.x) {
-    // q -> (i, j), i < j, row-major over the strict upper triangle
-    int i = (int)((2.0 * n - 1.0 - sqrt((2.0 * n - 1.0) * (2.0 * n - 1.0) - 8.0 * (double)q)) * 0.5);
-    long long base = (long long)i * (2 * n - i - 1) / 2;
-    while (base > q) { --i; base = (long long)i * (2 * n - i - 1) / 2; }
-    while (base + (n - i - 1) <= q) { base += (n - i - 1); ++i; }
-    int j = i + 1 + (int)(q - base);
-    float m = maha_f32(relf + 3 * i, covf + 9 * i, relf + 3 * j, covf + 9 * j);
-    if (m < thr) { atomicAdd(&sizes[i], 1); atomicAdd(&sizes[j], 1); }
+  // every unordered pair once (the reference evaluates (i, j), i < j, and credits both sets): one warp per row i,
+  // the lanes run over j > i (coalesced reads of the j side, no index decoding); the counts are order-free
+  {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = blockDim.x >> 5;
+    for (int i = warp; i < n - 1; i += nw) {
+      int ci = 0;
+      for (int j = i + 1 + lane; j < n; j += 32) {
+        const float m = maha_f32(relf + 3 * i, covf + 9 * i, relf + 3 * j, covf + 9 * j);
+        if (m < thr) { ++ci; atomicAdd(&sizes[j], 1); }
+      }
+      ci = warp_sum_i(ci);
+      if (lane == 0 && ci) atomicAdd(&sizes[i], ci);
+    }
   }
   __syncthreads();
   if (threadIdx.x < 32) {                       // first maximum (strict >), warp arg-max

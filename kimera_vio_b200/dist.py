@@ -33,3 +33,31 @@ def max_over_ranks(value_ms: float, device: Optional[torch.device] = None) -> fl
     t = torch.tensor([value_ms], dtype=torch.float64, device=device)
     dist.all_reduce(t, op=dist.ReduceOp.MAX)
     return float(t[0])
+
+
+class PacketGather:
+    """The optional gather of the keypoint packets to rank 0, without a pack kernel: the context's
+    finalize kernel assembles the packets of every step directly in this rank's send buffer
+    (kvfe_frontend_bind_packets), and the NCCL gather is enqueued on the context's own CUDA stream right behind
+    the step graph, so it overlaps nothing it should not and needs no host synchronisation."""
+
+    def __init__(self, ctx, dst: int = 0):
+        self.ctx, self.dst = ctx, dst
+        self.world = dist.get_world_size() if dist.is_initialized() else 1
+        self.rank = dist.get_rank() if dist.is_initialized() else 0
+        nbytes = ctx.B * ctx.packet_bytes
+        self.send = torch.zeros(nbytes, dtype=torch.uint8, device="cuda")
+        self.recv = [torch.empty(nbytes, dtype=torch.uint8, device="cuda") for _ in range(self.world)] if self.rank == dst else None
+        ctx.bind_packets(self.send.data_ptr())
+        self.stream = torch.cuda.ExternalStream(int(ctx.lib.kvfe_cuda_stream(ctx.h)))
+
+    def gather(self):
+        """Enqueue the gather of the last step's packets (returns rank 0's list of per-rank buffers, or None)."""
+        if self.world == 1:
+            return [self.send]
+        with torch.cuda.stream(self.stream):
+            dist.gather(self.send, self.recv, dst=self.dst)
+        return self.recv
+
+    def close(self):
+        self.ctx.bind_packets(0)

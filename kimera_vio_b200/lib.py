@@ -453,6 +453,10 @@ class Context:
     def reset(self):
         self._chk(self.lib.kvfe_frontend_reset(self.h))
 
+    def bind_packets(self, dev_ptr: int):
+        """finalize_kernel writes the packets straight into this device buffer (0 / None: the internal one)."""
+        self._chk(self.lib.kvfe_frontend_bind_packets(self.h, C.c_void_p(dev_ptr or None)))
+
     def force_keyframe(self, flags):
         f = np.ascontiguousarray(flags, np.int32)
         assert f.size == self.B
