@@ -636,6 +636,40 @@ class StereoMatcher:
             return (KP_VALID, match), min_val
         return (KP_NO_RIGHT_RECT, match), min_val
 
+    def exact_sqdiff(self, left_rect, kp, right_rect, stripe_cols, stripe_rows):
+        """The template / stripe of searchRightKeypointEpipolar for one keypoint and its TM_SQDIFF map in EXACT
+        integers (cv::matchTemplate goes through a float DFT): returns (map int64 [rows x cols], scx, scy, offset_temp)
+        or None when the keypoint is rejected before matching.  Used by the tests to classify near-tie divergences."""
+        p = self.p
+        rx, ry = c_round(kp[0]), c_round(kp[1])
+        rows, cols = left_rect.shape
+        tcy = ry - (p.templ_rows - 1) // 2
+        if tcy < 0 or tcy + p.templ_rows > rows - 1:
+            return None
+        offset_temp = 0
+        tcx = rx - (p.templ_cols - 1) // 2
+        if tcx < 0:
+            offset_temp, tcx = tcx, 0
+        if tcx + p.templ_cols > cols - 1:
+            offset_temp = (tcx + p.templ_cols) - (cols - 1)
+            tcx -= offset_temp
+        templ = left_rect[tcy:tcy + p.templ_rows, tcx:tcx + p.templ_cols].astype(np.int64)
+        scy = ry - (stripe_rows - 1) // 2
+        if scy < 0 or scy + stripe_rows > right_rect.shape[0] - 1:
+            return None
+        scx = rx + (p.templ_cols - 1) // 2 - stripe_cols
+        if scx + stripe_cols > right_rect.shape[1] - 1:
+            scx -= (scx + stripe_cols) - (right_rect.shape[1] - 1)
+        if scx < 0:
+            scx = 0
+        stripe = right_rect[scy:scy + stripe_rows, scx:scx + stripe_cols].astype(np.int64)
+        ny, nx = stripe.shape[0] - templ.shape[0] + 1, stripe.shape[1] - templ.shape[1] + 1
+        out = np.zeros((ny, nx), np.int64)
+        for dy in range(ny):
+            win = np.lib.stride_tricks.sliding_window_view(stripe[dy:dy + templ.shape[0]], templ.shape[1], axis=1)  # rows x nx x tc
+            out[dy] = ((win - templ[:, None, :]) ** 2).sum(axis=(0, 2))
+        return out, scx, scy, offset_temp
+
     def get_right_keypoints_rectified(self, left_rect, right_rect, left_kps_rect, fx, baseline):
         """StereoMatcher::getRightKeypointsRectified (StereoMatcher.cpp:196-281)."""
         stripe_cols, stripe_rows = self.stripe_geometry(fx, baseline, right_rect.shape[1])

@@ -84,7 +84,7 @@ def test_shim_methods_with_data(tmp_path):
     lre = np.stack([ss["left_rect_x"], ss["left_rect_y"]], 1)
     rre = np.stack([ss["right_rect_x"], ss["right_rect_y"]], 1)
     p3, cov = ctx.point3_and_covariance(lre, rre, ss["points_3d"], np.eye(3))
-    assert np.array_equal(arr("p3", np.float64).reshape(-1, 3), p3) and np.array_equal(arr("cov", np.float64).reshape(-1, 3, 3), cov)
+    assert np.array_equal(arr("p3", np.float64).reshape(-1, 3), p3, equal_nan=True) and np.array_equal(arr("cov", np.float64).reshape(-1, 3, 3), cov, equal_nan=True)
     v2 = ctx.bearing_vectors(trk)
     st2, _, inl2 = ctx.ransac_mono(vers[m], v2[m], np.eye(3))
     assert int(arr("ransac2_status", np.int32)[0]) == st2 and list(arr("ransac2_inliers", np.int32)) == inl2
