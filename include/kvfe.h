@@ -114,6 +114,12 @@ typedef struct {
    * never silently ignored */
   int32_t optimize_2d2d_pose_from_inliers;  /* VisionImuTrackerParams.cpp:119-122: nonlinear refinement of the RANSAC */
   int32_t optimize_3d3d_pose_from_inliers;  /* pose (opengv optimize_nonlinear); must be 0: KVFE_ERR_INVALID_ARG otherwise */
+  int32_t frontend_type;                /* 0: StereoVisionImuFrontend (default); 1: MonoVisionImuFrontend
+                                           (src/frontend/MonoVisionImuFrontend.cpp:194-371) -- the same kernels without the
+                                           stereo half: no rectification, stereo matching or stereo RANSAC; statuses reset on
+                                           every frame (mono INVALID, stereo DISABLED); the keyframe's keypoints_undistorted_
+                                           (Camera::undistortKeypoints, P = K, R = I) travel in left_status / left_rect_*.
+                                           The rig is kvfe_rig with R1 = I, P1 = [K | 0]; right images are ignored */
   int32_t equalize_image;               /* StereoMatchingParams.cpp:80-90 "equalizeImage": cv::equalizeHist on both raw
                                            images (UtilsOpenCV::ReadAndConvertToGrayScale, UtilsOpenCV.cpp:390-403),
                                            done on the device as the first kernels of a step */

@@ -80,7 +80,7 @@ extern "C" void kvfe_config_default(kvfe_config* c) {
   c->min_number_features = 0; c->use_stereo_tracking = 1; c->use_ransac = 1;
   c->max_disparity_since_lkf = 1000.0;
   c->mesh_2d = 0; c->subdiv_bounding_factor = 0.f;
-  c->optimize_2d2d_pose_from_inliers = 0; c->optimize_3d3d_pose_from_inliers = 0; c->equalize_image = 0;
+  c->optimize_2d2d_pose_from_inliers = 0; c->optimize_3d3d_pose_from_inliers = 0; c->equalize_image = 0; c->frontend_type = 0;
 }
 
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
@@ -215,6 +215,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   if (c.pose_2d2d_algorithm != 1) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "pose_2d2d_algorithm must be 1 (NISTER)");
   if (c.klt_max_level < 0 || c.klt_max_level >= KVFE_MAX_LEVELS) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "klt_max_level must be in [0,%d]", KVFE_MAX_LEVELS - 1);
   if (c.min_distance < 0) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "min_distance must be >= 0");
+  if (c.frontend_type != 0 && c.frontend_type != 1) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "frontend_type must be 0 (stereo) or 1 (mono)");
+  if (c.frontend_type == 1 && c.mesh_2d) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "the 2-D mesh needs stereo matches: not available with the mono front-end");
   if (c.optimize_2d2d_pose_from_inliers || c.optimize_3d3d_pose_from_inliers)
     return set_err(nullptr, KVFE_ERR_INVALID_ARG, "optimize_{2d2d,3d3d}_pose_from_inliers (nonlinear refinement of the RANSAC pose) is not implemented");
 
@@ -395,6 +397,7 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   CUC(dmalloc(&db.st, B));
   dc.mesh_on = c.mesh_2d ? 1 : 0;
   dc.equalize = c.equalize_image ? 1 : 0;
+  dc.mono = c.frontend_type == 1 ? 1 : 0;
   dc.subdiv_factor = c.subdiv_bounding_factor > 0.f ? c.subdiv_bounding_factor : 6.f;
   packet_layout(cap, dc.mesh_on != 0, db.pk_off, &db.packet_bytes);
   launch_mesh_init(dc);
@@ -1243,6 +1246,18 @@ static int enqueue_part_keyframe(kvfe_ctx* ctx, int* kf_counter, long long* n_la
   const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
   unsigned char* Lcur = db.pyr[cur] + dc.lvl_off[0];
   long long n = 0;
+  if (dc.mono) {
+    // MonoVisionImuFrontend::processFrame (MonoVisionImuFrontend.cpp:271-316): mono RANSAC, detection,
+    // Camera::undistortKeypoints (left_rect_kernel with R1 = I, P1 = [K | 0]); no stereo half
+    n += launch_ransac_mono(dc, db, M_KF, s);
+    n += launch_detect_pre(dc, db, M_BOOT | M_KF, kf_counter, s);
+    n += launch_gftt(dc, db, Lcur, dc.pyr_stride, ctx->circle_hw, ctx->circle_r, M_BOOT | M_KF, s);
+    n += launch_select(dc, db, Lcur, dc.pyr_stride, ctx->d_cam, M_BOOT | M_KF, 1, s);
+    n += launch_sparse_stereo_part(dc, db, ctx->d_cam, M_BOOT | M_KF, 0, s);
+    *n_launch += n;
+    CU(cudaGetLastError());
+    return KVFE_OK;
+  }
   // keyframe: mono RANSAC -> sparse stereo -> stereo RANSAC
   n += launch_ransac_mono(dc, db, M_KF, s);
   n += launch_rectify(dc, db.rmap[0], Lcur, dc.pyr_stride, db.rectL, dc.img_stride, dc.B, db.st, M_KF | M_BOOT, s);
@@ -1661,6 +1676,7 @@ extern "C" int kvfe_frontend_step_dev_timed(kvfe_ctx* ctx, const uint8_t* left_d
                                             size_t pitch, const int64_t* timestamps, const double* keyframe_R_cur,
                                             float* stage_ms) {
   if (!ctx || !left_dev || !right_dev || !timestamps || !keyframe_R_cur || !stage_ms) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  if (ctx->dc.mono) return set_err(ctx, KVFE_ERR_INVALID_ARG, "the per-stage timing pass is written for the stereo front-end");
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const size_t B = dc.B;
   RET(stage_inputs(ctx, timestamps, keyframe_R_cur));

@@ -237,7 +237,11 @@ __global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db, cudaG
   }
   const int fk = b * 3 + s.slot_k, fl = b * 3 + s.slot_lkf;
   const int nk = db.fr.n[fk];
-  if (nk == 0) {                       // StereoVisionImuFrontend.cpp:312-323
+  if (dc.mono && threadIdx.x == 0) {   // MonoVisionImuFrontend.cpp:266-267: reset on every frame, before the decision
+    s.mono_status = KVFE_TRK_INVALID; s.stereo_status = KVFE_TRK_DISABLED;
+  }
+  __syncthreads();
+  if (nk == 0 && !dc.mono) {           // StereoVisionImuFrontend.cpp:312-323 (the mono front-end has no such shortcut)
     if (threadIdx.x == 0) { s.mode = 3; db.force_kf[b] = 0; if (cond) cudaGraphSetConditional(cond, 1); }
     return;
   }
@@ -272,7 +276,7 @@ __global__ void __launch_bounds__(256) decide_kernel(DevCfg dc, DevBuf db, cudaG
     if (kf) {
       // StereoVisionImuFrontend.cpp:345-346, :402-404
       s.mono_status = dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED;
-      s.stereo_status = dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED;
+      s.stereo_status = dc.mono ? KVFE_TRK_DISABLED : (dc.use_ransac ? KVFE_TRK_INVALID : KVFE_TRK_DISABLED);
       if (cond) cudaGraphSetConditional(cond, 1);
     }
   }
@@ -338,8 +342,9 @@ __global__ void __launch_bounds__(256) finalize_kernel(DevCfg dc, DevBuf db) {
       o_score[i] = 0.0;
       o_ver[3 * i] = db.fr.versor[3 * k]; o_ver[3 * i + 1] = db.fr.versor[3 * k + 1]; o_ver[3 * i + 2] = db.fr.versor[3 * k + 2];
       if (stereo_valid) {
-        int rs = db.fr.rstat[k];
+        int rs = dc.mono ? -1 : db.fr.rstat[k];          // mono: no right camera; left_* = keypoints_undistorted_
         o_ls[i] = db.fr.lstat[k]; o_lx[i] = db.fr.lrx[k]; o_ly[i] = db.fr.lry[k];
+        if (dc.mono) { db.fr.rrx[k] = 0.f; db.fr.rry[k] = 0.f; db.fr.depth[k] = 0.0; db.fr.p3d[3 * k] = db.fr.p3d[3 * k + 1] = db.fr.p3d[3 * k + 2] = 0.0; db.fr.rkx[k] = db.fr.rky[k] = 0.f; }
         o_rs[i] = rs; o_rx[i] = db.fr.rrx[k]; o_ry[i] = db.fr.rry[k];
         o_depth[i] = db.fr.depth[k];
         o_p3d[3 * i] = db.fr.p3d[3 * k]; o_p3d[3 * i + 1] = db.fr.p3d[3 * k + 1]; o_p3d[3 * i + 2] = db.fr.p3d[3 * k + 2];
@@ -356,7 +361,7 @@ __global__ void __launch_bounds__(256) finalize_kernel(DevCfg dc, DevBuf db) {
       o_sl[pos] = db.fr.lmk[k];
       o_suL[pos] = (double)db.fr.lrx[k];
       o_sv[pos] = (double)db.fr.lry[k];
-      o_suR[pos] = (dc.use_stereo_tracking && db.fr.rstat[k] == KVFE_KP_VALID) ? (double)db.fr.rrx[k]
+      o_suR[pos] = (!dc.mono && dc.use_stereo_tracking && db.fr.rstat[k] == KVFE_KP_VALID) ? (double)db.fr.rrx[k]
                                                                                 : __longlong_as_double(0x7ff8000000000000LL);
     }
   }
@@ -605,7 +610,7 @@ __global__ void __launch_bounds__(128) publish_io_kernel(DevCfg dc, DevBuf db, S
         }
       }
     }
-  } else if (io->dst_rectL && io->dst_rectR) {
+  } else if (io->dst_rectL && io->dst_rectR && !dc.mono) {
     const size_t img = (size_t)dc.W * dc.H;
     const int part = blockIdx.x - 1, nparts = gridDim.x - 1;
     unsigned int uses[FETCH_STAGES] = {0};

@@ -122,6 +122,7 @@ struct DevCfg {          // passed by value to kernels
   double fx, fy, cxr, cyr, baseline;
   // mesher
   int mesh_on; float subdiv_factor;
+  int mono;              // frontend_type 1: MonoVisionImuFrontend (no stereo half)
   // ingest
   int equalize;          // cv::equalizeHist on both raw images before anything else (stereo_matching_params.equalize_image)
 };

@@ -386,6 +386,7 @@ extern "C" int kvfe_pipeline_create(const kvfe_config* cfg, const kvfe_rig* rig,
 
 static int push_one(kvfe_pipeline* p, int stream, const uint8_t* left, const uint8_t* right, size_t pitch,
                     int64_t timestamp, const double* R, uint64_t tag, bool notify) {
+  if (p && !right && !p->streams.empty() && p->streams[0]->ctx->dc.mono) right = left;      // mono front-end: no right camera
   if (!p || !left || !right || !R) return KVFE_ERR_INVALID_ARG;
   if (stream < 0 || stream >= (int)p->streams.size() || pitch < (size_t)p->W) return pipe_fail(p, KVFE_ERR_INVALID_ARG, "push: bad stream or pitch");
   if (int f = p->failed.load()) return f;

@@ -60,6 +60,7 @@ class Config(C.Structure):
         ("max_disparity_since_lkf", C.c_double),
         ("mesh_2d", C.c_int32), ("subdiv_bounding_factor", C.c_float),
         ("optimize_2d2d_pose_from_inliers", C.c_int32), ("optimize_3d3d_pose_from_inliers", C.c_int32),
+        ("frontend_type", C.c_int32),
         ("equalize_image", C.c_int32),
     ]
 
@@ -136,7 +137,7 @@ def _p(a: Optional[np.ndarray]):
 
 
 def make_config(p: FrontendParams, width: int, height: int, batch: int = 1, max_keypoints: int = 0,
-                rnd_libstdcxx: str = "lemire", sobel_cpu_tail_start: int = -1, mesh_2d: bool = False) -> Config:
+                rnd_libstdcxx: str = "lemire", sobel_cpu_tail_start: int = -1, mesh_2d: bool = False, mono: bool = False) -> Config:
     c = Config()
     load().kvfe_config_default(C.byref(c))
     c.width, c.height, c.batch, c.max_keypoints = width, height, batch, max_keypoints
@@ -178,6 +179,7 @@ def make_config(p: FrontendParams, width: int, height: int, batch: int = 1, max_
     c.optimize_2d2d_pose_from_inliers = int(getattr(p, "optimize_2d2d_pose_from_inliers", 0))
     c.optimize_3d3d_pose_from_inliers = int(getattr(p, "optimize_3d3d_pose_from_inliers", 0))
     c.equalize_image = int(p.equalize_image)
+    c.frontend_type = 1 if mono else 0
     return c
 
 

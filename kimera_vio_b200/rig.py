@@ -31,3 +31,20 @@ class StereoRigSetup:
 
     def to_c(self) -> "_lib.Rig":
         return _lib.make_rig(self.left, self.right, self.R1, self.R2, self.P1, self.P2, self.baseline)
+
+
+class MonoRigSetup:
+    """Camera (reference src/frontend/Camera.cpp:29-47) as a kvfe_rig: UndistorterRectifier(P = K, cam_params, R = I)."""
+
+    def __init__(self, cam: CameraParams):
+        if cam.distortion_model != "radtan":
+            raise NotImplementedError("only the radial-tangential pinhole model is supported")
+        self.left = self.right = cam
+        self.W, self.H = cam.width, cam.height
+        self.R1 = self.R2 = np.eye(3)
+        self.P1 = self.P2 = np.hstack([cam.K, np.zeros((3, 1))])
+        self.baseline = 0.0
+        self.fx, self.fy, self.cx, self.cy = cam.K[0, 0], cam.K[1, 1], cam.K[0, 2], cam.K[1, 2]
+
+    def to_c(self) -> "_lib.Rig":
+        return _lib.make_rig(self.left, self.right, self.R1, self.R2, self.P1, self.P2, self.baseline)
