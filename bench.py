@@ -531,9 +531,12 @@ def run_gpu(args):
                                  "wall clock between barriers; every pass reads other frames of a %d MB frame pool (> L2), no L2 flush" %
                                  ((2 * left.nbytes) // 2 ** 20)},
             "e2e": {"value": e2e_value, "unit": "frame-pairs/s", "ms_per_step": e2e_ms / K, "ms_per_pass": e2e_ms / n_timed,
-                    "h2d_bytes_per_step": int(R_in * B * (2 * img + 80)),
+                    # left image + step inputs of every frame, right image of the keyframes only (fetched after the
+                    # keyframe decision: the reference does not touch the right image on other frames)
+                    "h2d_bytes_per_step": int((n_timed * B * (img + 80) + n_kf_timed * img) / K),
                     "d2h_bytes_per_step": int((n_timed * B * pkb + n_kf_timed * 2 * img) / K),
-                    "what": "kvfe_pipeline push/pop, images in pinned host memory read over the link inside the step graph; packets "
+                    "what": "kvfe_pipeline push/pop, images in pinned host memory pulled over the link by the TMA unit inside the step "
+                            "graph (left image of every frame, right image of the keyframes after the on-device decision); packets "
                             "+ keyframe rectified pairs stored into pinned host memory and checksummed by the dispatcher",
                     "outputs_identical_to_value_run": same_outputs},
             "gpu_launches": int(r_v["kernel_launches"]),

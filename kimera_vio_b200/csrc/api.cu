@@ -1240,12 +1240,14 @@ static int enqueue_part_track(kvfe_ctx* ctx, unsigned long long cond, long long*
   return KVFE_OK;
 }
 
-static int enqueue_part_keyframe(kvfe_ctx* ctx, int* kf_counter, long long* n_launch) {
+static int enqueue_part_keyframe(kvfe_ctx* ctx, int* kf_counter, long long* n_launch, const StepIO* io = nullptr) {
   const DevCfg& dc = ctx->dc; DevBuf& db = ctx->db; cudaStream_t s = ctx->stream;
   const int cur = ctx->cur_slot;
   const int M_BOOT = 1 << 0, M_KF = 1 << 2, M_LOST = 1 << 3;
   unsigned char* Lcur = db.pyr[cur] + dc.lvl_off[0];
   long long n = 0;
+  // pipeline step: the right image crosses the host link only when the frame is a keyframe (or the first frame)
+  if (io) n += launch_fetch_right_io(dc, db, io, cur, M_KF | M_BOOT, s);
   if (dc.mono) {
     // MonoVisionImuFrontend::processFrame (MonoVisionImuFrontend.cpp:271-316): mono RANSAC, detection,
     // Camera::undistortKeypoints (left_rect_kernel with R1 = I, P1 = [K | 0]); no stereo half
@@ -1297,7 +1299,7 @@ static int enqueue_step_kernels(kvfe_ctx* ctx, long long* n_launch) {
 int kvfe_enqueue_step_kernels(kvfe_ctx* ctx, const StepIO* io, long long* n_launch) {
   *n_launch = 0;
   RET(enqueue_part_track(ctx, 0ull, n_launch, io));
-  RET(enqueue_part_keyframe(ctx, nullptr, n_launch));
+  RET(enqueue_part_keyframe(ctx, nullptr, n_launch, io));
   return enqueue_part_finalize(ctx, n_launch);
 }
 

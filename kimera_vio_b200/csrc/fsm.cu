@@ -516,15 +516,23 @@ __device__ __forceinline__ void bulk_stream_copy(BulkRing& r, unsigned int (&use
 // Head of the step graph: the frame's images go to pyramid level 0 / the right raw image -- from the staging slot
 // when the previous step's prefetch branch already pulled them (stage_seq == this step's sequence number: an
 // HBM -> HBM copy), else straight from the source the I/O block names.
+// cam_base: grid z = 0 handles camera cam_base, z = 1 camera cam_base + 1.  The head of the step graph fetches the LEFT
+// image only (grid z extent 1, cam_base 0); the RIGHT image is needed by keyframes alone (rectification, stereo
+// matching: "the right image is not touched by the reference on non-keyframes"), so it is fetched after
+// the keyframe decision by the same kernel with cam_base 1 and the keyframe mode mask (st != null): three frames out of
+// four move half the bytes over the host link.
 __global__ void __launch_bounds__(32) fetch_io_kernel(DevCfg dc, const StepIO* __restrict__ io, unsigned char* __restrict__ dstL,
                                                       unsigned char* __restrict__ dstR, const unsigned char* __restrict__ stage,
-                                                      const unsigned long long* __restrict__ stage_seq) {
+                                                      const unsigned long long* __restrict__ stage_seq, int cam_base,
+                                                      const StreamState* __restrict__ st, int mode_mask) {
   __shared__ __align__(128) BulkRing ring;
+  if (st && !mode_on(st[blockIdx.y].mode, mode_mask)) return;
+  const int cam = cam_base + (int)blockIdx.z;
   const bool staged = stage != nullptr && *stage_seq == io->seq;
   const size_t sp = staged ? (size_t)dc.W : (size_t)io->src_pitch;
-  const unsigned char* src = staged ? stage + ((size_t)blockIdx.z * dc.B + blockIdx.y) * dc.img_stride
-                                    : (blockIdx.z ? io->srcR : io->srcL) + (size_t)blockIdx.y * sp * dc.H;
-  unsigned char* dst = blockIdx.z ? dstR + (size_t)blockIdx.y * dc.img_stride : dstL + (size_t)blockIdx.y * dc.pyr_stride;
+  const unsigned char* src = staged ? stage + ((size_t)cam * dc.B + blockIdx.y) * dc.img_stride
+                                    : (cam ? io->srcR : io->srcL) + (size_t)blockIdx.y * sp * dc.H;
+  unsigned char* dst = cam ? dstR + (size_t)blockIdx.y * dc.img_stride : dstL + (size_t)blockIdx.y * dc.pyr_stride;
   const size_t img = (size_t)dc.W * dc.H;
   if (sp == (size_t)dc.W && dc.pitch == dc.W && ((((size_t)src | (size_t)dst) | img) & 15) == 0) {
     if (threadIdx.x == 0) {
@@ -574,8 +582,19 @@ static int bulk_grid(const DevCfg& dc) {
   return g < 2 ? 2 : (g > 16 ? 16 : g);
 }
 int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s) {
-  fetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, 2), 32, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw,
-                                                              db.stage_img[cur_slot], db.stage_seq ? db.stage_seq + cur_slot : nullptr);
+  // left image now; the right one after the keyframe decision (launch_fetch_right_io) -- unless the images are equalised
+  // (then both are conditioned up front like the reference's data provider does) or there is no right camera
+  const int both = dc.equalize && !dc.mono;
+  fetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, both ? 2 : 1), 32, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw,
+                                                                        db.stage_img[cur_slot], db.stage_seq ? db.stage_seq + cur_slot : nullptr,
+                                                                        0, nullptr, 0);
+  return 1;
+}
+int launch_fetch_right_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, int mode_mask, cudaStream_t s) {
+  if (dc.mono || dc.equalize) return 0;
+  fetch_io_kernel<<<dim3(bulk_grid(dc), dc.B, 1), 32, 0, s>>>(dc, io, db.pyr[cur_slot] + dc.lvl_off[0], db.right_raw,
+                                                              db.stage_img[cur_slot], db.stage_seq ? db.stage_seq + cur_slot : nullptr,
+                                                              1, db.st, mode_mask);
   return 1;
 }
 int launch_prefetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, unsigned int* counter, cudaStream_t s) {

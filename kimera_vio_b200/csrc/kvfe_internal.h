@@ -273,6 +273,7 @@ int launch_ransac_3pt_raw(const DevCfg& dc, const DevBuf& db, const double* p_re
 int launch_prep(const DevCfg& dc, const DevBuf& db, const CamModel* d_cam, const long long* ts,
                 const double* Rin, const StepIO* io, cudaStream_t s);
 int launch_fetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, cudaStream_t s);
+int launch_fetch_right_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, int mode_mask, cudaStream_t s);
 int launch_prefetch_io(const DevCfg& dc, const DevBuf& db, const StepIO* io, int cur_slot, unsigned int* counter, cudaStream_t s);
 int launch_publish_io(const DevCfg& dc, const DevBuf& db, StepIO* io, unsigned int* counter, cudaStream_t s);
 int launch_track_pre(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
