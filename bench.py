@@ -8,7 +8,8 @@ One PASS = the whole hot path over one batch of `batch` stereo frame-pairs, one 
 stream.  One STEP = `--inner` consecutive passes (default 128), so that the timed region of the
 driver's `--steps 20` lasts more than a second instead of 11 ms.  Every stream replays a synthetic
 sequence forwards then backwards (continuous motion, any length).  Both measurements go through
-kvfe_pipeline_* (include/kvfe.h), the queue-in / queue-out boundary of the reference's front-end module:
+kvfe_pipeline_* (include/kvfe.h), the queue-in / queue-out boundary of the reference's front-end module (split
+step graphs: the keyframe kernels are launched only for the frames the on-device decision makes keyframes):
 
   value  images already resident in HBM (the pipeline reads them in place); outputs -- packets and the
          keyframes' rectified images -- are still delivered to pinned host memory;

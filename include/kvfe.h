@@ -456,6 +456,9 @@ typedef struct {
                                aligned, device or pinned memory), its images are pulled into a staging slot by a side
                                branch of the current step's graph.  Off by default: with 32 streams on one B200 the
                                forked graphs measured slower than the plain chain (see pipeline.cu) */
+  int32_t split_graphs;     /* 0 = default (on), < 0 = off.  On: the step is two graph launches -- [fetch .. keyframe decision], then, once the dispatcher
+                               has seen the decision in the mapped I/O block, EITHER the keyframe kernels + packet assembly OR
+                               the packet assembly alone (13 kernel launches for a tracking frame instead of 36) */
 } kvfe_pipeline_config;
 typedef struct {
   int32_t stream, slot;     /* slot: pass back to kvfe_pipeline_release */

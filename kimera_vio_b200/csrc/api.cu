@@ -446,6 +446,7 @@ extern "C" void kvfe_destroy(kvfe_ctx* ctx) {
   DevBuf& db = ctx->db;
   for (int i = 0; i < 2; ++i) {
     if (ctx->pipe_graph_ready[i]) cudaGraphExecDestroy(ctx->pipe_graph[i]);
+    if (ctx->pipe_split_ready[i]) { cudaGraphExecDestroy(ctx->pipe_graph_a[i]); cudaGraphExecDestroy(ctx->pipe_graph_kf[i]); cudaGraphExecDestroy(ctx->pipe_graph_nokf[i]); }
     if (ctx->pio[i]) cudaFreeHost(ctx->pio[i]);
   }
   free(const_cast<void*>(db.lk_tmaps));
@@ -1300,6 +1301,18 @@ int kvfe_enqueue_step_kernels(kvfe_ctx* ctx, const StepIO* io, long long* n_laun
   *n_launch = 0;
   RET(enqueue_part_track(ctx, 0ull, n_launch, io));
   RET(enqueue_part_keyframe(ctx, nullptr, n_launch, io));
+  return enqueue_part_finalize(ctx, n_launch);
+}
+
+// the pieces of a pipeline step for the split graphs (pipeline.cu)
+int kvfe_enqueue_step_part(kvfe_ctx* ctx, StepIO* io, int part, long long* n_launch) {
+  *n_launch = 0;
+  if (part == 0) {
+    RET(enqueue_part_track(ctx, 0ull, n_launch, io));
+    *n_launch += launch_publish_decision(ctx->db, io, ctx->stream);
+    return KVFE_OK;
+  }
+  if (part == 1) RET(enqueue_part_keyframe(ctx, nullptr, n_launch, io));
   return enqueue_part_finalize(ctx, n_launch);
 }
 

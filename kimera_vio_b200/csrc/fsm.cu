@@ -667,6 +667,20 @@ int launch_publish_io(const DevCfg& dc, const DevBuf& db, StepIO* io, unsigned i
   publish_io_kernel<<<1 + bulk_grid(dc), 128, 0, s>>>(dc, db, io, counter);
   return 1;
 }
+// split step graphs (pipeline.cu): the keyframe decision of the (single) stream of a pipeline context goes to the mapped
+// I/O block as soon as it exists, so that the dispatcher launches the keyframe kernels only for the frames that need them
+__global__ void publish_decision_kernel(DevBuf db, StepIO* io) {
+  if (threadIdx.x == 0) {
+    io->decided_mode = db.st[0].mode;
+    __threadfence_system();
+    io->decided_seq = io->seq;
+    __threadfence_system();
+  }
+}
+int launch_publish_decision(const DevBuf& db, StepIO* io, cudaStream_t s) {
+  publish_decision_kernel<<<1, 32, 0, s>>>(db, io);
+  return 1;
+}
 int launch_finalize(const DevCfg& dc, const DevBuf& db, cudaStream_t s) {
   finalize_kernel<<<dc.B, 256, 0, s>>>(dc, db);
   return 1;

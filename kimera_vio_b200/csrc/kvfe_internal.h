@@ -87,6 +87,9 @@ struct StepIO {
   const unsigned char* next_srcR;   // aligned), else null: pulled into the staging slot while this step computes
   unsigned long long pad1[6];
   volatile unsigned long long done_seq;   // device -> host, own 64-byte line
+  unsigned long long pad2[7];
+  volatile unsigned long long decided_seq;  // split step graphs: published right after the keyframe decision, own line
+  volatile int decided_mode;                // StreamState::mode of the frame (1 = tracking frame: no keyframe kernels needed)
 };
 static_assert(sizeof(StepIO) <= KVFE_STEPIO_ARRAYS, "StepIO header must fit before the arrays");
 
@@ -217,6 +220,9 @@ struct kvfe_ctx {
   // pipeline step (pipeline.cu): I/O blocks in mapped pinned memory, one graph per pyramid slot
   unsigned char* pio[2];
   cudaGraphExec_t pipe_graph[2]; int pipe_graph_ready[2]; long long pipe_graph_launches;
+  // split variant: [fetch .. decide, publish_decision] | host picks | [keyframe kernels, finalize, publish] or [finalize, publish]
+  cudaGraphExec_t pipe_graph_a[2], pipe_graph_kf[2], pipe_graph_nokf[2]; int pipe_split_ready[2];
+  long long pipe_launches_a, pipe_launches_kf, pipe_launches_nokf;
   unsigned int* d_pub_count;   // last-block-done counters: [0] publish_io_kernel, [1] prefetch_io_kernel
   unsigned char* own_packets;  // the internal packet buffer while kvfe_frontend_bind_packets points db.packets elsewhere
   cudaStream_t side;           // capture-time fork of the pipeline step graph (prefetch branch); no work is ever queued on it
@@ -298,3 +304,5 @@ int launch_mesh_raw(const DevCfg& dc, const DevBuf& db, const float* x, const fl
 // api.cu (shared with pipeline.cu)
 int kvfe_set_err(kvfe_ctx* ctx, int code, const char* fmt, ...);
 int kvfe_enqueue_step_kernels(kvfe_ctx* ctx, const StepIO* io, long long* n_launch);
+int kvfe_enqueue_step_part(kvfe_ctx* ctx, StepIO* io, int part, long long* n_launch);   // 0 track + decision, 1 keyframe + finalize, 2 finalize
+int launch_publish_decision(const DevBuf& db, StepIO* io, cudaStream_t s);

@@ -11,6 +11,7 @@
 #include <chrono>
 #include <condition_variable>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <deque>
 #include <mutex>
@@ -30,7 +31,7 @@ struct PipeIn {
   int force_kf;
 };
 struct PipeOutSlot { unsigned char* packet; unsigned char* rectL; unsigned char* rectR; };
-struct PipeFlight { int out_slot, io_slot; unsigned long long seq, tag; };
+struct PipeFlight { int out_slot, io_slot; unsigned long long seq, tag; int phase; };   // phase 0: decision pending (split graphs)
 
 struct PipeStream {
   kvfe_ctx* ctx = nullptr;
@@ -68,6 +69,7 @@ struct kvfe_pipeline {
   std::atomic<long long> launch_ns{0};
   std::atomic<int> failed{0};
   std::mutex err_mu; char err[512] = "";
+  bool split = false;                 // split step graphs (keyframe kernels launched only for keyframes)
 };
 
 static thread_local char g_pipe_create_err[512] = "";
@@ -113,6 +115,47 @@ static int build_pipe_graph(kvfe_ctx* ctx, int slot) {
   ctx->pipe_graph_ready[slot] = 1;
   ctx->pipe_graph_launches = n;
   return KVFE_OK;
+}
+
+// Split variant: three graphs per pyramid slot.  A = fetch(left) .. decide + publish_decision; then the dispatcher, which
+// polls the decision in the mapped I/O block, launches EITHER the keyframe graph (fetch(right), RANSAC, rectification,
+// stereo, detection, finalize, publish) OR the two-kernel tracking tail (finalize, publish).  A tracking frame -- three out
+// of four -- costs 13 launches instead of 36; the price is one host reaction per frame, hidden by the other streams.
+static int capture_exec(kvfe_ctx* ctx, cudaGraphExec_t* exec, int (*body)(kvfe_ctx*, StepIO*, int, long long*), StepIO* io, int arg,
+                        long long* n) {
+  cudaGraph_t g = nullptr;
+  cudaError_t e = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeThreadLocal);
+  if (e != cudaSuccess) return kvfe_set_err(ctx, KVFE_ERR_CUDA, "pipeline graph capture: %s", cudaGetErrorString(e));
+  const int rc = body(ctx, io, arg, n);
+  e = cudaStreamEndCapture(ctx->stream, &g);
+  if (rc != KVFE_OK) { if (g) cudaGraphDestroy(g); return rc; }
+  if (e != cudaSuccess) return kvfe_set_err(ctx, KVFE_ERR_CUDA, "pipeline graph capture: %s", cudaGetErrorString(e));
+  e = cudaGraphInstantiate(exec, g, 0);
+  cudaGraphDestroy(g);
+  if (e != cudaSuccess) return kvfe_set_err(ctx, KVFE_ERR_CUDA, "pipeline graph instantiation: %s", cudaGetErrorString(e));
+  return KVFE_OK;
+}
+static int body_a(kvfe_ctx* ctx, StepIO* io, int slot, long long* n) {
+  long long k = 0;
+  *n = launch_fetch_io(ctx->dc, ctx->db, io, slot, ctx->stream);
+  const int rc = kvfe_enqueue_step_part(ctx, io, 0, &k);
+  *n += k;
+  return rc;
+}
+static int body_tail(kvfe_ctx* ctx, StepIO* io, int part, long long* n) {
+  long long k = 0;
+  const int rc = kvfe_enqueue_step_part(ctx, io, part, &k);
+  *n = k + launch_publish_io(ctx->dc, ctx->db, io, ctx->d_pub_count, ctx->stream);
+  return rc;
+}
+static int build_split_graphs(kvfe_ctx* ctx, int slot) {
+  ctx->cur_slot = slot;
+  StepIO* io = reinterpret_cast<StepIO*>(ctx->pio[slot]);
+  int rc = capture_exec(ctx, &ctx->pipe_graph_a[slot], body_a, io, slot, &ctx->pipe_launches_a);
+  if (rc == KVFE_OK) rc = capture_exec(ctx, &ctx->pipe_graph_kf[slot], body_tail, io, 1, &ctx->pipe_launches_kf);
+  if (rc == KVFE_OK) rc = capture_exec(ctx, &ctx->pipe_graph_nokf[slot], body_tail, io, 2, &ctx->pipe_launches_nokf);
+  if (rc == KVFE_OK) ctx->pipe_split_ready[slot] = 1;
+  return rc;
 }
 
 // sum of the 64-bit words of [p, p + bytes) (bytes is a multiple of 8 for every range used here)
@@ -198,6 +241,7 @@ static void worker_main(kvfe_pipeline* p, int widx) {
   std::vector<int> mine;
   for (int i = widx; i < (int)p->streams.size(); i += p->pc.n_workers) mine.push_back(i);
   const int depth = p->pc.max_in_flight;
+  const bool split = p->split;
   int idle = 0;
   while (!p->stop.load(std::memory_order_acquire)) {
     bool progress = false;
@@ -209,14 +253,34 @@ static void worker_main(kvfe_pipeline* p, int widx) {
       while (!s->fl.empty()) {
         const PipeFlight& f = s->fl.front();
         const StepIO* io = reinterpret_cast<const StepIO*>(ctx->pio[f.io_slot]);
-        if (io->done_seq != f.seq) break;
+        if (f.phase == 0 || io->done_seq != f.seq) break;
         std::atomic_thread_fence(std::memory_order_acquire);
         emit(p, si, s, f);
         s->fl.pop_front();
         progress = true;
       }
-      // launches
-      while ((int)s->fl.size() < depth) {
+      // split graphs: the frame whose keyframe decision has arrived gets its second graph (at most one frame per
+      // stream is in that phase, and it is the newest one)
+      if (split && !s->fl.empty() && s->fl.back().phase == 0) {
+        PipeFlight& f = s->fl.back();
+        const StepIO* io = reinterpret_cast<const StepIO*>(ctx->pio[f.io_slot]);
+        if (io->decided_seq == f.seq) {
+          std::atomic_thread_fence(std::memory_order_acquire);
+          const double t0 = now_s();
+          const bool kf = io->decided_mode != 1;
+          cudaError_t e = cudaGraphLaunch(kf ? ctx->pipe_graph_kf[f.io_slot] : ctx->pipe_graph_nokf[f.io_slot], ctx->stream);
+          if (e != cudaSuccess) { pipe_fail(p, KVFE_ERR_CUDA, cudaGetErrorString(e)); break; }
+          f.phase = 1;
+          const long long nk = kf ? ctx->pipe_launches_kf : ctx->pipe_launches_nokf;
+          ctx->launches += nk;
+          p->n_graph.fetch_add(1, std::memory_order_relaxed);
+          p->n_kernels.fetch_add(nk, std::memory_order_relaxed);
+          p->launch_ns.fetch_add((long long)((now_s() - t0) * 1e9), std::memory_order_relaxed);
+          progress = true;
+        }
+      }
+      // launches (split graphs: not while the newest frame still waits for its second graph -- stream order)
+      while ((int)s->fl.size() < depth && !(split && !s->fl.empty() && s->fl.back().phase == 0)) {
         PipeIn in, nxt; int oslot = -1;
         bool have_next = false;
         {
@@ -254,13 +318,14 @@ static void worker_main(kvfe_pipeline* p, int widx) {
         memcpy(arr, &in.ts, sizeof(long long));
         memcpy(arr + sizeof(long long), in.Rm, 9 * sizeof(double));
         std::atomic_thread_fence(std::memory_order_release);
-        cudaError_t e = cudaGraphLaunch(ctx->pipe_graph[io_slot], ctx->stream);
+        cudaError_t e = cudaGraphLaunch(split ? ctx->pipe_graph_a[io_slot] : ctx->pipe_graph[io_slot], ctx->stream);
         if (e != cudaSuccess) { pipe_fail(p, KVFE_ERR_CUDA, cudaGetErrorString(e)); break; }
         ctx->cur_slot ^= 1;
-        ctx->launches += ctx->pipe_graph_launches;
-        s->fl.push_back(PipeFlight{oslot, io_slot, s->seq, in.tag});
+        const long long nl = split ? ctx->pipe_launches_a : ctx->pipe_graph_launches;
+        ctx->launches += nl;
+        s->fl.push_back(PipeFlight{oslot, io_slot, s->seq, in.tag, split ? 0 : 1});
         p->n_graph.fetch_add(1, std::memory_order_relaxed);
-        p->n_kernels.fetch_add(ctx->pipe_graph_launches, std::memory_order_relaxed);
+        p->n_kernels.fetch_add(nl, std::memory_order_relaxed);
         p->launch_ns.fetch_add((long long)((now_s() - t0) * 1e9), std::memory_order_relaxed);
         progress = true;
       }
@@ -322,6 +387,12 @@ extern "C" int kvfe_pipeline_create(const kvfe_config* cfg, const kvfe_rig* rig,
   // 0.87): a step graph with a parallel branch costs twice the launch time on the host and the branches of 32
   // graphs compete for the 32 hardware work queues; the overlap across streams already hides the transfer
   p->pc.prefetch = pc->prefetch > 0 ? 1 : 0;
+  {
+    // KVFE_PIPE_SPLIT=0/1 overrides (diagnostic); the prefetch branch lives in the single-graph variant only
+    const char* e = getenv("KVFE_PIPE_SPLIT");
+    p->split = e ? (e[0] == '1') : (pc->split_graphs >= 0);      // library default: on (measured below)
+    if (p->pc.prefetch) p->split = false;
+  }
   p->W = cfg->width; p->H = cfg->height; p->img = (size_t)cfg->width * cfg->height;
   kvfe_config c1 = *cfg;
   c1.batch = 1;
@@ -351,7 +422,7 @@ extern "C" int kvfe_pipeline_create(const kvfe_config* cfg, const kvfe_rig* rig,
       }
     }
     for (int slot = 1; slot >= 0; --slot) {      // slot 0 last: cur_slot ends at 0
-      rc = build_pipe_graph(s->ctx, slot);
+      rc = p->split ? build_split_graphs(s->ctx, slot) : build_pipe_graph(s->ctx, slot);
       if (rc != KVFE_OK) {
         pipe_fail(nullptr, rc, kvfe_last_error(s->ctx));
         kvfe_pipeline_destroy(p);

@@ -563,7 +563,7 @@ class Context:
 class PipelineConfig(C.Structure):
     _fields_ = [("n_streams", C.c_int32), ("n_workers", C.c_int32), ("queue_depth", C.c_int32),
                 ("output_slots", C.c_int32), ("want_rectified", C.c_int32), ("rotation_mode", C.c_int32),
-                ("checksum_outputs", C.c_int32), ("max_in_flight", C.c_int32), ("prefetch", C.c_int32)]
+                ("checksum_outputs", C.c_int32), ("max_in_flight", C.c_int32), ("prefetch", C.c_int32), ("split_graphs", C.c_int32)]
 
 
 class PipelineOutput(C.Structure):
@@ -605,11 +605,11 @@ class Pipeline:
 
     def __init__(self, cfg: Config, rig: Rig, n_streams: int, n_workers: int = 0, queue_depth: int = 4,
                  output_slots: int = 4, want_rectified: bool = True, rotation_mode: int = 0,
-                 checksum_outputs: bool = False, max_in_flight: int = 0, prefetch: int = 0):
+                 checksum_outputs: bool = False, max_in_flight: int = 0, prefetch: int = 0, split_graphs: int = 0):
         self.lib = load()
         _pipeline_protos(self.lib)
         self.pc = PipelineConfig(n_streams, n_workers, queue_depth, output_slots, int(want_rectified), rotation_mode,
-                                 int(checksum_outputs), max_in_flight, prefetch)
+                                 int(checksum_outputs), max_in_flight, prefetch, split_graphs)
         h = C.c_void_p()
         rc = self.lib.kvfe_pipeline_create(C.byref(cfg), C.byref(rig), C.byref(self.pc), C.byref(h))
         if rc != 0:
