@@ -89,6 +89,10 @@ def main():
         ("HOST 32x1 w4 if2 norect nochk", 32, 1, 4, 2, False, False, True),
         ("HOST 32x1 w8 if2 rect chk", 32, 1, 8, 2, True, True, True),
         ("HOST 32x1 w4 if2 rect chk PREFETCH", 32, 1, 4, 2, True, True, True, 1),
+        ("32x1 w8 if2 rect chk", 32, 1, 8, 2, True, True),
+        ("32x1 w2 if2 rect chk", 32, 1, 2, 2, True, True),
+        ("HOST 32x1 w8 if2 rect chk", 32, 1, 8, 2, True, True, True),
+        ("HOST 32x1 w2 if2 rect chk", 32, 1, 2, 2, True, True, True),
         ("32x1 w4 if2 rect chk PREFETCH", 32, 1, 4, 2, True, True, False, 1),
     ]
     want = set(args.variants.split(",")) if args.variants else None
