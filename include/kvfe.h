@@ -127,13 +127,19 @@ typedef struct {
 
 /* Stereo rig after cv::stereoRectify -- what StereoCamera::StereoCamera hands to its two
  * UndistorterRectifiers (src/frontend/StereoCamera.cpp:34-94,
- * src/frontend/UndistorterRectifier.cpp:26-31, :230-292). Radial-tangential pinhole only. */
+ * src/frontend/UndistorterRectifier.cpp:26-31, :230-292). Pinhole cameras with the radial-tangential or the
+ * equidistant (cv::fisheye) distortion model (CameraParams.cpp:125-140); the omni model is not supported. */
+#define KVFE_DISTORTION_RADTAN 0        /* cv::stereoRectify / initUndistortRectifyMap / undistortPoints */
+#define KVFE_DISTORTION_EQUIDISTANT 1   /* cv::fisheye::stereoRectify / initUndistortRectifyMap / undistortPoints
+                                           (StereoCamera.cpp:350-373, UndistorterRectifier.cpp:49-56, :260-268) */
 typedef struct {
   double K_left[9], K_right[9];
-  double D_left[4], D_right[4];   /* k1 k2 p1 p2 */
+  double D_left[4], D_right[4];   /* radtan: k1 k2 p1 p2; equidistant: k1 k2 k3 k4 */
   double R1[9], R2[9];
   double P1[12], P2[12];
   double baseline;                /* 1 / Q(3,2), StereoCamera.cpp:70-72 */
+  int32_t distortion_model;       /* KVFE_DISTORTION_*; both cameras share it (StereoCamera.cpp:328 switches on the left one) */
+  int32_t reserved;               /* 0 */
 } kvfe_rig;
 
 /* Fills every field with the reference's struct defaults / the Euroc YAML. */

@@ -86,7 +86,8 @@ extern "C" void kvfe_config_default(kvfe_config* c) {
 static size_t round_up(size_t v, size_t a) { return (v + a - 1) / a * a; }
 
 // P[:, :3] * R with cv::gemm's 3x3 path, then cv::invert's 3x3 cofactor formula
-static void make_cam(CamModel& c, const double* K, const double* D, const double* R, const double* P) {
+static void make_cam(CamModel& c, const double* K, const double* D, const double* R, const double* P, int model) {
+  c.model = model; c.pad = 0;
   c.fx = K[0]; c.fy = K[4]; c.cx = K[2]; c.cy = K[5];
   c.k1 = D[0]; c.k2 = D[1]; c.p1 = D[2]; c.p2 = D[3];
   for (int i = 0; i < 9; ++i) c.R[i] = R[i];
@@ -216,6 +217,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   if (c.klt_max_level < 0 || c.klt_max_level >= KVFE_MAX_LEVELS) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "klt_max_level must be in [0,%d]", KVFE_MAX_LEVELS - 1);
   if (c.min_distance < 0) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "min_distance must be >= 0");
   if (c.frontend_type != 0 && c.frontend_type != 1) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "frontend_type must be 0 (stereo) or 1 (mono)");
+  if (rig->distortion_model != KVFE_DISTORTION_RADTAN && rig->distortion_model != KVFE_DISTORTION_EQUIDISTANT)
+    return set_err(nullptr, KVFE_ERR_INVALID_ARG, "kvfe_rig.distortion_model must be KVFE_DISTORTION_RADTAN or KVFE_DISTORTION_EQUIDISTANT (omni is not supported)");
   if (c.frontend_type == 1 && c.mesh_2d) return set_err(nullptr, KVFE_ERR_INVALID_ARG, "the 2-D mesh needs stereo matches: not available with the mono front-end");
   if (c.optimize_2d2d_pose_from_inliers || c.optimize_3d3d_pose_from_inliers)
     return set_err(nullptr, KVFE_ERR_INVALID_ARG, "optimize_{2d2d,3d3d}_pose_from_inliers (nonlinear refinement of the RANSAC pose) is not implemented");
@@ -289,8 +292,8 @@ extern "C" int kvfe_create(const kvfe_config* cfg, const kvfe_rig* rig, kvfe_ctx
   dc.use_stereo_tracking = c.use_stereo_tracking; dc.disparity_thr = c.disparity_threshold; dc.max_disparity = c.max_disparity_since_lkf;
   dc.min_kf_ns = c.min_intra_keyframe_time_ns; dc.max_kf_ns = c.max_intra_keyframe_time_ns; dc.min_features = c.min_number_features;
 
-  make_cam(ctx->cam[0], rig->K_left, rig->D_left, rig->R1, rig->P1);
-  make_cam(ctx->cam[1], rig->K_right, rig->D_right, rig->R2, rig->P2);
+  make_cam(ctx->cam[0], rig->K_left, rig->D_left, rig->R1, rig->P1, rig->distortion_model);
+  make_cam(ctx->cam[1], rig->K_right, rig->D_right, rig->R2, rig->P2, rig->distortion_model);
 
   CUC(cudaGetDevice(&ctx->device));
   CUC(cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking));

@@ -81,11 +81,52 @@ __device__ __forceinline__ void matmul3(const double* A, const double* B, double
   for (int i = 0; i < 9; ++i) C[i] = t[i];
 }
 
+// cv::fisheye::undistortPoints (OpenCV 4.13, default criteria COUNT + EPS, 10 iterations, 1e-8) -- the equidistant
+// model of UndistorterRectifier::UndistortRectifyKeypoints (UndistorterRectifier.cpp:49-56): Newton iterations on
+// theta_d = theta (1 + k1 theta^2 + k2 theta^4 + k3 theta^6 + k4 theta^8), f64; a point that does not converge or
+// whose theta changes sign comes back as (-1e6, -1e6).  Restated against cv2 in scratch/fisheye_probe.py (bit-exact
+// on 16 000 points incl. non-convergent ones).  Modes as below.
+__device__ __forceinline__ void undistort_point_fisheye(const CamModel& c, float u, float v, int mode, float* ox, float* oy) {
+  const double pw0 = ((double)u - c.cx) / c.fx, pw1 = ((double)v - c.cy) / c.fy;
+  double theta_d = sqrt(pw0 * pw0 + pw1 * pw1);
+  const double half_pi = 1.5707963267948966;
+  theta_d = fmin(fmax(-half_pi, theta_d), half_pi);
+  bool converged = false;
+  double theta = theta_d, scale = 0.0;
+  if (fabs(theta_d) > 1e-8) {
+#pragma unroll 1
+    for (int j = 0; j < 10; ++j) {
+      const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t6 * t2;
+      const double a = c.k1 * t2, b = c.k2 * t4, cc = c.p1 * t6, d = c.p2 * t8;
+      const double fix = (theta * (1 + a + b + cc + d) - theta_d) / (1 + 3 * a + 5 * b + 7 * cc + 9 * d);
+      theta = theta - fix;
+      if (fabs(fix) < 1e-8) { converged = true; break; }
+    }
+    scale = tan(theta) / theta_d;
+  } else {
+    converged = true;
+  }
+  const bool flipped = (theta_d < 0 && theta > 0) || (theta_d > 0 && theta < 0);
+  if (!converged || flipped) { *ox = -1000000.0f; *oy = -1000000.0f; return; }
+  double x = pw0 * scale, y = pw1 * scale;
+  if (mode != 0) {
+    const double* M = (mode == 1) ? c.R : (mode == 2 ? c.RP : c.PP);
+    const double xx = (M[0] * x + M[1] * y) + M[2];
+    const double yy = (M[3] * x + M[4] * y) + M[5];
+    const double ww = (M[6] * x + M[7] * y) + M[8];
+    x = xx / ww;
+    y = yy / ww;
+  }
+  *ox = (float)x;
+  *oy = (float)y;
+}
+
 // cv::undistortPoints (cvUndistortPointsInternal), radial-tangential 4-coefficient model, default
 // criteria = exactly 5 fixed-point iterations, f64.  mode 0: no R, no P; 1: R only; 2: R and P
 // (OpenCV folds P into the rotation first: RR = P[:, :3] * R, CamModel::RP); 3: P only.
 __device__ __forceinline__ void undistort_point(const CamModel& c, float u, float v, int mode, float* ox,
                                                 float* oy) {
+  if (c.model == 1) { undistort_point_fisheye(c, u, v, mode, ox, oy); return; }
   const double ifx = 1.0 / c.fx, ify = 1.0 / c.fy;
   double x0 = ((double)u - c.cx) * ifx;
   double y0 = ((double)v - c.cy) * ify;
@@ -112,9 +153,38 @@ __device__ __forceinline__ void undistort_point(const CamModel& c, float u, floa
   *oy = (float)y;
 }
 
+// f32 map value of cv::fisheye::initUndistortRectifyMap (CV_32FC1; UndistorterRectifier.cpp:260-268) at integer pixel
+// (u, v).  OpenCV walks a row with three running f64 sums (_x += iR(0,0) per column), so column u is reached by u
+// sequential additions from the row start -- reproduced as such (one-off table build and a few hundred sparse
+// look-ups per keyframe).  0 mismatches against cv2 in 2 x 307 200 values (scratch/fisheye_probe.py).
+__device__ __forceinline__ void rect_map_at_fisheye(const CamModel& c, int u, int v, float* mx, float* my) {
+  const double vd = (double)v;
+  double X = vd * c.iR[1] + c.iR[2], Y = vd * c.iR[4] + c.iR[5], Wd = vd * c.iR[7] + c.iR[8];
+#pragma unroll 1
+  for (int j = 0; j < u; ++j) { X += c.iR[0]; Y += c.iR[3]; Wd += c.iR[6]; }
+  double uu, vv;
+  if (Wd <= 0) {
+    const double inf = __longlong_as_double(0x7ff0000000000000LL);
+    uu = (X > 0) ? -inf : inf;
+    vv = (Y > 0) ? -inf : inf;
+  } else {
+    const double x = X / Wd, y = Y / Wd;
+    const double r = sqrt(x * x + y * y);
+    const double theta = atan(r);
+    const double t2 = theta * theta, t4 = t2 * t2, t6 = t4 * t2, t8 = t4 * t4;
+    const double theta_d = theta * (1 + c.k1 * t2 + c.k2 * t4 + c.p1 * t6 + c.p2 * t8);
+    const double scale = (r == 0) ? 1.0 : theta_d / r;
+    uu = c.fx * x * scale + c.cx;
+    vv = c.fy * y * scale + c.cy;
+  }
+  *mx = (float)uu;
+  *my = (float)vv;
+}
+
 // f32 map value of cv::initUndistortRectifyMap (CV_32FC1) at integer pixel (u, v), recomputed in
 // f64 exactly as validated against cv2 (scratch prototype: 0 mismatches in 4 x 360 960 values).
 __device__ __forceinline__ void rect_map_at(const CamModel& c, int u, int v, float* mx, float* my) {
+  if (c.model == 1) { rect_map_at_fisheye(c, u, v, mx, my); return; }
   double ud = (double)u, vd = (double)v;
   double X = (c.iR[0] * ud + c.iR[1] * vd) + c.iR[2];
   double Y = (c.iR[3] * ud + c.iR[4] * vd) + c.iR[5];

@@ -25,6 +25,8 @@ struct CamModel {        // one camera of the rig, everything the kernels need (
   double PP[9];          // P[:, :3]
   double RP[9];          // P[:, :3] * R   (cv::gemm 3x3 fast path: (a0*b0 + a1*b1) + a2*b2)
   double iR[9];          // inv(RP), cv::invert 3x3 cofactor formula -- for map recomputation
+  int model;             // 0 radial-tangential (k1 k2 p1 p2), 1 equidistant / cv::fisheye (k1..k4 held in k1 k2 p1 p2)
+  int pad;
 };
 
 struct FrameSoA {        // flat arrays, index (stream*3 + slot)*cap + i

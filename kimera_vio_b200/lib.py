@@ -65,12 +65,15 @@ class Config(C.Structure):
     ]
 
 
+DISTORTION_MODELS = {"radtan": 0, "equidistant": 1}   # KVFE_DISTORTION_*
+
+
 class Rig(C.Structure):
     _fields_ = [("K_left", C.c_double * 9), ("K_right", C.c_double * 9),
                 ("D_left", C.c_double * 4), ("D_right", C.c_double * 4),
                 ("R1", C.c_double * 9), ("R2", C.c_double * 9),
                 ("P1", C.c_double * 12), ("P2", C.c_double * 12),
-                ("baseline", C.c_double)]
+                ("baseline", C.c_double), ("distortion_model", C.c_int32), ("reserved", C.c_int32)]
 
 
 class PacketHeader(C.Structure):
@@ -194,6 +197,9 @@ def make_rig(left: CameraParams, right: CameraParams, R1, R2, P1, P2, baseline: 
     r.P1[:] = list(np.asarray(P1, np.float64).reshape(-1))
     r.P2[:] = list(np.asarray(P2, np.float64).reshape(-1))
     r.baseline = float(baseline)
+    if left.distortion_model not in DISTORTION_MODELS or right.distortion_model != left.distortion_model:
+        raise ValueError("unsupported distortion model %r / %r" % (left.distortion_model, right.distortion_model))
+    r.distortion_model = DISTORTION_MODELS[left.distortion_model]
     return r
 
 

@@ -22,10 +22,14 @@ class StereoRigSetup:
         camL_T_camR = np.linalg.inv(left.T_BS) @ right.T_BS
         inv = np.linalg.inv(camL_T_camR)
         R, T = inv[:3, :3].copy(), inv[:3, 3].copy()
-        if left.distortion_model != "radtan":
-            raise NotImplementedError("only the radial-tangential pinhole model is supported")
-        self.R1, self.R2, self.P1, self.P2, self.Q, _, _ = cv2.stereoRectify(
-            left.K, left.D, right.K, right.D, (self.W, self.H), R, T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
+        if left.distortion_model == "radtan":
+            self.R1, self.R2, self.P1, self.P2, self.Q, _, _ = cv2.stereoRectify(
+                left.K, left.D, right.K, right.D, (self.W, self.H), R, T, flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)
+        elif left.distortion_model == "equidistant":      # StereoCamera.cpp:350-373
+            self.R1, self.R2, self.P1, self.P2, self.Q = cv2.fisheye.stereoRectify(
+                left.K, left.D, right.K, right.D, (self.W, self.H), R, T, flags=cv2.CALIB_ZERO_DISPARITY)
+        else:
+            raise NotImplementedError("distortion model %r: only radtan and equidistant pinhole cameras" % left.distortion_model)
         self.baseline = 1.0 / self.Q[3, 2]
         self.fx, self.fy, self.cx, self.cy = self.P1[0, 0], self.P1[1, 1], self.P1[0, 2], self.P1[1, 2]
 
@@ -37,8 +41,8 @@ class MonoRigSetup:
     """Camera (reference src/frontend/Camera.cpp:29-47) as a kvfe_rig: UndistorterRectifier(P = K, cam_params, R = I)."""
 
     def __init__(self, cam: CameraParams):
-        if cam.distortion_model != "radtan":
-            raise NotImplementedError("only the radial-tangential pinhole model is supported")
+        if cam.distortion_model not in ("radtan", "equidistant"):
+            raise NotImplementedError("distortion model %r: only radtan and equidistant pinhole cameras" % cam.distortion_model)
         self.left = self.right = cam
         self.W, self.H = cam.width, cam.height
         self.R1 = self.R2 = np.eye(3)

@@ -1,7 +1,7 @@
 """Deterministic synthetic Euroc-shaped stereo sequences.
 
 Scene: three textured fronto-parallel planes (Z = 1.5, 3, 6 m, nearest first, the two nearer ones
-bounded in world X) observed by the distorted (radial-tangential) stereo rig; texture = random
+bounded in world X) observed by the distorted (radial-tangential or equidistant) stereo rig; texture = random
 Gaussian blobs + band-limited noise; smooth camera motion (small rotation + translation) so that
 features persist and keyframes are triggered by the reference's time / disparity logic; per-frame
 sensor noise.  numpy only.  Used by bench.py (input data of the timed runs) and by the tests.
@@ -55,6 +55,17 @@ def _undistort_grid(cam: CameraParams) -> np.ndarray:
     k1, k2, p1, p2 = cam.distortion[:4]
     u, v = np.meshgrid(np.arange(cam.width, dtype=np.float64), np.arange(cam.height, dtype=np.float64))
     x0, y0 = (u - cx) / fx, (v - cy) / fy
+    if cam.distortion_model == "equidistant":
+        # theta_d = theta (1 + k1 theta^2 + k2 theta^4 + k3 theta^6 + k4 theta^8); Newton on theta, ray = tan(theta) / theta_d
+        td = np.sqrt(x0 * x0 + y0 * y0)
+        th = td.copy()
+        for _ in range(20):
+            t2 = th * th
+            f = th * (1 + t2 * (k1 + t2 * (k2 + t2 * (p1 + t2 * p2)))) - td
+            df = 1 + t2 * (3 * k1 + t2 * (5 * k2 + t2 * (7 * p1 + t2 * 9 * p2)))
+            th = th - f / df
+        sc = np.where(td > 1e-12, np.tan(th) / np.maximum(td, 1e-12), 1.0)
+        return np.stack([x0 * sc, y0 * sc], -1)
     x, y = x0.copy(), y0.copy()
     for _ in range(12):
         r2 = x * x + y * y

@@ -106,11 +106,17 @@ class StereoFrame:
 # a7: sparse undistortion
 # ----------------------------------------------------------------------------------------------
 def undistort_rectify_keypoints(kps, cam: CameraParams, R=None, P=None) -> np.ndarray:
-    """UndistorterRectifier::UndistortRectifyKeypoints (UndistorterRectifier.cpp:33-68), RADTAN."""
+    """UndistorterRectifier::UndistortRectifyKeypoints (UndistorterRectifier.cpp:33-68): cv::undistortPoints for
+    RADTAN (:41-48), cv::fisheye::undistortPoints for EQUIDISTANT (:49-56)."""
     if len(kps) == 0:
         return np.zeros((0, 2), f32)
     pts = np.asarray(kps, f32).reshape(-1, 1, 2)
-    out = cv2.undistortPoints(pts, cam.K, cam.D, R=R, P=P)
+    if cam.distortion_model == "equidistant":
+        out = cv2.fisheye.undistortPoints(pts, cam.K, cam.D, R=R, P=P)
+    elif cam.distortion_model == "radtan":
+        out = cv2.undistortPoints(pts, cam.K, cam.D, R=R, P=P)
+    else:
+        raise NotImplementedError("Unknown distortion model.")      # LOG(FATAL), UndistorterRectifier.cpp:64-66
     return out.reshape(-1, 2)
 
 

@@ -32,8 +32,8 @@ class MonoCamera:
         self.W, self.H = cam.width, cam.height
         self.R1 = np.eye(3)
         self.P1 = np.hstack([cam.K, np.zeros((3, 1))])
-        self.map_lx, self.map_ly = cv2.initUndistortRectifyMap(cam.K, cam.D, np.eye(3, dtype=np.float32), cam.K,
-                                                               (self.W, self.H), cv2.CV_32FC1)
+        init = cv2.fisheye.initUndistortRectifyMap if cam.distortion_model == "equidistant" else cv2.initUndistortRectifyMap
+        self.map_lx, self.map_ly = init(cam.K, cam.D, np.eye(3, dtype=np.float32), cam.K, (self.W, self.H), cv2.CV_32FC1)
 
     def undistort_keypoints(self, kps, pixel_tol: float = 2.0):
         """Camera::undistortKeypoints: undistortPoints(K, D, R = I, P = K) + checkUndistortedRectifiedLeftKeypoints."""

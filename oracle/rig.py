@@ -4,7 +4,8 @@ Row a1 of SURVEY.md section 8(a): the stereo rig, restating
   * StereoCamera::StereoCamera                      src/frontend/StereoCamera.cpp:34-94
   * StereoCamera::computeRectificationParameters    src/frontend/StereoCamera.cpp:292-379
   * UndistorterRectifier::initUndistortRectifyMaps  src/frontend/UndistorterRectifier.cpp:230-292
-with the same OpenCV calls (cv2.stereoRectify, cv2.initUndistortRectifyMap).
+with the same OpenCV calls (cv2.stereoRectify, cv2.initUndistortRectifyMap; their cv2.fisheye counterparts for the
+equidistant distortion model).
 Pinned by tests/testStereoMatcher.cpp:148 (baseline 0.110078 on the Euroc rig).
 """
 from __future__ import annotations
@@ -29,8 +30,12 @@ class StereoRig:
             self.R1, self.R2, self.P1, self.P2, self.Q, self.roi1, self.roi2 = cv2.stereoRectify(
                 left.K, left.D, right.K, right.D, size, R, T,
                 flags=cv2.CALIB_ZERO_DISPARITY, alpha=0)          # kAlpha = 0, StereoCamera.cpp:326
+        elif left.distortion_model == "equidistant":
+            # StereoCamera.cpp:350-373: cv::fisheye::stereoRectify(..., CALIB_ZERO_DISPARITY), no alpha, no ROIs
+            self.R1, self.R2, self.P1, self.P2, self.Q = cv2.fisheye.stereoRectify(
+                left.K, left.D, right.K, right.D, size, R, T, flags=cv2.CALIB_ZERO_DISPARITY)
         else:
-            raise NotImplementedError("only the radtan pinhole model is on the graded path")
+            raise NotImplementedError("Unknown DistortionModel")        # LOG(FATAL), StereoCamera.cpp:370-377
         # baseline = 1 / Q(3,2)  (StereoCamera.cpp:70-72)
         self.baseline = 1.0 / self.Q[3, 2]
         assert self.baseline > 0
@@ -39,8 +44,10 @@ class StereoRig:
         self.skew = self.P1[0, 1]
         self.cx, self.cy = self.P1[0, 2], self.P1[1, 2]
         # float32 maps, CV_32FC1 (UndistorterRectifier.cpp:238-258)
-        self.map_lx, self.map_ly = cv2.initUndistortRectifyMap(left.K, left.D, self.R1, self.P1, size, cv2.CV_32FC1)
-        self.map_rx, self.map_ry = cv2.initUndistortRectifyMap(right.K, right.D, self.R2, self.P2, size, cv2.CV_32FC1)
+        # UndistorterRectifier.cpp:246-268: cv::initUndistortRectifyMap (RADTAN) / cv::fisheye:: (EQUIDISTANT)
+        init = cv2.fisheye.initUndistortRectifyMap if left.distortion_model == "equidistant" else cv2.initUndistortRectifyMap
+        self.map_lx, self.map_ly = init(left.K, left.D, self.R1, self.P1, size, cv2.CV_32FC1)
+        self.map_rx, self.map_ry = init(right.K, right.D, self.R2, self.P2, size, cv2.CV_32FC1)
 
     # UndistorterRectifier::undistortRectifyImage  UndistorterRectifier.cpp:115-128
     def rectify_left(self, img: np.ndarray) -> np.ndarray:
