@@ -270,6 +270,38 @@ int kvfe_remove_outliers_stereo(const int32_t* inliers, int n_inliers, int32_t* 
 /* cv::equalizeHist as UtilsOpenCV::ReadAndConvertToGrayScale applies it (src/utils/UtilsOpenCV.cpp:390-403), one image. */
 int kvfe_equalize_hist(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* out, size_t out_pitch);
 
+/* ---- RGB-D (row f2, stage level): the two functions RgbdVisionImuFrontend adds to the mono / stereo ones ----------
+ * CameraParams::DepthParams (include/kimera-vio/frontend/CameraParams.h:131-155) as parsed by parseDepthParams
+ * (src/frontend/CameraParams.cpp:342-349).  The depth image has the context's width x height; it must already be
+ * registered to the intensity camera (is_registered: cv::rgbd::registerDepth is not built). */
+#define KVFE_DEPTH_U16 0   /* CV_16UC1 */
+#define KVFE_DEPTH_F32 1   /* CV_32FC1 */
+typedef struct {
+  int32_t depth_type;        /* KVFE_DEPTH_U16 / KVFE_DEPTH_F32 */
+  float virtual_baseline;    /* virtual_baseline_ (also the baseline of RgbdCamera::getFakeStereoCamera) */
+  float depth_to_meters;     /* depth_to_meters_ */
+  float min_depth;           /* min_depth_ */
+  float max_depth;           /* max_depth_ */
+} kvfe_depth_params;
+/* DepthFrame::getDetectionMask (src/frontend/DepthFrame.cpp:75-98): cv::inRange(depth, min_depth / depth_to_meters,
+ * max_depth / depth_to_meters) -> 255 / 0 (CV_16UC1: the bounds truncated to uint16, clamped to [0, 65535]); the mask
+ * kvfe_detect_masked takes (RgbdVisionImuFrontend.cpp:196-198, :354-356).  pitch in BYTES. */
+int kvfe_depth_detection_mask(kvfe_ctx* ctx, const void* depth, size_t depth_pitch_bytes, const kvfe_depth_params* dp,
+                              uint8_t* mask, size_t mask_pitch);
+/* RgbdFrame::fillStereoFrame (src/frontend/RgbdFrame.cpp:52-115) for the n keypoints of a frame:
+ *   kp_x/kp_y         left_frame_.keypoints_ (raw pixels; DepthFrame::getDepthAtPoint truncates them, DepthFrame.cpp:39-73)
+ *   left_status/x/y   left_keypoints_rectified_ (Camera::undistortKeypoints == kvfe_undistort_rectify_left_keypoints
+ *                     on a mono rig)
+ *   versors           left_frame_.versors_ (3 doubles each)
+ * out: right_keypoints_rectified_ (status: the left status when it is not VALID, NO_DEPTH for a non-finite depth, a depth
+ * below min_depth or uR < 0), keypoints_depth_, keypoints_3d_ (versor * depth / versor.z) and right_frame_.keypoints_
+ * (RgbdCamera::distortKeypoints, RgbdCamera.cpp:81-85).  fx is K_left's. */
+int kvfe_rgbd_fill_stereo_frame(kvfe_ctx* ctx, const void* depth, size_t depth_pitch_bytes, const kvfe_depth_params* dp,
+                                const float* kp_x, const float* kp_y, const int32_t* left_status, const float* left_x,
+                                const float* left_y, const double* versors, int n, int32_t* right_status, float* right_x,
+                                float* right_y, double* keypoints_depth, double* keypoints_3d, float* right_kp_x,
+                                float* right_kp_y);
+
 /* Mesher::createMesh2dImpl (src/mesh/Mesher.cpp:1712-1817): cv::Subdiv2D(rect(0, 0, width, height)), insert the
  * keypoints that lie inside the image, getTriangleList, keep the triangles with all vertices inside.  triangles:
  * 6 floats each (x0 y0 x1 y1 x2 y2) in cv::Subdiv2D's order; n_triangles may exceed max_triangles (then only the

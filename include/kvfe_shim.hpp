@@ -274,5 +274,38 @@ class StereoMatcher {
   Context c_;
 };
 
+// The RGB-D additions (src/frontend/DepthFrame.cpp, src/frontend/RgbdFrame.cpp): a registered depth image of the context's
+// size, CV_16UC1 or CV_32FC1 as kvfe_depth_params.depth_type says; pitch in bytes
+struct DepthView { const void* data; size_t pitch_bytes; };
+struct RgbdFillResult {
+  std::vector<int32_t> right_status;
+  Keypoints right_rectified, right_keypoints;
+  std::vector<double> depth, points_3d;
+};
+class RgbdFrame {
+ public:
+  RgbdFrame(Context ctx, const kvfe_depth_params& dp) : c_(std::move(ctx)), dp_(dp) {}
+  // DepthFrame::getDetectionMask (DepthFrame.cpp:75-98) -> Frame::detection_mask_ for FeatureDetector::featureDetection
+  void getDetectionMask(const DepthView& depth, MutableImage* mask) const {
+    c_.check(kvfe_depth_detection_mask(c_.get(), depth.data, depth.pitch_bytes, &dp_, mask->data, mask->pitch), "getDetectionMask");
+  }
+  // RgbdFrame::fillStereoFrame (RgbdFrame.cpp:52-115): the hallucinated right half of the StereoFrame
+  RgbdFillResult fillStereoFrame(const DepthView& depth, const Keypoints& left_kps, const std::vector<int32_t>& left_status,
+                                 const Keypoints& left_rect, const std::vector<double>& versors) const {
+    const size_t n = left_kps.size();
+    RgbdFillResult r;
+    r.right_status.resize(n); r.depth.resize(n); r.points_3d.resize(3 * n);
+    for (Keypoints* k : {&r.right_rectified, &r.right_keypoints}) { k->x.resize(n); k->y.resize(n); }
+    c_.check(kvfe_rgbd_fill_stereo_frame(c_.get(), depth.data, depth.pitch_bytes, &dp_, left_kps.x.data(), left_kps.y.data(),
+                                         left_status.data(), left_rect.x.data(), left_rect.y.data(), versors.data(), (int)n,
+                                         r.right_status.data(), r.right_rectified.x.data(), r.right_rectified.y.data(), r.depth.data(),
+                                         r.points_3d.data(), r.right_keypoints.x.data(), r.right_keypoints.y.data()), "fillStereoFrame");
+    return r;
+  }
+ private:
+  Context c_;
+  kvfe_depth_params dp_;
+};
+
 }  // namespace kvfe
 #endif  // KVFE_SHIM_HPP_

@@ -12,7 +12,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "libkvfe.so")
 OBJ = os.path.join(HERE, "build")
-SOURCES = ["api.cu", "pipeline.cu", "rectify.cu", "pyramid.cu", "lk.cu", "gftt.cu", "select.cu", "stereo.cu", "ransac.cu", "fsm.cu", "mesh.cu", "ingest.cu"]
+SOURCES = ["api.cu", "pipeline.cu", "rectify.cu", "pyramid.cu", "lk.cu", "gftt.cu", "select.cu", "stereo.cu", "ransac.cu", "fsm.cu", "mesh.cu", "ingest.cu", "rgbd.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",
          "-fmad=false",                       # IEEE op-by-op arithmetic; FMAs only where written

@@ -864,6 +864,96 @@ extern "C" int kvfe_distort_unrectify_keypoints(kvfe_ctx* ctx, int cam, const in
   return KVFE_OK;
 }
 
+// ---- RGB-D, stage level (rgbd.cu) ---------------------------------------------------------------------------------
+static int check_depth_params(kvfe_ctx* ctx, const kvfe_depth_params* dp) {
+  if (dp->depth_type != KVFE_DEPTH_U16 && dp->depth_type != KVFE_DEPTH_F32)
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "depth_type must be KVFE_DEPTH_U16 or KVFE_DEPTH_F32");
+  if (!(dp->virtual_baseline > 0.f)) return set_err(ctx, KVFE_ERR_INVALID_ARG, "virtual_baseline must be positive");   // CameraParams.cpp:344
+  return KVFE_OK;
+}
+
+// depth image (W x H, u16 or f32) to the device, densely packed
+static int upload_depth(kvfe_ctx* ctx, const void* depth, size_t pitch_bytes, int depth_type, unsigned char** out, size_t* row_bytes) {
+  const size_t es = depth_type == KVFE_DEPTH_F32 ? 4 : 2;
+  *row_bytes = (size_t)ctx->dc.W * es;
+  if (pitch_bytes < *row_bytes) return set_err(ctx, KVFE_ERR_INVALID_ARG, "depth pitch %zu smaller than a row (%zu bytes)", pitch_bytes, *row_bytes);
+  CU(cudaMalloc((void**)out, *row_bytes * ctx->dc.H));
+  cudaError_t e = cudaMemcpy2DAsync(*out, *row_bytes, depth, pitch_bytes, *row_bytes, ctx->dc.H, cudaMemcpyHostToDevice, ctx->stream);
+  if (e != cudaSuccess) { cudaFree(*out); *out = nullptr; return set_err(ctx, KVFE_ERR_CUDA, "depth upload: %s", cudaGetErrorString(e)); }
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_depth_detection_mask(kvfe_ctx* ctx, const void* depth, size_t depth_pitch_bytes, const kvfe_depth_params* dp,
+                                         uint8_t* mask, size_t mask_pitch) {
+  if (!ctx || !depth || !dp || !mask) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  RET(check_depth_params(ctx, dp));
+  if (mask_pitch < (size_t)ctx->dc.W) return set_err(ctx, KVFE_ERR_INVALID_ARG, "mask pitch smaller than the width");
+  // DepthFrame.cpp:76-77: float arithmetic
+  const float lo = dp->min_depth * 1.0f / dp->depth_to_meters, hi = dp->max_depth * 1.0f / dp->depth_to_meters;
+  auto to_u16 = [](float v) -> unsigned int { return !(v > 0.f) ? 0u : (v >= 65535.f ? 65535u : (unsigned int)v); };
+  unsigned char* d_depth = nullptr; size_t rb = 0;
+  RET(upload_depth(ctx, depth, depth_pitch_bytes, dp->depth_type, &d_depth, &rb));
+  StageScratch m;
+  cudaError_t e = m.alloc((size_t)ctx->dc.W * ctx->dc.H);
+  if (e == cudaSuccess) {
+    ctx->launches += launch_depth_mask(ctx->dc, d_depth, rb, dp->depth_type, lo, hi, to_u16(lo), to_u16(hi), m.p, ctx->dc.W, ctx->stream);
+    e = cudaGetLastError();
+  }
+  if (e == cudaSuccess) e = cudaMemcpy2DAsync(mask, mask_pitch, m.p, ctx->dc.W, ctx->dc.W, ctx->dc.H, cudaMemcpyDeviceToHost, ctx->stream);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  cudaFree(d_depth);
+  if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "kvfe_depth_detection_mask: %s", cudaGetErrorString(e));
+  return KVFE_OK;
+}
+
+extern "C" int kvfe_rgbd_fill_stereo_frame(kvfe_ctx* ctx, const void* depth, size_t depth_pitch_bytes, const kvfe_depth_params* dp,
+                                           const float* kp_x, const float* kp_y, const int32_t* left_status, const float* left_x,
+                                           const float* left_y, const double* versors, int n, int32_t* right_status, float* right_x,
+                                           float* right_y, double* keypoints_depth, double* keypoints_3d, float* right_kp_x,
+                                           float* right_kp_y) {
+  if (!ctx || !depth || !dp) return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  RET(check_depth_params(ctx, dp));
+  if (n <= 0) return KVFE_OK;                         // "no features": every output stays empty (testRgbdFrame.cpp:108-117)
+  if (!kp_x || !kp_y || !left_status || !left_x || !left_y || !versors || !right_status || !right_x || !right_y || !keypoints_depth ||
+      !keypoints_3d || !right_kp_x || !right_kp_y)
+    return set_err(ctx, KVFE_ERR_INVALID_ARG, "null argument");
+  unsigned char* d_depth = nullptr; size_t rb = 0;
+  RET(upload_depth(ctx, depth, depth_pitch_bytes, dp->depth_type, &d_depth, &rb));
+  // doubles first (8-byte alignment): versors 3n | depth n | p3d 3n ; then 4-byte arrays: 4 in f32 + status in, 5 out
+  StageScratch d;
+  const size_t N = (size_t)n;
+  cudaError_t e = d.alloc(7 * N * 8 + 10 * N * 4);
+  if (e != cudaSuccess) { cudaFree(d_depth); return set_err(ctx, KVFE_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e)); }
+  double* dv = reinterpret_cast<double*>(d.p);
+  double* dd = dv + 3 * N;
+  double* dp3 = dd + N;
+  float* f = reinterpret_cast<float*>(dp3 + 3 * N);
+  float *d_kx = f, *d_ky = f + N, *d_lx = f + 2 * N, *d_ly = f + 3 * N;
+  int* d_ls = reinterpret_cast<int*>(f + 4 * N);
+  int* d_rs = reinterpret_cast<int*>(f + 5 * N);
+  float *d_rx = f + 6 * N, *d_ry = f + 7 * N, *d_rkx = f + 8 * N, *d_rky = f + 9 * N;
+  cudaStream_t s = ctx->stream;
+  const struct { void* dst; const void* src; size_t bytes; } ups[] = {
+      {dv, versors, 3 * N * 8}, {d_kx, kp_x, N * 4}, {d_ky, kp_y, N * 4}, {d_lx, left_x, N * 4}, {d_ly, left_y, N * 4}, {d_ls, left_status, N * 4}};
+  for (const auto& u : ups)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyHostToDevice, s);
+  if (e == cudaSuccess) {
+    const double fx_b = ctx->cam[0].fx * (double)dp->virtual_baseline;        // RgbdFrame.cpp:66
+    ctx->launches += launch_rgbd_fill(ctx->dc, ctx->d_cam, d_depth, rb, dp->depth_type, dp->depth_to_meters, dp->min_depth, fx_b, d_kx, d_ky,
+                                      d_ls, d_lx, d_ly, dv, n, d_rs, d_rx, d_ry, dd, dp3, d_rkx, d_rky, s);
+    e = cudaGetLastError();
+  }
+  const struct { void* dst; const void* src; size_t bytes; } downs[] = {
+      {right_status, d_rs, N * 4}, {right_x, d_rx, N * 4}, {right_y, d_ry, N * 4}, {keypoints_depth, dd, N * 8},
+      {keypoints_3d, dp3, 3 * N * 8}, {right_kp_x, d_rkx, N * 4}, {right_kp_y, d_rky, N * 4}};
+  for (const auto& u : downs)
+    if (e == cudaSuccess) e = cudaMemcpyAsync(u.dst, u.src, u.bytes, cudaMemcpyDeviceToHost, s);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(s);
+  cudaFree(d_depth);
+  if (e != cudaSuccess) return set_err(ctx, KVFE_ERR_CUDA, "kvfe_rgbd_fill_stereo_frame: %s", cudaGetErrorString(e));
+  return KVFE_OK;
+}
+
 // the frame-level stereo kernels work on frame slot 0 of stream 0: a stage call fills the fields a kernel reads
 static int stage_frame_begin(kvfe_ctx* ctx, int n) {
   if (n > ctx->dc.cap) return set_err(ctx, KVFE_ERR_CAPACITY, "n %d exceeds capacity %d", n, ctx->dc.cap);

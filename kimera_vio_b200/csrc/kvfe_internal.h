@@ -296,6 +296,13 @@ int launch_reset(const DevCfg& dc, const DevBuf& db, cudaStream_t s);
 // ingest.cu
 int launch_equalize(const DevCfg& dc, unsigned char* imgs, size_t img_stride, int nimg, const StreamState* st, int mode_mask,
                     cudaStream_t s);
+// rgbd.cu
+int launch_depth_mask(const DevCfg& dc, const unsigned char* depth, size_t pitch_bytes, int depth_type, float lo, float hi,
+                      unsigned int lo16, unsigned int hi16, unsigned char* mask, size_t mask_pitch, cudaStream_t s);
+int launch_rgbd_fill(const DevCfg& dc, const CamModel* d_cam, const unsigned char* depth, size_t pitch_bytes, int depth_type,
+                     float depth_to_meters, float min_depth, double fx_b, const float* kp_x, const float* kp_y, const int* left_status,
+                     const float* left_x, const float* left_y, const double* versors, int n, int* right_status, float* right_x,
+                     float* right_y, double* depth_out, double* p3d, float* right_kp_x, float* right_kp_y, cudaStream_t s);
 // mesh.cu
 bool mesh_fits_smem(const DevCfg& dc);
 size_t mesh_global_ws_ints(const DevCfg& dc);

@@ -76,6 +76,21 @@ class Rig(C.Structure):
                 ("baseline", C.c_double), ("distortion_model", C.c_int32), ("reserved", C.c_int32)]
 
 
+class DepthParams(C.Structure):
+    """kvfe_depth_params == CameraParams::DepthParams (include/kimera-vio/frontend/CameraParams.h:131-155)."""
+    _fields_ = [("depth_type", C.c_int32), ("virtual_baseline", C.c_float), ("depth_to_meters", C.c_float),
+                ("min_depth", C.c_float), ("max_depth", C.c_float)]
+
+
+def make_depth_params(depth_dtype, virtual_baseline=1.0e-2, depth_to_meters=1.0, min_depth=0.0, max_depth=10.0) -> DepthParams:
+    """Defaults are the struct defaults of the reference (CameraParams.h:136-145)."""
+    dt = np.dtype(depth_dtype)
+    if dt not in (np.dtype(np.uint16), np.dtype(np.float32)):
+        raise ValueError("depth images are CV_16UC1 or CV_32FC1 (DepthFrame.cpp:29)")
+    return DepthParams(1 if dt == np.dtype(np.float32) else 0, float(virtual_baseline), float(depth_to_meters), float(min_depth),
+                       float(max_depth))
+
+
 class PacketHeader(C.Structure):
     _fields_ = [("n", C.c_int32), ("is_keyframe", C.c_int32), ("mono_status", C.c_int32),
                 ("stereo_status", C.c_int32), ("n_smart", C.c_int32), ("nr_tracked", C.c_int32),
@@ -413,6 +428,28 @@ class Context:
         out = np.empty_like(a)
         self._chk(self.lib.kvfe_equalize_hist(self.h, _p(a), C.c_size_t(a.shape[1]), _p(out), C.c_size_t(a.shape[1])))
         return out
+
+    def depth_detection_mask(self, depth: np.ndarray, dp: DepthParams) -> np.ndarray:
+        d = np.ascontiguousarray(depth)
+        mask = np.empty(d.shape, np.uint8)
+        self._chk(self.lib.kvfe_depth_detection_mask(self.h, _p(d), C.c_size_t(d.strides[0]), C.byref(dp), _p(mask), C.c_size_t(mask.shape[1])))
+        return mask
+
+    def rgbd_fill_stereo_frame(self, depth: np.ndarray, dp: DepthParams, kps_xy, left_status, left_xy, versors):
+        """RgbdFrame::fillStereoFrame: returns (right_status, right_xy, keypoints_depth, keypoints_3d, right_keypoints)."""
+        d = np.ascontiguousarray(depth)
+        k = np.ascontiguousarray(kps_xy, np.float32).reshape(-1, 2)
+        l = np.ascontiguousarray(left_xy, np.float32).reshape(-1, 2)
+        st = np.ascontiguousarray(left_status, np.int32)
+        v = np.ascontiguousarray(versors, np.float64).reshape(-1, 3)
+        n = len(k)
+        assert len(l) == n and len(st) == n and len(v) == n
+        kx, ky, lx, ly = (np.ascontiguousarray(a) for a in (k[:, 0], k[:, 1], l[:, 0], l[:, 1]))
+        rs, rx, ry = np.zeros(n, np.int32), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        dep, p3, rkx, rky = np.zeros(n), np.zeros((n, 3)), np.zeros(n, np.float32), np.zeros(n, np.float32)
+        self._chk(self.lib.kvfe_rgbd_fill_stereo_frame(self.h, _p(d), C.c_size_t(d.strides[0]), C.byref(dp), _p(kx), _p(ky), _p(st), _p(lx),
+                                                       _p(ly), _p(v), n, _p(rs), _p(rx), _p(ry), _p(dep), _p(p3), _p(rkx), _p(rky)))
+        return rs, np.stack([rx, ry], 1), dep, p3, np.stack([rkx, rky], 1)
 
     def mesh_2d(self, kps_xy):
         xy = np.asarray(kps_xy, np.float32).reshape(-1, 2)

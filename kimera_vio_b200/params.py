@@ -205,13 +205,16 @@ class FrontendParams:
 
 @dataclass
 class CameraParams:
-    """Pinhole + radial-tangential camera (CameraParams.cpp:30-120). T_BS is body_Pose_cam."""
+    """Pinhole camera with radial-tangential or equidistant distortion (CameraParams.cpp:30-140). T_BS is body_Pose_cam.
+    `depth`: the RGB-D block (CameraParams.cpp:342-349, parsed when the YAML carries `virtual_baseline`): a dict with
+    virtual_baseline, depth_to_meters, min_depth, max_depth (float32 values, like the reference's struct) and is_registered."""
     width: int
     height: int
     intrinsics: List[float]            # fu, fv, cu, cv
-    distortion: List[float]            # k1, k2, p1, p2 (radtan)
+    distortion: List[float]            # k1, k2, p1, p2 (radtan) / k1..k4 (equidistant)
     T_BS: np.ndarray = field(default_factory=lambda: np.eye(4))
     distortion_model: str = "radtan"
+    depth: Optional[dict] = None
 
     @property
     def K(self) -> np.ndarray:
@@ -232,8 +235,17 @@ class CameraParams:
             dm = "radtan"
         elif dm in ("none",):
             dm = "none"
+        depth = None
+        if "virtual_baseline" in y:
+            depth = {"virtual_baseline": float(np.float32(y["virtual_baseline"])),
+                     "depth_to_meters": float(np.float32(y.get("depth_to_meters", 1.0))),
+                     "min_depth": float(np.float32(y.get("min_depth", 0.0))),
+                     "max_depth": float(np.float32(y.get("max_depth", 10.0))),
+                     "is_registered": bool(int(y.get("is_registered", 1)))}
+            if not depth["virtual_baseline"] > 0:
+                raise ValueError("Baseline must be positive")            # CHECK_GT, CameraParams.cpp:344
         return CameraParams(int(res[0]), int(res[1]), [float(v) for v in y["intrinsics"]],
-                            [float(v) for v in y["distortion_coefficients"]], T, dm)
+                            [float(v) for v in y["distortion_coefficients"]], T, dm, depth)
 
     @staticmethod
     def euroc_left() -> "CameraParams":

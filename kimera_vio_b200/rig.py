@@ -52,3 +52,15 @@ class MonoRigSetup:
 
     def to_c(self) -> "_lib.Rig":
         return _lib.make_rig(self.left, self.right, self.R1, self.R2, self.P1, self.P2, self.baseline)
+
+
+class RgbdRigSetup(MonoRigSetup):
+    """RgbdCamera (reference src/frontend/RgbdCamera.cpp:79-101): the mono camera (P = K, R = I) plus the fake stereo
+    camera of getFakeStereoCamera -- Cal3_S2Stereo(K, virtual_baseline) at the identity pose -- which the stereo outlier
+    rejection of the RGB-D front-end runs on (RgbdVisionImuFrontend.cpp:325-336)."""
+
+    def __init__(self, cam: CameraParams):
+        super().__init__(cam)
+        if not cam.depth:
+            raise ValueError("camera parameters without the RGB-D block (virtual_baseline, ...)")
+        self.baseline = float(cam.depth["virtual_baseline"])

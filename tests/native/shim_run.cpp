@@ -104,6 +104,19 @@ int main(int argc, char** argv) {
     dump("ransac3_status", std::vector<int32_t>{r3.status}); dump("ransac3_inliers", r3.inliers);
     kvfe::RansacResult r1 = tr.geometricOutlierRejection3d3dGivenRotation(lxy, rxy, lxy, rxy, p3v, p3v, I3);
     dump("ransac1_status", std::vector<int32_t>{r1.status}); dump("ransac1_inliers", r1.inliers);
+    // RGB-D additions: a synthetic CV_16UC1 depth image in millimetres, derived from the left image
+    std::vector<uint16_t> depth16(L.size());
+    for (size_t i = 0; i < L.size(); ++i) depth16[i] = (uint16_t)(500 + 20 * (int)L[i]);
+    const kvfe_depth_params dpar{KVFE_DEPTH_U16, 0.1f, 0.001f, 2.0f, 4.0f};
+    kvfe::RgbdFrame rg(c, dpar);
+    const kvfe::DepthView dv{depth16.data(), (size_t)W * 2};
+    std::vector<uint8_t> dmask(L.size());
+    kvfe::MutableImage mm{dmask.data(), W, H, (size_t)W};
+    rg.getDetectionMask(dv, &mm);
+    dump("depth_mask", dmask);
+    kvfe::RgbdFillResult fill = rg.fillStereoFrame(dv, kps, lstat, lrect, versors);
+    dump("fill_right_status", fill.right_status); dump("fill_right_rect", fill.right_rectified); dump("fill_depth", fill.depth);
+    dump("fill_points", fill.points_3d); dump("fill_right_kps", fill.right_keypoints);
     // host bookkeeping
     dump("outliers", kvfe::Tracker::findOutliers((int)mref.size(), r2.inliers));
     std::vector<int64_t> lr(kps.size()), lc(kps.size());

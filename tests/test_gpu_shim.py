@@ -88,6 +88,15 @@ def test_shim_methods_with_data(tmp_path):
     v2 = ctx.bearing_vectors(trk)
     st2, _, inl2 = ctx.ransac_mono(vers[m], v2[m], np.eye(3))
     assert int(arr("ransac2_status", np.int32)[0]) == st2 and list(arr("ransac2_inliers", np.int32)) == inl2
+    # the RGB-D additions (RgbdFrame in the shim)
+    depth16 = (500 + 20 * L.astype(np.int32)).astype(np.uint16)
+    dpar = kl.DepthParams(0, 0.1, 0.001, 2.0, 4.0)
+    dmask = ctx.depth_detection_mask(depth16, dpar)
+    assert np.array_equal(arr("depth_mask", np.uint8).reshape(L.shape), dmask) and 0 < dmask.mean() < 255
+    frs, frx, fdep, fp3, frk = ctx.rgbd_fill_stereo_frame(depth16, dpar, kps, lst, lrect, vers)
+    assert np.array_equal(arr("fill_right_status", np.int32), frs) and np.array_equal(xy("fill_right_rect"), frx)
+    assert np.array_equal(arr("fill_depth", np.float64), fdep) and np.array_equal(arr("fill_points", np.float64).reshape(-1, 3), fp3)
+    assert np.array_equal(xy("fill_right_kps"), frk) and (frs == 0).sum() > 20 and (frs == 3).sum() > 0
     ctx.close()
     for name in ("ransac5_status", "ransac3_inliers", "ransac1_inliers", "outliers", "lmk_ref_after", "matches_after", "ss_right_kps.x"):
         assert name in b
