@@ -92,9 +92,9 @@ def _compare_fill(tag, ctx, depth, d, dp, cam, mono, kps, left, versors):
     H.diag("rgbd_fill", **rec)
     assert rec["status_mismatches"] == 0 and rec["right_mismatches"] == 0 and rec["depth_mismatches"] == 0
     assert rec["p3d_mismatches"] == 0
-    # right_frame_.keypoints_ are raw map values: exact except where the map crosses zero (column 0 / row 0 of a
-    # zero-distortion camera), where OpenCV's fused operations leave a residue of 1e-14 px
-    assert rec["right_kp_max_err"] <= 1e-3 and rec["right_kp_mismatches"] <= 2
+    # right_frame_.keypoints_ are raw map values, incl. column 0 / row 0 of this zero-distortion camera where the map is a
+    # residue of 1e-14 px that only OpenCV's fused operation order reproduces (common.cuh: rect_map_at, tests/test_oracle_maps.py)
+    assert rec["right_kp_mismatches"] == 0
     return rec
 
 
