@@ -85,3 +85,15 @@ def test_distort_unrectify_keypoints_reference_camera():
         assert abs(g[0] - ex) < 1e-3 and abs(g[1] - ey) < 1e-3, ((x, y), g, (ex, ey))
         n_checked += 1
     assert n_checked >= 30
+
+
+def test_get_bearing_vector_grid_reference():
+    """tests/testFrame.cpp:101-139 (sensor.yaml == the Euroc left camera): GetBearingVector has unit norm and, distorted
+    again with Cal3DS2::uncalibrate, lands within 0.5 px of the pixel it came from, on an 8 x 8 grid over 752 x 480."""
+    from kimera_vio_b200.params import CameraParams
+    cam = CameraParams.euroc_left()
+    pts = [(np.float32(c * 752 // 7), np.float32(r * 480 // 7)) for r in range(8) for c in range(8)]
+    for (px, py), v in zip(pts, ofe.get_bearing_vectors(pts, cam, None)):
+        assert abs(np.linalg.norm(v) - 1.0) < 4e-16
+        ex, ey = _cal3ds2_uncalibrate(cam, v[0] / v[2], v[1] / v[2])
+        assert np.hypot(ex - float(px), ey - float(py)) < 0.5
