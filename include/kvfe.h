@@ -267,6 +267,24 @@ int kvfe_remove_outliers_stereo(const int32_t* inliers, int n_inliers, int32_t* 
                                 double* ref_points_3d, int n_ref, int32_t* cur_right_status, double* cur_depth,
                                 double* cur_points_3d, int n_cur, int32_t* match_ref, int32_t* match_cur, int* n_matches);
 
+/* Tracker::findMatchingKeypoints (include/kimera-vio/frontend/Tracker.h:195, src/frontend/Tracker.cpp:919-946): pairs
+ * (ref index, cur index) observing the same landmark, in current-frame order.  Host bookkeeping (no ctx), like the
+ * reference's; match arrays sized n_cur. */
+int kvfe_find_matching_keypoints(const int64_t* ref_landmarks, int n_ref, const int64_t* cur_landmarks, int n_cur,
+                                 int32_t* match_ref, int32_t* match_cur, int* n_matches);
+/* Tracker::findMatchingStereoKeypoints (Tracker.h:199-208, Tracker.cpp:948-989): the mono matches with a VALID right
+ * keypoint in both frames. */
+int kvfe_find_matching_stereo_keypoints(const int32_t* ref_right_status, int n_ref, const int32_t* cur_right_status, int n_cur,
+                                        const int32_t* mono_match_ref, const int32_t* mono_match_cur, int n_mono,
+                                        int32_t* match_ref, int32_t* match_cur, int* n_matches);
+/* StereoVisionImuFrontend::getSmartStereoMeasurements (src/frontend/StereoVisionImuFrontend.cpp:485-531; use_right =
+ * use_stereo_tracking_) / RgbdVisionImuFrontend::fillSmartStereoMeasurements (src/frontend/RgbdVisionImuFrontend.cpp:
+ * 368-395; use_right = 1): (landmark, uL, uR, v) per keypoint with a landmark; uR = NaN without a VALID right keypoint.
+ * Output arrays sized n.  (The frame-level step assembles the same list in the packet: smart_* arrays.) */
+int kvfe_smart_stereo_measurements(const int64_t* landmarks, const float* left_x, const float* left_y,
+                                   const int32_t* right_status, const float* right_x, int n, int use_right,
+                                   int64_t* out_landmarks, double* out_uL, double* out_uR, double* out_v, int* n_out);
+
 /* cv::equalizeHist as UtilsOpenCV::ReadAndConvertToGrayScale applies it (src/utils/UtilsOpenCV.cpp:390-403), one image. */
 int kvfe_equalize_hist(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* out, size_t out_pitch);
 

@@ -204,6 +204,25 @@ class Tracker {
     c_.check(kvfe_point3_and_covariance(c_.get(), left_rect.x.data(), right_rect.x.data(), left_rect.y.data(), points_3d.data(), (int)n,
                                         Rmat, points->data(), covariances->data()), "getPoint3AndCovariance");
   }
+  // findMatchingKeypoints :919-946 (landmark vectors of the two frames -> index pairs)
+  static void findMatchingKeypoints(const std::vector<int64_t>& ref_landmarks, const std::vector<int64_t>& cur_landmarks,
+                                    std::vector<int32_t>* match_ref, std::vector<int32_t>* match_cur) {
+    match_ref->assign(cur_landmarks.size() + 1, 0); match_cur->assign(cur_landmarks.size() + 1, 0);
+    int nm = 0;
+    if (kvfe_find_matching_keypoints(ref_landmarks.data(), (int)ref_landmarks.size(), cur_landmarks.data(), (int)cur_landmarks.size(),
+                                     match_ref->data(), match_cur->data(), &nm) != KVFE_OK) throw Error(KVFE_ERR_INVALID_ARG, "findMatchingKeypoints");
+    match_ref->resize(nm); match_cur->resize(nm);
+  }
+  // findMatchingStereoKeypoints :948-989 (keeps the mono matches whose right keypoints are VALID in both frames)
+  static void findMatchingStereoKeypoints(const std::vector<int32_t>& ref_right_status, const std::vector<int32_t>& cur_right_status,
+                                          std::vector<int32_t>* match_ref, std::vector<int32_t>* match_cur) {
+    int nm = 0;
+    if (kvfe_find_matching_stereo_keypoints(ref_right_status.data(), (int)ref_right_status.size(), cur_right_status.data(),
+                                            (int)cur_right_status.size(), match_ref->data(), match_cur->data(), (int)match_ref->size(),
+                                            match_ref->data(), match_cur->data(), &nm) != KVFE_OK)
+      throw Error(KVFE_ERR_INVALID_ARG, "findMatchingStereoKeypoints");
+    match_ref->resize(nm); match_cur->resize(nm);
+  }
   // findOutliers :836-853
   static std::vector<int32_t> findOutliers(int n_matches, const std::vector<int32_t>& inliers) {
     std::vector<int32_t> out(n_matches > 0 ? n_matches : 1);

@@ -9,6 +9,8 @@
 #include <cstring>
 #include <numeric>
 #include <random>
+#include <map>
+#include <limits>
 #include <vector>
 
 #include <cuda.h>           // CUtensorMap types only: the encoder is resolved through the runtime, libcuda is not linked
@@ -1076,6 +1078,62 @@ extern "C" int kvfe_point3_and_covariance(kvfe_ctx* ctx, const float* left_x, co
   CU(cudaMemcpyAsync(out_points, dop, pbytes, cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaMemcpyAsync(out_cov, dcov, 9 * (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, ctx->stream));
   CU(cudaStreamSynchronize(ctx->stream));
+  return KVFE_OK;
+}
+
+// Tracker::findMatchingKeypoints (Tracker.cpp:919-946): (ref index, cur index) of the keypoints that observe the same
+// landmark, in the order of the current frame; a landmark id seen twice in the reference frame resolves to its last
+// position (std::map assignment).  Host logic, as in the reference (the frame-level step does it on the device:
+// matches.cuh).  match_ref / match_cur must hold n_cur entries.
+extern "C" int kvfe_find_matching_keypoints(const int64_t* ref_landmarks, int n_ref, const int64_t* cur_landmarks, int n_cur,
+                                            int32_t* match_ref, int32_t* match_cur, int* n_matches) {
+  if (n_ref < 0 || n_cur < 0 || (n_ref > 0 && !ref_landmarks) || (n_cur > 0 && (!cur_landmarks || !match_ref || !match_cur)) || !n_matches)
+    return KVFE_ERR_INVALID_ARG;
+  std::map<int64_t, int32_t> ref_index;
+  for (int i = 0; i < n_ref; ++i) if (ref_landmarks[i] != -1) ref_index[ref_landmarks[i]] = i;
+  int m = 0;
+  for (int i = 0; i < n_cur; ++i) {
+    if (cur_landmarks[i] == -1) continue;
+    auto it = ref_index.find(cur_landmarks[i]);
+    if (it != ref_index.end()) { match_ref[m] = it->second; match_cur[m] = i; ++m; }
+  }
+  *n_matches = m;
+  return KVFE_OK;
+}
+// Tracker::findMatchingStereoKeypoints (Tracker.cpp:948-989): the mono matches whose right keypoints are VALID in both
+// frames.  match_ref / match_cur may alias the inputs.
+extern "C" int kvfe_find_matching_stereo_keypoints(const int32_t* ref_right_status, int n_ref, const int32_t* cur_right_status, int n_cur,
+                                                   const int32_t* mono_match_ref, const int32_t* mono_match_cur, int n_mono,
+                                                   int32_t* match_ref, int32_t* match_cur, int* n_matches) {
+  if (n_mono < 0 || !n_matches || (n_mono > 0 && (!ref_right_status || !cur_right_status || !mono_match_ref || !mono_match_cur || !match_ref || !match_cur)))
+    return KVFE_ERR_INVALID_ARG;
+  int m = 0;
+  for (int i = 0; i < n_mono; ++i) {
+    const int ir = mono_match_ref[i], ic = mono_match_cur[i];
+    if (ir < 0 || ir >= n_ref || ic < 0 || ic >= n_cur) return KVFE_ERR_INVALID_ARG;
+    if (ref_right_status[ir] == KVFE_KP_VALID && cur_right_status[ic] == KVFE_KP_VALID) { match_ref[m] = ir; match_cur[m] = ic; ++m; }
+  }
+  *n_matches = m;
+  return KVFE_OK;
+}
+// StereoVisionImuFrontend::getSmartStereoMeasurements (StereoVisionImuFrontend.cpp:485-531; use_right =
+// use_stereo_tracking_) and RgbdVisionImuFrontend::fillSmartStereoMeasurements (RgbdVisionImuFrontend.cpp:368-395;
+// use_right = 1): one (landmark, uL, uR, v) per keypoint with a landmark, uR = NaN unless the right keypoint is VALID.
+extern "C" int kvfe_smart_stereo_measurements(const int64_t* landmarks, const float* left_x, const float* left_y,
+                                              const int32_t* right_status, const float* right_x, int n, int use_right,
+                                              int64_t* out_landmarks, double* out_uL, double* out_uR, double* out_v, int* n_out) {
+  if (n < 0 || !n_out || (n > 0 && (!landmarks || !left_x || !left_y || !right_status || !right_x || !out_landmarks || !out_uL || !out_uR || !out_v)))
+    return KVFE_ERR_INVALID_ARG;
+  int m = 0;
+  for (int i = 0; i < n; ++i) {
+    if (landmarks[i] == -1) continue;
+    out_landmarks[m] = landmarks[i];
+    out_uL[m] = (double)left_x[i];
+    out_v[m] = (double)left_y[i];
+    out_uR[m] = (use_right && right_status[i] == KVFE_KP_VALID) ? (double)right_x[i] : std::numeric_limits<double>::quiet_NaN();
+    ++m;
+  }
+  *n_out = m;
   return KVFE_OK;
 }
 

@@ -121,6 +121,13 @@ int main(int argc, char** argv) {
     dump("outliers", kvfe::Tracker::findOutliers((int)mref.size(), r2.inliers));
     std::vector<int64_t> lr(kps.size()), lc(kps.size());
     for (size_t i = 0; i < kps.size(); ++i) { lr[i] = (int64_t)i; lc[i] = (int64_t)i; }
+    std::vector<int32_t> fm_ref, fm_cur;
+    std::vector<int64_t> lc2 = lc;
+    for (size_t i = 0; i < lc2.size(); i += 3) lc2[i] = -1;             // every third keypoint lost its landmark
+    kvfe::Tracker::findMatchingKeypoints(lr, lc2, &fm_ref, &fm_cur);
+    dump("find_matches_ref", fm_ref);
+    kvfe::Tracker::findMatchingStereoKeypoints(s.right_status, s.right_status, &fm_ref, &fm_cur);
+    dump("find_stereo_matches_ref", fm_ref); dump("find_stereo_matches_cur", fm_cur);
     kvfe::Tracker::removeOutliersMono(r2.inliers, &lr, &lc, &mref, &mcur);
     dump("lmk_ref_after", lr); dump("matches_after", mref);
   } catch (const kvfe::Error& e) {

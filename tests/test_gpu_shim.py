@@ -97,6 +97,12 @@ def test_shim_methods_with_data(tmp_path):
     assert np.array_equal(arr("fill_right_status", np.int32), frs) and np.array_equal(xy("fill_right_rect"), frx)
     assert np.array_equal(arr("fill_depth", np.float64), fdep) and np.array_equal(arr("fill_points", np.float64).reshape(-1, 3), fp3)
     assert np.array_equal(xy("fill_right_kps"), frk) and (frs == 0).sum() > 20 and (frs == 3).sum() > 0
+    # host bookkeeping added to the Tracker shim: findMatchingKeypoints / findMatchingStereoKeypoints
+    n_k = len(kps)
+    want = [i for i in range(n_k) if i % 3 != 0]
+    assert list(arr("find_matches_ref", np.int32)) == want
+    wants = [i for i in want if ss["right_status"][i] == 0]
+    assert list(arr("find_stereo_matches_ref", np.int32)) == wants and list(arr("find_stereo_matches_cur", np.int32)) == wants
     ctx.close()
     for name in ("ransac5_status", "ransac3_inliers", "ransac1_inliers", "outliers", "lmk_ref_after", "matches_after", "ss_right_kps.x"):
         assert name in b

@@ -193,3 +193,60 @@ def test_find_and_remove_outliers_host_logic():
         assert sorted(np.nonzero(cd == 0)[0]) == sorted(int(mc[o]) for o in outl)
         assert all((rp[mr[o]] == 0).all() and (cp[mc[o]] == 0).all() for o in outl)
         assert nm.value == n_inl and np.array_equal(mr3[:n_inl], emr)
+
+
+def test_find_matching_and_smart_measurements_host_logic():
+    """kvfe_find_matching_keypoints / _stereo_keypoints (Tracker.cpp:919-989) and kvfe_smart_stereo_measurements
+    (StereoVisionImuFrontend.cpp:485-531, RgbdVisionImuFrontend.cpp:368-395): host bookkeeping, no GPU; against the oracle,
+    incl. the reference's own fillSmartStereoMeasurements scenario (tests/testRgbdVisionImuFrontend.cpp:140-230: 12 valid,
+    12 without a right keypoint, 12 without a landmark -> 24 measurements, uR NaN where the right keypoint is missing)."""
+    import ctypes as C
+    from types import SimpleNamespace as NS
+    from kimera_vio_b200 import lib as kl
+    from oracle import frontend as ofe
+    lib = kl.load()
+    vp = lambda a: a.ctypes.data_as(C.c_void_p)
+    rng = np.random.default_rng(3)
+    for trial in range(20):
+        n_ref, n_cur = int(rng.integers(0, 60)), int(rng.integers(0, 60))
+        ids = rng.permutation(100)
+        lr = np.where(rng.random(n_ref) < 0.2, -1, ids[:n_ref]).astype(np.int64)
+        lc = np.where(rng.random(n_cur) < 0.2, -1, rng.permutation(ids)[:n_cur]).astype(np.int64)
+        if n_ref > 3 and trial % 3 == 0:
+            lr[1] = lr[0]                                   # a duplicated id: the later position wins (std::map assignment)
+        exp = ofe.find_matching_keypoints(NS(landmarks=list(lr)), NS(landmarks=list(lc)))
+        mr, mc, nm = np.zeros(max(n_cur, 1), np.int32), np.zeros(max(n_cur, 1), np.int32), C.c_int()
+        assert lib.kvfe_find_matching_keypoints(vp(lr), n_ref, vp(lc), n_cur, vp(mr), vp(mc), C.byref(nm)) == 0
+        assert list(zip(mr[:nm.value], mc[:nm.value])) == exp
+        rs = rng.integers(0, 5, max(n_ref, 1)).astype(np.int32)
+        cs = rng.integers(0, 3, max(n_cur, 1)).astype(np.int32)
+        ref = NS(left_frame=NS(landmarks=list(lr)), right_keypoints_rectified=[(int(s), (0.0, 0.0)) for s in rs])
+        cur = NS(left_frame=NS(landmarks=list(lc)), right_keypoints_rectified=[(int(s), (0.0, 0.0)) for s in cs])
+        exps = ofe.find_matching_stereo_keypoints(ref, cur)
+        sr, sc, ns = np.zeros(max(nm.value, 1), np.int32), np.zeros(max(nm.value, 1), np.int32), C.c_int()
+        assert lib.kvfe_find_matching_stereo_keypoints(vp(rs), n_ref, vp(cs), n_cur, vp(mr), vp(mc), nm.value, vp(sr), vp(sc), C.byref(ns)) == 0
+        assert list(zip(sr[:ns.value], sc[:ns.value])) == exps
+    # the reference's fillSmartStereoMeasurements scenario
+    n = 36
+    lm = np.concatenate([np.arange(24), np.full(12, -1)]).astype(np.int64)
+    lx, ly = rng.integers(0, 800, n).astype(np.float32), rng.integers(0, 600, n).astype(np.float32)
+    rstat = np.concatenate([np.zeros(12), np.full(12, 2), np.zeros(12)]).astype(np.int32)      # VALID / NO_RIGHT_RECT / VALID
+    rx = (lx - 7.25).astype(np.float32)
+    for use_right in (1, 0):
+        ol, ouL, ouR, ov, no = np.zeros(n, np.int64), np.zeros(n), np.zeros(n), np.zeros(n), C.c_int()
+        assert lib.kvfe_smart_stereo_measurements(vp(lm), vp(lx), vp(ly), vp(rstat), vp(rx), n, use_right, vp(ol), vp(ouL), vp(ouR), vp(ov), C.byref(no)) == 0
+        assert no.value == 24 and list(ol[:24]) == list(range(24))
+        assert np.array_equal(ouL[:24], lx[:24].astype(np.float64)) and np.array_equal(ov[:24], ly[:24].astype(np.float64))
+        if use_right:
+            assert np.array_equal(ouR[:12], rx[:12].astype(np.float64)) and np.isnan(ouR[12:24]).all()
+        else:
+            assert np.isnan(ouR[:24]).all()
+    # and against the oracle's getSmartStereoMeasurements
+    fe = NS(p=NS(use_stereo_tracking=True))
+    sf = NS(left_frame=NS(landmarks=list(lm)), left_keypoints_rectified=[(0, (x, y)) for x, y in zip(lx, ly)],
+            right_keypoints_rectified=[(int(s), (x, 0.0)) for s, x in zip(rstat, rx)])
+    exp = ofe.StereoFrontend.get_smart_stereo_measurements(fe, sf)
+    ol, ouL, ouR, ov, no = np.zeros(n, np.int64), np.zeros(n), np.zeros(n), np.zeros(n), C.c_int()
+    lib.kvfe_smart_stereo_measurements(vp(lm), vp(lx), vp(ly), vp(rstat), vp(rx), n, 1, vp(ol), vp(ouL), vp(ouR), vp(ov), C.byref(no))
+    got = list(zip(ol[:no.value], ouL[:no.value], ouR[:no.value], ov[:no.value]))
+    assert len(got) == len(exp) and all(a[0] == b[0] and a[1] == b[1] and a[3] == b[3] and (a[2] == b[2] or (np.isnan(a[2]) and np.isnan(b[2]))) for a, b in zip(got, exp))
