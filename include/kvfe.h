@@ -285,6 +285,13 @@ int kvfe_smart_stereo_measurements(const int64_t* landmarks, const float* left_x
                                    const int32_t* right_status, const float* right_x, int n, int use_right,
                                    int64_t* out_landmarks, double* out_uL, double* out_uR, double* out_v, int* n_out);
 
+/* VisionImuFrontend::shouldBeKeyframe (src/frontend/VisionImuFrontend.cpp:175-232) for a front-end composed at the stage
+ * level (mono / RGB-D): thresholds from cfg, median_disparity from kvfe_compute_median_disparity over
+ * kvfe_find_matching_keypoints(lkf, frame) (0.0 without matches), mono_status = kfTrackingStatus_mono_ (KVFE_TRK_*),
+ * user_keyframe = Frame::isKeyframe_.  Host logic. */
+int kvfe_should_be_keyframe(const kvfe_config* cfg, int64_t timestamp_ns, int64_t lkf_timestamp_ns, int nr_valid_features,
+                            double median_disparity, int mono_status, int user_keyframe, int* is_keyframe);
+
 /* cv::equalizeHist as UtilsOpenCV::ReadAndConvertToGrayScale applies it (src/utils/UtilsOpenCV.cpp:390-403), one image. */
 int kvfe_equalize_hist(kvfe_ctx* ctx, const uint8_t* img, size_t pitch, uint8_t* out, size_t out_pitch);
 

@@ -1137,6 +1137,26 @@ extern "C" int kvfe_smart_stereo_measurements(const int64_t* landmarks, const fl
   return KVFE_OK;
 }
 
+// VisionImuFrontend::shouldBeKeyframe (VisionImuFrontend.cpp:175-232) from the quantities the caller holds: the two
+// timestamps, Frame::getNrValidKeypoints, the median disparity of computeMedianDisparity over findMatchingKeypoints(lkf,
+// frame) (0.0 when there is no match, Tracker.cpp:1004-1008), kfTrackingStatus_mono_ and Frame::isKeyframe_.  The
+// frame-level step takes the same decision on the device (fsm.cu: decide_kernel).
+extern "C" int kvfe_should_be_keyframe(const kvfe_config* cfg, int64_t timestamp_ns, int64_t lkf_timestamp_ns, int nr_valid_features,
+                                       double median_disparity, int mono_status, int user_keyframe, int* is_keyframe) {
+  if (!cfg || !is_keyframe) return KVFE_ERR_INVALID_ARG;
+  const int64_t kf_diff_ns = timestamp_ns - lkf_timestamp_ns;
+  const bool min_time_elapsed = kf_diff_ns >= cfg->min_intra_keyframe_time_ns;
+  const bool max_time_elapsed = kf_diff_ns >= cfg->max_intra_keyframe_time_ns;
+  const bool nr_features_low = nr_valid_features <= cfg->min_number_features;
+  const bool is_disparity_low = median_disparity < cfg->disparity_threshold;
+  const bool disparity_low_first_time = is_disparity_low && !(mono_status == KVFE_TRK_LOW_DISPARITY);
+  const bool enough_disparity = !is_disparity_low;
+  const bool max_disparity_reached = median_disparity > cfg->max_disparity_since_lkf;
+  const bool disparity_flipped = (enough_disparity || disparity_low_first_time) && min_time_elapsed;
+  *is_keyframe = (max_time_elapsed || max_disparity_reached || disparity_flipped || nr_features_low || user_keyframe) ? 1 : 0;
+  return KVFE_OK;
+}
+
 // Tracker::findOutliers (Tracker.cpp:836-853): the match indices that are not in the (sorted or unsorted) inlier list,
 // ascending.  Host logic: the reference's own implementation is a std::set_difference on the host.
 extern "C" int kvfe_find_outliers(int n_matches, const int32_t* inliers, int n_inliers, int32_t* outliers, int* n_outliers) {

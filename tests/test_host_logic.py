@@ -250,3 +250,39 @@ def test_find_matching_and_smart_measurements_host_logic():
     lib.kvfe_smart_stereo_measurements(vp(lm), vp(lx), vp(ly), vp(rstat), vp(rx), n, 1, vp(ol), vp(ouL), vp(ouR), vp(ov), C.byref(no))
     got = list(zip(ol[:no.value], ouL[:no.value], ouR[:no.value], ov[:no.value]))
     assert len(got) == len(exp) and all(a[0] == b[0] and a[1] == b[1] and a[3] == b[3] and (a[2] == b[2] or (np.isnan(a[2]) and np.isnan(b[2]))) for a, b in zip(got, exp))
+
+
+def test_should_be_keyframe_host_logic():
+    """kvfe_should_be_keyframe == VisionImuFrontend::shouldBeKeyframe (VisionImuFrontend.cpp:175-232), against the oracle's
+    method over the whole truth table of its conditions."""
+    import ctypes as C
+    import itertools
+    from types import SimpleNamespace as NS
+    from kimera_vio_b200 import lib as kl
+    from oracle import frontend as ofe
+    lib = kl.load()
+    lib.kvfe_should_be_keyframe.argtypes = [C.c_void_p, C.c_int64, C.c_int64, C.c_int, C.c_double, C.c_int, C.c_int, C.c_void_p]
+    p = FrontendParams.euroc()
+    cfg = kl.make_config(p, 752, 480, batch=1)
+    t0 = 1403715273262142976
+    n_true = 0
+    for dt, nvalid, disp, status, user in itertools.product(
+            (0, p.min_intra_keyframe_time_ns - 1, p.min_intra_keyframe_time_ns, p.max_intra_keyframe_time_ns - 1, p.max_intra_keyframe_time_ns),
+            (0, p.min_number_features, p.min_number_features + 1, 200),
+            (0.0, p.disparity_threshold - 1e-9, p.disparity_threshold, 50.0, p.max_disparity_since_lkf, p.max_disparity_since_lkf + 1e-6),
+            (ofe.VALID, ofe.LOW_DISPARITY, ofe.INVALID), (0, 1)):
+        # the oracle method reads disparity through its helpers: feed it one match with the wanted displacement
+        lkf = ofe.Frame(0, t0, None, None, False, [(np.float32(10.0), np.float32(10.0))], [7], [1], [0.0], [np.zeros(3)])
+        cur = ofe.Frame(1, t0 + dt, None, None, bool(user), [(np.float32(10.0 + disp), np.float32(10.0))], [7] + [], [1], [0.0], [np.zeros(3)])
+        cur.landmarks = [7] + list(range(100, 100 + max(nvalid - 1, 0)))
+        cur.keypoints = cur.keypoints + [(np.float32(0), np.float32(0))] * max(nvalid - 1, 0)
+        if nvalid == 0:
+            cur.landmarks, cur.keypoints = [-1], [(np.float32(0), np.float32(0))]
+        fe = NS(p=p, mono_status=status, _last_disparity=0.0)
+        want = ofe.StereoFrontend.should_be_keyframe(fe, cur, lkf)
+        d_eff = float(fe._last_disparity)                    # what computeMedianDisparity returned (float32 pixel arithmetic)
+        got = C.c_int(-1)
+        assert lib.kvfe_should_be_keyframe(C.byref(cfg), t0 + dt, t0, sum(1 for l in cur.landmarks if l != -1), d_eff, status, user, C.byref(got)) == 0
+        assert bool(got.value) == bool(want), (dt, nvalid, disp, status, user)
+        n_true += bool(want)
+    assert 50 < n_true < 700
