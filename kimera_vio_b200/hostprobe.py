@@ -6,7 +6,7 @@ body and, depending on the build and the CPU it dispatches to, a NON-fused scala
 columns of every row.  The response map therefore depends on the host the reference
 runs on; `sobel_cpu_tail_start` measures where that tail starts with the OpenCV the caller links, and
 the value goes into kvfe_config.sobel_cpu_tail_start (-1: no scalar tail).  The C++ shim does the same
-probe once at start-up (INTEGRATION.md section 5)."""
+probe once at start-up (INTEGRATION.md section 2b)."""
 from __future__ import annotations
 
 import numpy as np
