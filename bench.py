@@ -547,7 +547,7 @@ def run_gpu(args):
             "device_ms_e2e_events": r_e["ms_events"], "staged_copies": int(r_e["staged"]),
             "host_link": link, "latency_ms": latency,
             "clocks": r_v["clocks"], "clocks_e2e": r_e["clocks"],
-            "roofline": {"bound": "hbm", "kernel": "lk_kernel_col<24> (pyramidal LK: ~70% of the path's warp instructions)",
+            "roofline": {"bound": "hbm", "kernel": "lk_kernel_tma<24> (pyramidal LK, patch boxes staged by TMA: ~67% of the path's warp instructions)",
                          "achieved": achieved, "peak": peaks["hbm_gbs"], "unit": "GB/s", "frac": achieved / peaks["hbm_gbs"],
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": which + " (burst copy)",
                          "algorithmic_bytes_per_launch": lk_alg, "launch_ms": lk_ms,
