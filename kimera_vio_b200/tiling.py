@@ -199,3 +199,98 @@ def tiled_good_features_to_track(backend: BandBackend, plan: BandPlan, width: in
         dist.broadcast(buf, src=0)
         corners = buf[:int(n[0])].numpy().copy()
     return corners
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# the other axis: one stream's keypoints spread over the ranks (every rank holds the whole frame)
+# ------------------------------------------------------------------------------------------------------------------
+# Pyramidal LK (Tracker.cpp:92-211) and the sparse stereo reconstruction (StereoMatcher.cpp:123-483) treat every keypoint
+# on its own, so for a single large frame they shard over the keypoint list with no halo at all: a rank tracks / matches
+# its block of keypoints with the ordinary stage-level entry points (kvfe_track, kvfe_sparse_stereo work on any subset of
+# a frame's keypoints) and one all-gather puts the per-keypoint results back in order.  The frame itself has to be on
+# every rank (an 8 MB broadcast per 4K image over NVLink).  Host logic verified under gloo (tests/test_tiling_gloo.py);
+# KvfeStageBackend below wires it to libkvfe.so's verified stage calls but has never run at N > 1 on hardware.
+def keypoint_block(n: int, world: int, rank: int) -> Tuple[int, int]:
+    return band_rows(n, world, rank)
+
+
+def _all_gather_rows(local: np.ndarray, n_total: int) -> np.ndarray:
+    """Blocks of keypoint_block() order, float64 (n_i, k) -> (n_total, k) on every rank."""
+    if not dist.is_initialized() or dist.get_world_size() == 1:
+        return local
+    world = dist.get_world_size()
+    nmax = max(keypoint_block(n_total, world, r)[1] - keypoint_block(n_total, world, r)[0] for r in range(world))
+    pad = torch.zeros((max(nmax, 1), local.shape[1]), dtype=torch.float64)
+    pad[:local.shape[0]] = torch.from_numpy(np.ascontiguousarray(local, np.float64))
+    out = [torch.empty_like(pad) for _ in range(world)]
+    dist.all_gather(out, pad)
+    parts = []
+    for r, o in enumerate(out):
+        b, e = keypoint_block(n_total, world, r)
+        parts.append(o[:e - b].numpy())
+    return np.concatenate(parts) if parts else np.zeros((0, local.shape[1]))
+
+
+class TrackBackend(Protocol):
+    def track(self, ref_xy: np.ndarray) -> Tuple[np.ndarray, np.ndarray, np.ndarray]:
+        """(predicted xy, tracked xy, status u8) of the given reference keypoints (Tracker::featureTracking's LK call)."""
+
+    def sparse_stereo(self, kps_xy: np.ndarray, versors: np.ndarray) -> dict:
+        """per-keypoint arrays of StereoMatcher::sparseStereoReconstruction (left/right status, rectified xy, depth, 3-D)."""
+
+
+def sharded_track(backend: TrackBackend, ref_xy: np.ndarray):
+    """Every rank returns (predicted, tracked, status) for ALL keypoints; it computed only its block."""
+    xy = np.asarray(ref_xy, np.float32).reshape(-1, 2)
+    n = len(xy)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    b, e = keypoint_block(n, world, rank)
+    pred, trk, st = backend.track(xy[b:e])
+    # float32 coordinates travel as float64 (exact); one all-gather for the three results
+    loc = np.concatenate([np.asarray(pred, np.float64).reshape(-1, 2), np.asarray(trk, np.float64).reshape(-1, 2),
+                          np.asarray(st, np.float64).reshape(-1, 1)], 1)
+    full = _all_gather_rows(loc, n)
+    return full[:, 0:2].astype(np.float32), full[:, 2:4].astype(np.float32), full[:, 4].astype(np.uint8)
+
+
+STEREO_FIELDS = (("left_status", 1, np.int32), ("left_rect_x", 1, np.float32), ("left_rect_y", 1, np.float32),
+                 ("right_status", 1, np.int32), ("right_rect_x", 1, np.float32), ("right_rect_y", 1, np.float32),
+                 ("depth", 1, np.float64), ("points_3d", 3, np.float64), ("right_x", 1, np.float32), ("right_y", 1, np.float32))
+
+
+def sharded_sparse_stereo(backend: TrackBackend, kps_xy: np.ndarray, versors: np.ndarray) -> dict:
+    xy = np.asarray(kps_xy, np.float32).reshape(-1, 2)
+    vs = np.asarray(versors, np.float64).reshape(-1, 3)
+    n = len(xy)
+    world = dist.get_world_size() if dist.is_initialized() else 1
+    rank = dist.get_rank() if dist.is_initialized() else 0
+    b, e = keypoint_block(n, world, rank)
+    res = backend.sparse_stereo(xy[b:e], vs[b:e])
+    loc = np.concatenate([np.asarray(res[k], np.float64).reshape(e - b, w) for k, w, _ in STEREO_FIELDS], 1)
+    full = _all_gather_rows(loc, n)
+    out, c = {}, 0
+    for k, w, dt in STEREO_FIELDS:
+        a = full[:, c:c + w].astype(dt)
+        out[k] = a.reshape(-1) if w == 1 else a
+        c += w
+    return out
+
+
+class KvfeStageBackend:
+    """The per-rank compute through libkvfe.so: a context (kimera_vio_b200.lib.Context) on this rank's GPU holding the
+    whole frame's configuration; track() / sparse_stereo() are the stage-level calls on the rank's keypoint block."""
+
+    def __init__(self, ctx, ref_img=None, cur_img=None, ref_R_cur=None, left=None, right=None):
+        self.ctx, self.ref_img, self.cur_img, self.R, self.left, self.right = ctx, ref_img, cur_img, ref_R_cur, left, right
+
+    def track(self, ref_xy):
+        if len(ref_xy) == 0:
+            z = np.zeros((0, 2), np.float32)
+            return z, z, np.zeros(0, np.uint8)
+        return self.ctx.track(self.ref_img, self.cur_img, np.eye(3) if self.R is None else self.R, ref_xy)
+
+    def sparse_stereo(self, kps_xy, versors):
+        if len(kps_xy) == 0:
+            return {k: np.zeros((0, w) if w > 1 else 0, dt) for k, w, dt in STEREO_FIELDS}
+        return self.ctx.sparse_stereo(self.left, self.right, kps_xy, versors)

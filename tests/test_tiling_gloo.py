@@ -115,3 +115,97 @@ def test_band_plan_and_remap_halo():
         # rows whose taps stay inside the crop are identical; replicate-border rows at the frame edge as well
         same = (band == full[b:e]).mean()
         assert same > 0.999, (world, rank, same)
+
+
+# ---- the keypoint axis: LK and sparse stereo of one frame's keypoints spread over the ranks ----------------------------
+class CpuTrackBackend:
+    """cv2.calcOpticalFlowPyrLK with the reference's parameters (Tracker.cpp:137-146) and the oracle's sparse stereo
+    reconstruction on a block of keypoints."""
+
+    def __init__(self, p, rig, ref_img, cur_img, left, right):
+        from oracle import frontend as ofe
+        self.ofe, self.p, self.rig, self.ref_img, self.cur_img, self.left, self.right = ofe, p, rig, ref_img, cur_img, left, right
+
+    def track(self, ref_xy):
+        p = self.p
+        if len(ref_xy) == 0:
+            z = np.zeros((0, 2), np.float32)
+            return z, z, np.zeros(0, np.uint8)
+        a = np.asarray(ref_xy, np.float32).reshape(-1, 1, 2)
+        crit = (cv2.TERM_CRITERIA_COUNT + cv2.TERM_CRITERIA_EPS, p.klt_max_iter, p.klt_eps)
+        nxt, st, _ = cv2.calcOpticalFlowPyrLK(self.ref_img, self.cur_img, a, a.copy(), winSize=(p.klt_win_size, p.klt_win_size),
+                                              maxLevel=p.klt_max_level, criteria=crit, flags=cv2.OPTFLOW_USE_INITIAL_FLOW)
+        return a.reshape(-1, 2), nxt.reshape(-1, 2), st.reshape(-1)
+
+    def sparse_stereo(self, kps_xy, versors):
+        ofe = self.ofe
+        n = len(kps_xy)
+        if n == 0:
+            return {k: np.zeros((0, w) if w > 1 else 0, dt) for k, w, dt in kt.STEREO_FIELDS}
+        sf = ofe.StereoFrame.make(0, 0, self.left, self.right, self.rig)
+        sf.left_frame.keypoints = [(np.float32(x), np.float32(y)) for x, y in kps_xy]
+        sf.left_frame.versors = [np.asarray(v, np.float64) for v in versors]
+        sf.left_frame.landmarks = list(range(n))
+        ofe.StereoMatcher(self.p, self.rig).sparse_stereo_reconstruction(sf)
+        lr, rr = sf.left_keypoints_rectified, sf.right_keypoints_rectified
+        rk = np.array(sf.right_frame.keypoints, np.float32).reshape(-1, 2)
+        return dict(left_status=np.array([s for s, _ in lr], np.int32), left_rect_x=np.array([q[0] for _, q in lr], np.float32),
+                    left_rect_y=np.array([q[1] for _, q in lr], np.float32), right_status=np.array([s for s, _ in rr], np.int32),
+                    right_rect_x=np.array([q[0] for _, q in rr], np.float32), right_rect_y=np.array([q[1] for _, q in rr], np.float32),
+                    depth=np.array(sf.keypoints_depth, np.float64), points_3d=np.array(sf.keypoints_3d, np.float64).reshape(-1, 3),
+                    right_x=rk[:, 0].copy(), right_y=rk[:, 1].copy())
+
+
+def _kp_setup():
+    from kimera_vio_b200.params import CameraParams, FrontendParams
+    from oracle import frontend as ofe
+    from oracle.rig import StereoRig
+    p = FrontendParams.euroc()
+    rig = StereoRig(CameraParams.euroc_left(), CameraParams.euroc_right())
+    g, lefts, rights = H.golden()
+    kps = cv2.goodFeaturesToTrack(lefts[0], 301, 0.001, 12).reshape(-1, 2).astype(np.float32)      # 301: uneven blocks
+    versors = np.array(ofe.get_bearing_vectors([tuple(q) for q in kps], rig.left, rig.R1))
+    return p, rig, lefts, rights, kps, versors
+
+
+def _kp_worker(rank, world, port, q):
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    p, rig, lefts, rights, kps, versors = _kp_setup()
+    be = CpuTrackBackend(p, rig, lefts[0], lefts[1], lefts[0], rights[0])
+    trk = kt.sharded_track(be, kps)
+    ss = kt.sharded_sparse_stereo(be, kps, versors)
+    empty = kt.sharded_track(be, np.zeros((0, 2), np.float32))
+    few = kt.sharded_track(be, kps[:2])                     # fewer keypoints than ranks: some blocks are empty
+    q.put((rank, trk, ss, len(empty[0]), few))
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_keypoint_sharded_lk_and_stereo_equal_single_rank(world):
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31300 + (os.getpid() % 1500) + world
+    procs = [ctx.Process(target=_kp_worker, args=(r, world, port, q)) for r in range(world)]
+    for pr in procs:
+        pr.start()
+    res = {}
+    for _ in range(world):
+        rank, trk, ss, n_empty, few = q.get(timeout=300)
+        res[rank] = (trk, ss, n_empty, few)
+    for pr in procs:
+        pr.join(timeout=60)
+        assert pr.exitcode == 0
+    p, rig, lefts, rights, kps, versors = _kp_setup()
+    be = CpuTrackBackend(p, rig, lefts[0], lefts[1], lefts[0], rights[0])
+    w_pred, w_trk, w_st = be.track(kps)
+    w_ss = be.sparse_stereo(kps, versors)
+    w_few = be.track(kps[:2])
+    assert w_st.sum() > 200 and (w_ss["right_status"] == 0).sum() > 150
+    for r in range(world):
+        (pred, trk, st), ss, n_empty, few = res[r]
+        assert np.array_equal(pred, w_pred) and np.array_equal(trk, w_trk) and np.array_equal(st, w_st)
+        for k, _, _ in kt.STEREO_FIELDS:
+            assert np.array_equal(ss[k], w_ss[k]), k
+        assert n_empty == 0
+        assert np.array_equal(few[1], w_few[1]) and np.array_equal(few[2], w_few[2])
