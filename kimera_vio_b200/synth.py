@@ -111,7 +111,7 @@ class SynthStream:
         t = m * np.array([0.02 * 12 * np.sin(0.05 * k), 0.01 * 8 * np.sin(0.031 * k + 0.5), 0.015 * 6 * np.sin(0.043 * k)])
         return R, t
 
-    def _render(self, grid: np.ndarray, R: np.ndarray, t: np.ndarray, rng: np.random.Generator) -> np.ndarray:
+    def _render(self, grid: np.ndarray, R: np.ndarray, t: np.ndarray, rng: np.random.Generator, depth_out=None) -> np.ndarray:
         H, W = grid.shape[:2]
         d = np.concatenate([grid, np.ones((H, W, 1))], -1) @ R.T      # ray directions in world
         img = np.zeros((H, W), np.float32)
@@ -131,6 +131,8 @@ class SynthStream:
             val = (tex[iv, iu] * (1 - fu) * (1 - fv) + tex[iv, iu1] * fu * (1 - fv) +
                    tex[iv1, iu] * (1 - fu) * fv + tex[iv1, iu1] * fu * fv)
             img = np.where(ok, val, img)
+            if depth_out is not None:            # the ray is (x, y, 1) * lam in the camera frame: lam is the z-depth
+                depth_out[ok] = lam[ok]
             done |= ok
         img = img + rng.normal(0.0, 1.5, img.shape).astype(np.float32)
         return np.clip(np.rint(img), 0, 255).astype(np.uint8)
@@ -143,6 +145,15 @@ class SynthStream:
         tr = t + R @ self.camL_T_camR[:3, 3]
         right = self._render(self.grid_r, Rr, tr, rng)
         return SynthFrame(left, right, self.t0 + k * self.dt_ns, R)
+
+    def frame_with_depth(self, k: int):
+        """frame(k) plus the registered metric depth image of the LEFT camera (float32, 0 where no plane is hit): the input
+        of the RGB-D front-end (RgbdFrame: intensity + depth, src/frontend/RgbdFrame.cpp)."""
+        rng = np.random.default_rng(self.seed * 1000003 + k)
+        R, t = self.pose(k)
+        depth = np.zeros(self.grid_l.shape[:2], np.float32)
+        left = self._render(self.grid_l, R, t, rng, depth)
+        return SynthFrame(left, left, self.t0 + k * self.dt_ns, R), depth
 
     def kf_rotation(self, k_lkf: int, k: int) -> np.ndarray:
         """camLrectLkf_R_camLrectK = R1 * (camL_lkf^T camL_k) * R1^T (what the IMU front-end provides)."""

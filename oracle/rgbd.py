@@ -96,3 +96,148 @@ def fill_stereo_frame(depth_img: np.ndarray, cam, keypoints, left_rect, versors,
             else:
                 right_kps.append((f32(0.0), f32(0.0)))
     return right, depths, p3d, right_kps
+
+
+# ----------------------------------------------------------------------------------------------------------------
+# RgbdVisionImuFrontend (src/frontend/RgbdVisionImuFrontend.cpp:183-395) -- the caller of the two functions above, restated
+# so that whole RGB-D sequences have an oracle (the frame-level RGB-D step of kvfe is not built yet; this is its checker).
+# PnP (use_pnp_tracking, Tracker.cpp:1064-1288) is left out: it needs the back-end's landmark map.
+# ----------------------------------------------------------------------------------------------------------------
+class RgbdCamera:
+    """RgbdCamera (RgbdCamera.cpp:79-101) = Camera (P = K, R = I, Camera.cpp:29-47) + the fake stereo calibration
+    Cal3_S2Stereo(K, virtual_baseline) at the identity pose."""
+
+    def __init__(self, cam):
+        from .mono import MonoCamera
+        m = MonoCamera(cam)
+        self.left = self.right = cam
+        self.W, self.H, self.R1, self.P1 = m.W, m.H, m.R1, m.P1
+        self.map_lx, self.map_ly = m.map_lx, m.map_ly
+        self.fx, self.fy, self.cx, self.cy = (float(v) for v in cam.intrinsics)
+        self.baseline = float(f32(cam.depth["virtual_baseline"]))
+        self._mono = m
+
+    def undistort_keypoints(self, kps):
+        return self._mono.undistort_keypoints(kps)
+
+
+class _DepthMaskedDetector(ofe.FeatureDetector):
+    """FeatureDetector::featureDetection with Frame::detection_mask_ set (FeatureDetector.cpp:185-203): the circles around
+    the tracked keypoints are drawn into the caller's mask."""
+    detection_mask = None
+
+    def build_mask(self, frame):
+        mask = self.detection_mask.copy()
+        for kp, lmk in zip(frame.keypoints, frame.landmarks):
+            if lmk != -1:
+                c = (int(np.rint(f32(kp[0]))), int(np.rint(f32(kp[1]))))
+                cv2.circle(mask, c, self.p.min_distance, 0, cv2.FILLED)
+        return mask
+
+
+class RgbdFrontend:
+    def __init__(self, p, cam, rnd_libstdcxx: str = "lemire"):
+        import numpy as _np
+        from . import ransac as rs
+        self._rs = rs
+        self.p, self.cam_params, self.cam = p, cam, RgbdCamera(cam)
+        self.detector = _DepthMaskedDetector(p)
+        self.tracker = ofe.Tracker(p, self.cam, rnd_libstdcxx)
+        self.frame_count = self.keyframe_count = 0
+        self.km1 = self.lkf = None
+        self.keyframe_R_ref = _np.eye(3)
+        self.mono_status = self.stereo_status = ofe.INVALID
+        self.lkf_T_k_mono = _np.hstack([_np.eye(3), _np.zeros((3, 1))])
+        self.lkf_T_k_stereo = self.lkf_T_k_mono.copy()
+        self._last_disparity = 0.0
+
+    should_be_keyframe = ofe.StereoFrontend.should_be_keyframe
+
+    def _stereo_frame(self, k, ts, img):
+        return ofe.StereoFrame.make(k, ts, img, np.zeros((0, 0), np.uint8), self.cam)      # getStereoFrame: empty right image
+
+    def _fill(self, sf, depth):
+        """camera_->undistortKeypoints (when new keypoints exist) + RgbdFrame::fillStereoFrame."""
+        lf = sf.left_frame
+        if len(lf.keypoints) > len(sf.left_keypoints_rectified):
+            sf.left_keypoints_rectified = self.cam.undistort_keypoints(lf.keypoints)
+        r, d, p3, rk = fill_stereo_frame(depth, self.cam_params, lf.keypoints, sf.left_keypoints_rectified, lf.versors,
+                                         self.cam.map_lx, self.cam.map_ly)
+        sf.right_keypoints_rectified, sf.keypoints_depth, sf.keypoints_3d = r, d, p3
+        sf.right_frame.keypoints = rk
+
+    def _detect(self, sf, depth):
+        self.detector.detection_mask = get_detection_mask(depth, self.cam_params.depth)
+        self.detector.feature_detection(sf.left_frame, None)
+        sf.left_keypoints_rectified = self.cam.undistort_keypoints(sf.left_frame.keypoints)
+
+    def _track(self, ref, cur, ref_R_cur):
+        R1 = self.tracker.rig.R1
+        self.tracker.rig.R1 = None                    # featureTracking without R: versors in the camera frame
+        try:
+            self.tracker.feature_tracking(ref, cur, ref_R_cur)
+        finally:
+            self.tracker.rig.R1 = R1
+
+    def smart_measurements(self, sf):
+        """RgbdVisionImuFrontend::fillSmartStereoMeasurements (:368-395)."""
+        out = []
+        for i, l in enumerate(sf.left_frame.landmarks):
+            if l == -1:
+                continue
+            uL, v = float(sf.left_keypoints_rectified[i][1][0]), float(sf.left_keypoints_rectified[i][1][1])
+            st, (rx, _) = sf.right_keypoints_rectified[i]
+            out.append((l, uL, float(rx) if st == ofe.KP_VALID else float("nan"), v))
+        return out
+
+    def spin(self, k: int, timestamp: int, img: np.ndarray, depth: np.ndarray, keyframe_R_cur: np.ndarray):
+        """Returns (stereo frame, is_keyframe, smart measurements)."""
+        rs, p = self._rs, self.p
+        sf = self._stereo_frame(k, timestamp, img)
+        if self.frame_count == 0:                                            # processFirstFrame :183-209
+            sf.is_keyframe = sf.left_frame.is_keyframe = True
+            self._detect(sf, depth)
+            self._fill(sf, depth)
+            self.km1 = self.lkf = sf
+            self.frame_count += 1
+            return sf, True, []
+        R = np.asarray(keyframe_R_cur, np.float64)
+        ref_R_cur = rs.matmul3(self.keyframe_R_ref.T.copy(), R)
+        self._track(self.km1.left_frame, sf.left_frame, ref_R_cur)           # processFrame :236-292
+        sf.left_keypoints_rectified = self.cam.undistort_keypoints(sf.left_frame.keypoints)
+        self.mono_status = self.stereo_status = ofe.INVALID
+        smart = []
+        if self.should_be_keyframe(sf.left_frame, self.lkf.left_frame):
+            if p.use_ransac:                                                 # handleKeyframe :313-366
+                given_rot = not ofe.rot_equals_identity(R)
+                st, pose, _ = self.tracker.outlier_rejection_2d2d(self.lkf.left_frame, sf.left_frame,
+                                                                  R if (p.ransac_use_2point_mono and given_rot) else None)
+                self.mono_status = st
+                if st == ofe.VALID:
+                    self.lkf_T_k_mono = pose
+                self._fill(sf, depth)
+                if p.use_stereo_tracking:
+                    if p.ransac_use_1point_stereo and given_rot:
+                        st, pose, _, _ = self.tracker.outlier_rejection_3d3d_given_rotation(self.lkf, sf, R)
+                    else:
+                        st, pose, _, _ = self.tracker.outlier_rejection_3d3d(self.lkf, sf)
+                    self.stereo_status = st
+                    if st == ofe.VALID:
+                        self.lkf_T_k_stereo = pose
+                else:
+                    self.stereo_status = ofe.INVALID
+            else:
+                self.mono_status = self.stereo_status = ofe.DISABLED
+            self._detect(sf, depth)
+            self._fill(sf, depth)
+            sf.is_keyframe = sf.left_frame.is_keyframe = True
+            smart = self.smart_measurements(sf)
+            self.lkf = sf
+            self.keyframe_R_ref = np.eye(3)
+            self.keyframe_count += 1
+        else:
+            sf.is_keyframe = False
+            self.keyframe_R_ref = R
+        self.km1 = sf
+        self.frame_count += 1
+        return sf, sf.is_keyframe, smart

@@ -89,3 +89,58 @@ def test_depth_params_and_rgbd_rig_marshalling():
     assert c.baseline == float(f32(0.3)) and np.array_equal(np.array(c.P1).reshape(3, 4)[:, :3], cam.K) and c.distortion_model == 0
     with pytest.raises(ValueError):
         RgbdRigSetup(CameraParams.euroc_left())
+
+
+def test_rgbd_frontend_oracle_on_synthetic_sequence():
+    """oracle/rgbd.py: RgbdFrontend (RgbdVisionImuFrontend.cpp:183-395) over a synthetic RGB-D stream (the stereo test scene
+    seen by one camera, with its metric depth image): the properties the reference's flow guarantees -- first frame is a
+    keyframe with detections only where the depth mask allows, keyframes follow the time rule, the hallucinated right
+    keypoints satisfy uR = uL - fx b / depth with the depth of the truncated raw pixel, 3-D points lie on the rendered
+    planes, both RANSAC stages accept the rigid scene, smart measurements carry uR (fillSmartStereoMeasurements)."""
+    import dataclasses
+    from kimera_vio_b200.params import FrontendParams
+    from kimera_vio_b200.rig import StereoRigSetup
+    from kimera_vio_b200.synth import SynthStream
+    p = FrontendParams.euroc()
+    left, right = CameraParams.euroc_left(), CameraParams.euroc_right()
+    cam = dataclasses.replace(left, depth={"virtual_baseline": float(f32(0.1)), "depth_to_meters": 1.0, "min_depth": 0.3,
+                                           "max_depth": 4.0, "is_registered": True})
+    s = SynthStream(left, right, np.eye(3), seed=99)
+    fe = org.RgbdFrontend(p, cam)
+    lkf, n_kf, statuses = 0, 0, []
+    for k in range(13):
+        f, depth = s.frame_with_depth(k)
+        assert depth.shape == f.left.shape and 1.0 < depth[depth > 0].min() and depth.max() < 7.0
+        R = s.kf_rotation(lkf, k)
+        sf, is_kf, smart = fe.spin(k, f.timestamp, f.left, depth, R)
+        lf = sf.left_frame
+        assert len(lf.keypoints) == len(lf.landmarks) == len(lf.versors) == len(sf.left_keypoints_rectified)
+        if is_kf:
+            n_kf += 1
+            lkf = k
+            assert len(sf.right_keypoints_rectified) == len(lf.keypoints) == len(sf.keypoints_3d)
+            fx_b = cam.intrinsics[0] * float(f32(0.1))
+            n_valid = 0
+            for i, (st, (rx, ry)) in enumerate(sf.right_keypoints_rectified):
+                lst, (lx, ly) = sf.left_keypoints_rectified[i]
+                if st != ofe.KP_VALID:
+                    continue
+                n_valid += 1
+                d = float(depth[int(lf.keypoints[i][1]), int(lf.keypoints[i][0])])
+                assert lst == ofe.KP_VALID and d >= 0.3 and sf.keypoints_depth[i] == d
+                assert abs(float(rx) - (float(lx) - fx_b / d)) < 1e-4 and ry == ly
+                assert abs(sf.keypoints_3d[i][2] - d) < 1e-9                       # versor * depth / versor.z
+            assert n_valid > 150
+            # detections respect the depth mask (max_depth 4 m cuts the far plane at 6 m) up to the sub-pixel refinement
+            new = [kp for kp, age in zip(lf.keypoints, lf.landmarks_age) if age == 1]
+            far = sum(1 for (x, y) in new if depth[int(y), int(x)] > 4.5)
+            assert far <= len(new) * 0.05
+            if k > 0:
+                statuses.append((fe.mono_status, fe.stereo_status))
+                assert len(smart) == sum(1 for l in lf.landmarks if l != -1)
+                with_uR = sum(1 for m in smart if not math.isnan(m[2]))
+                assert with_uR > 100
+        else:
+            assert smart == []
+    assert n_kf >= 4
+    assert all(m == ofe.VALID and st == ofe.VALID for m, st in statuses), statuses
