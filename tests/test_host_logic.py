@@ -286,3 +286,20 @@ def test_should_be_keyframe_host_logic():
         assert bool(got.value) == bool(want), (dt, nvalid, disp, status, user)
         n_true += bool(want)
     assert 50 < n_true < 700
+
+
+@needs_reference
+def test_camera_yaml_distortion_models_and_depth_blocks():
+    """CameraParams.from_yaml on the shipped camera files: distortion model names (CameraParams.cpp:114-140) and the RGB-D
+    block (CameraParams.cpp:342-349)."""
+    seen = {}
+    for rig in ("Euroc", "uHumans2", "D455", "RealSenseIR", "KinectAzure", "EurocMono"):
+        path = os.path.join(REF, "params", rig, "LeftCameraParams.yaml")
+        if not os.path.exists(path):
+            continue
+        c = CameraParams.from_yaml(path)
+        seen[rig] = (c.distortion_model, c.depth)
+        assert c.distortion_model in ("radtan", "equidistant") and len(c.distortion) >= 4
+    assert seen["RealSenseIR"][0] == "equidistant" and seen["Euroc"][0] == "radtan" and seen["Euroc"][1] is None
+    d = seen["KinectAzure"][1]
+    assert d and d["is_registered"] and abs(d["virtual_baseline"] - 0.3) < 1e-6 and d["max_depth"] == 10.0
